@@ -1,0 +1,208 @@
+/* ipoc.h — C ABI of the B200-native (sm_100a, FP64) scans behind the parallel-in-time
+ * interior-point Newton step of casiacob/ip-parallel-optimal-control.
+ *
+ * This is the drop-in boundary.  The reference has NO native interface for this path: it is
+ * pure Python/JAX (`jax.lax.associative_scan` + `vmap`), so each entry point below cites the
+ * reference *Python* interface it replaces; INTEGRATION.md shows the `jax.ffi` / ctypes
+ * bindings a maintainer of the reference would add on top of these symbols.
+ *
+ * Conventions
+ *   - All tensors are float64, row-major, contiguous, 16-byte aligned, in DEVICE memory
+ *     (the *_host_* wrappers at the end take HOST memory and copy inside).
+ *   - `batch` independent problems are stacked on a leading axis (batch = 1 for a single OCP);
+ *     time is the next axis.  Shapes are given per problem.
+ *   - Every call only ENQUEUES work on `stream` (no allocation, no implicit synchronisation,
+ *     no host reads) and is therefore CUDA-graph capturable.  The caller owns all buffers
+ *     including the workspace (`ipoc_workspace_bytes`).  The library keeps no mutable state
+ *     apart from the optional tuning knobs below.
+ *   - Return value: 0 on success, a negative IPOC_E* code otherwise.  Numerical failure (NaN,
+ *     non-positive-definite G) is DATA (`feasible = 0`), never an error — it is an ordinary
+ *     branch of the algorithm (ref noc/par_interior_point_newton.py:166).
+ *   - There is no CPU fallback: unsupported (nx, nu) -> IPOC_EUNSUPPORTED_DIM.
+ *     Supported: nx in {1..8} as instantiated (see ipoc_supported), nu in {1, 2}.
+ */
+#ifndef IPOC_H
+#define IPOC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ipoc_stream_t; /* cudaStream_t */
+
+enum {
+    IPOC_OK = 0,
+    IPOC_EUNSUPPORTED_DIM = -1,
+    IPOC_EWORKSPACE = -2,
+    IPOC_ECUDA = -3,
+    IPOC_ENCCL = -4,
+    IPOC_EINVAL = -5,
+    IPOC_EALIGN = -6
+};
+
+enum { /* `kind` of ipoc_workspace_bytes */
+    IPOC_WS_NEWTON_STEP = 0,
+    IPOC_WS_LQT_BWD = 1,
+    IPOC_WS_LQT_FWD = 2,
+    IPOC_WS_AFFINE_SCAN = 3,
+    IPOC_WS_REDUCTIONS = 4
+};
+
+const char* ipoc_strerror(int code);
+int ipoc_version(void);
+/* 1 if kernels for (nx, nu) are compiled in, else 0. */
+int ipoc_supported(int nx, int nu);
+size_t ipoc_workspace_bytes(int kind, int N, int nx, int nu, int batch);
+
+/* Optional tuning knobs (0 = keep default): leaf chunk length (steps folded per thread),
+ * mid-level fan-in, maximum number of aggregates handled by the single-CTA top scan. */
+void ipoc_set_tuning(int leaf_chunk, int mid_fanin, int top_max);
+
+/* ---- K2 + K3: one Newton step ----------------------------------------------------------
+ * Replaces `par_Newton` (ref noc/par_interior_point_newton.py:107-124) from the regularisation
+ * add onwards: R + reg*I (:118), `noc_to_lqt` (:50-84, r/s by two small solves per step,
+ * XT = Q[0], H = Z = I, c = 0), `paroc.par_bwd_pass` (:120: reverse associative scan over
+ * (A, b, C, eta, J), gains, pred_reduction, feasibility) and `paroc.par_fwd_pass` with zero
+ * initial deviation (:121-123).
+ *   in : fx (N,nx,nx) fu (N,nx,nu) ru (N,nu) Q (N,nx,nx) R (N,nu,nu) M (N,nx,nu)
+ *        reg (batch) device scalars = reg_param * ||cu||_F (:116-117)
+ *   out: dx (N+1,nx) du (N,nu) Kx (N,nu,nx) d (N,nu) pred (batch) feasible (batch, int32)
+ */
+int ipoc_newton_step_f64(int N, int nx, int nu, int batch,
+                         const double* fx, const double* fu, const double* ru,
+                         const double* Q, const double* R, const double* M,
+                         const double* reg,
+                         double* dx, double* du, double* Kx, double* d,
+                         double* pred, int32_t* feasible,
+                         void* ws, size_t ws_bytes, ipoc_stream_t stream);
+
+/* ---- K2 alone: raw `paroc.par_bwd_pass(lqt)` --------------------------------------------
+ * (call sites ref noc/par_interior_point_newton.py:120, examples/linear_mpc_parallel.py:68)
+ * for an LQT problem already reduced to effective terms (H, Z folded in by the caller):
+ *   x+ = A x + B u + c,  stage cost 1/2 x'Xx + 1/2 u'Uu + x'Mu + q'x + p'u,
+ *   terminal value S_N = ST, v_N = vT   (V(x) = 1/2 x'Sx - v'x).
+ *   in : A (N,nx,nx) B (N,nx,nu) c (N,nx) X (N,nx,nx) U (N,nu,nu) M (N,nx,nu) q (N,nx) p (N,nu)
+ *        ST (nx,nx) vT (nx)  per problem
+ *   out: Kx (N,nu,nx) d (N,nu) [S (N+1,nx,nx) v (N+1,nx) — may be NULL] pred, feasible
+ */
+int ipoc_lqt_bwd_f64(int N, int nx, int nu, int batch,
+                     const double* A, const double* B, const double* c,
+                     const double* X, const double* U, const double* M,
+                     const double* q, const double* p,
+                     const double* ST, const double* vT,
+                     double* Kx, double* d, double* S, double* v,
+                     double* pred, int32_t* feasible,
+                     void* ws, size_t ws_bytes, ipoc_stream_t stream);
+
+/* ---- K3 alone: raw `paroc.par_fwd_pass(lqt, x0, Kx, d)` ---------------------------------
+ * (call sites ref noc/par_interior_point_newton.py:121-123, examples/linear_mpc_parallel.py:69)
+ *   in : A, B, c (c may be NULL = 0), Kx (N,nu,nx), d (N,nu), x0 (nx) per problem
+ *   out: u (N,nu), x (N+1,nx)          [u_k = -Kx_k x_k + d_k]
+ */
+int ipoc_lqt_fwd_f64(int N, int nx, int nu, int batch,
+                     const double* A, const double* B, const double* c,
+                     const double* Kx, const double* d, const double* x0,
+                     double* u, double* x,
+                     void* ws, size_t ws_bytes, ipoc_stream_t stream);
+
+/* ---- K1: affine-map scan -----------------------------------------------------------------
+ * Replaces `par_costates` / `par_scan` / `combine_fc` (ref noc/costates.py:6-40).
+ *   reverse = 0: out[0] = seed,  out[k+1] = F_k    out[k]   + c_k
+ *   reverse = 1: out[N] = seed,  out[k]   = F_k(') out[k+1] + c_k    (transpose = 1 uses F_k')
+ * Costates: reverse = 1, transpose = 1, F = fx, c = cx, seed = grad final_cost(x_N).
+ *   in : F (N,nx,nx) c (N,nx) seed (nx) per problem;   out: (N+1,nx)
+ */
+int ipoc_affine_scan_f64(int reverse, int transpose, int N, int nx, int batch,
+                         const double* F, const double* c, const double* seed, double* out,
+                         void* ws, size_t ws_bytes, ipoc_stream_t stream);
+
+/* ---- K4: reductions of the accept/reject test ---------------------------------------------
+ * (ref noc/par_interior_point_newton.py:45-47 `all(cons <= 0)`, :116 `norm(d.cu)`, :158
+ * `max|ru|`).  Any input pointer may be NULL (its output is then left untouched).
+ *   in : ru (N,nu) cu (N,nu) cons (N,nc);  out per problem: hu_norm, cu_norm, traj_feasible
+ * Fixed reduction order -> bit-reproducible run to run.
+ */
+int ipoc_reductions_f64(int N, int nu, int nc, int batch,
+                        const double* ru, const double* cu, const double* cons,
+                        double* hu_norm, double* cu_norm, int32_t* traj_feasible,
+                        void* ws, size_t ws_bytes, ipoc_stream_t stream);
+
+/* ---- A8: scalar accept / regularisation update, on device --------------------------------
+ * (ref noc/par_interior_point_newton.py:159-173) for `batch` independent problems:
+ *   new_cost = traj_feasible ? new_cost : inf;  rho = (new_cost - cost) / pred;
+ *   success = rho > 0 && bwd_feasible;
+ *   rp <- clip(success ? rp*max(1/3, 1-(2 rho-1)^3) : rp*r_inc, 1e-16, 1e16);
+ *   r_inc <- success ? 2 : 2*r_inc
+ * `active` (may be NULL) masks problems that must be left untouched.
+ */
+int ipoc_accept_update_f64(int batch, const double* cost, const double* new_cost,
+                           const int32_t* traj_feasible, const double* pred,
+                           const int32_t* bwd_feasible, const int32_t* active,
+                           double* rp, double* r_inc, int32_t* success, double* gain_ratio,
+                           ipoc_stream_t stream);
+
+/* ---- time-sharded (multi-GPU) split-phase variants -----------------------------------------
+ * A horizon of P*N steps is cut into P contiguous segments, one per rank (no reference
+ * counterpart — the reference is single-device).  Each scan is: local reduce -> exchange of
+ * the P segment aggregates (caller: NCCL all-gather) -> local seeded scan.
+ * Carry sizes in doubles: ipoc_carry_doubles(kind, nx).
+ */
+enum { IPOC_CARRY_RICCATI = 0, IPOC_CARRY_AFFINE = 1 };
+int ipoc_carry_doubles(int kind, int nx);
+
+/* Phase 1 of K2 on this rank's segment: writes the segment aggregate (A,b,C,eta,J packed) to
+ * `carry_out`.  Newton-step inputs as in ipoc_newton_step_f64 (batch = 1). */
+int ipoc_newton_bwd_reduce_f64(int N, int nx, int nu,
+                               const double* fx, const double* fu, const double* ru,
+                               const double* Q, const double* R, const double* M,
+                               const double* reg, double* carry_out,
+                               void* ws, size_t ws_bytes, ipoc_stream_t stream);
+/* Phase 2 of K2: `carries` = the gathered aggregates of all `nranks` segments (rank-major);
+ * `ST` (nx,nx) = terminal weight of the WHOLE horizon (Q[0] of rank 0's segment in the
+ * reference's convention).  Produces this segment's Kx, d, partial pred / feasible, and the
+ * forward-scan aggregate of the segment in `fwd_carry_out`. */
+int ipoc_newton_bwd_apply_f64(int N, int nx, int nu, int rank, int nranks,
+                              const double* fx, const double* fu, const double* ru,
+                              const double* Q, const double* R, const double* M,
+                              const double* reg, const double* carries, const double* ST,
+                              double* Kx, double* d, double* pred, int32_t* feasible,
+                              double* fwd_carry_out,
+                              void* ws, size_t ws_bytes, ipoc_stream_t stream);
+/* K3 on this rank's segment given the gathered forward aggregates; rank 0 starts from dx = 0.
+ * dx has N+1 rows (row N duplicates the next rank's row 0). */
+int ipoc_newton_fwd_apply_f64(int N, int nx, int nu, int rank, int nranks,
+                              const double* fx, const double* fu,
+                              const double* Kx, const double* d, const double* fwd_carries,
+                              double* dx, double* du,
+                              void* ws, size_t ws_bytes, ipoc_stream_t stream);
+/* K1, time-sharded: reduce and apply phases of the reverse/transposed affine scan. */
+int ipoc_affine_reduce_f64(int reverse, int transpose, int N, int nx,
+                           const double* F, const double* c, double* carry_out,
+                           void* ws, size_t ws_bytes, ipoc_stream_t stream);
+int ipoc_affine_apply_f64(int reverse, int transpose, int N, int nx, int rank, int nranks,
+                          const double* F, const double* c, const double* carries,
+                          const double* seed, double* out,
+                          void* ws, size_t ws_bytes, ipoc_stream_t stream);
+
+/* ---- host-buffer convenience wrapper (end-to-end timing, simple embedding) -----------------
+ * Same as ipoc_newton_step_f64 but every pointer is HOST memory (pinned for best speed);
+ * `dws` is a DEVICE scratch buffer of at least ipoc_newton_step_host_scratch_bytes().  Copies
+ * H2D, runs, copies D2H, all on `stream`; the caller synchronises the stream. */
+size_t ipoc_newton_step_host_scratch_bytes(int N, int nx, int nu, int batch);
+int ipoc_newton_step_host_f64(int N, int nx, int nu, int batch,
+                              const double* fx, const double* fu, const double* ru,
+                              const double* Q, const double* R, const double* M,
+                              const double* reg,
+                              double* dx, double* du, double* pred, int32_t* feasible,
+                              void* dws, size_t dws_bytes, ipoc_stream_t stream);
+
+/* Number of kernels the library has launched since load (for launch accounting in bench.py). */
+unsigned long long ipoc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPOC_H */

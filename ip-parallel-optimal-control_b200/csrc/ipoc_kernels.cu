@@ -1,0 +1,1413 @@
+// Hand-written sm_100a FP64 kernels + C ABI for the par IP-Newton hot path.
+//
+// Scan organisation (all three scans: K1 costates, K2 Riccati, K3 forward):
+//   a hierarchical reduce / seeded-rescan.  A leaf thread folds `T0` consecutive time steps
+//   sequentially (work-optimal, no idle lanes), mid levels fold `Tm` aggregates per thread, a
+//   single CTA per sequence scans the few hundred top-level aggregates (warp-shuffle
+//   Kogge-Stone + shared-memory warp carries), and the way down only propagates VALUES
+//   ((S, v) for K2, a state vector for K1/K3), which is roughly half the cost of combining
+//   full elements.  Aggregates live in SoA planes (component-major) so that neighbouring
+//   threads touch neighbouring addresses.  No spin-waiting between CTAs anywhere, so every call
+//   is graph-capturable and cannot hang.
+//   With enough independent problems (`batch`) the plan degenerates to one chunk per problem:
+//   a single pass, no up-sweep at all.
+//
+// K2's down-sweep emits K3's leaf aggregates for free (same chunks), so one Newton step reads
+// fx, fu, Q, R, M, ru twice (the second time from L2 when the working set fits) and Kx, d once.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "ipoc_math.cuh"
+#include "../../include/ipoc.h"
+
+namespace ipoc {
+
+static unsigned long long g_launches = 0;
+struct Tuning {
+    int leaf_chunk, mid_fanin, top_max;
+};
+static Tuning g_tune = {0, 0, 0};
+
+constexpr int kLeafThreads = 128;
+constexpr int kMidThreads = 128;
+constexpr int kTopThreads = 256;
+constexpr int kTargetThreads = 148 * 256;
+
+// ------------------------------------------------------------------ SoA helpers
+template <class T>
+IPOC_DEV void soa_load(T& t, const double* __restrict__ base, size_t stride, size_t idx) {
+    constexpr int SZ = sizeof(T) / sizeof(double);
+#pragma unroll
+    for (int c = 0; c < SZ; ++c) t.r[c] = base[(size_t)c * stride + idx];
+}
+template <class T>
+IPOC_DEV void soa_store(const T& t, double* __restrict__ base, size_t stride, size_t idx) {
+    constexpr int SZ = sizeof(T) / sizeof(double);
+#pragma unroll
+    for (int c = 0; c < SZ; ++c) base[(size_t)c * stride + idx] = t.r[c];
+}
+template <class T>
+IPOC_DEV T shfl_up_all(const T& t, int delta) {
+    constexpr int SZ = sizeof(T) / sizeof(double);
+    T o;
+#pragma unroll
+    for (int c = 0; c < SZ; ++c) o.r[c] = __shfl_up_sync(0xffffffffu, t.r[c], delta);
+    return o;
+}
+
+// contiguous per-step loads: CNT doubles at p (16-byte aligned when CNT is even)
+template <int CNT>
+IPOC_DEV void ld_vec(double* dst, const double* __restrict__ p) {
+    if constexpr (CNT % 2 == 0) {
+        const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+        for (int i = 0; i < CNT / 2; ++i) {
+            const double2 v = __ldg(p2 + i);
+            dst[2 * i] = v.x;
+            dst[2 * i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; ++i) dst[i] = __ldg(p + i);
+    }
+}
+template <int CNT>
+IPOC_DEV void st_vec(double* __restrict__ p, const double* src) {
+    if constexpr (CNT % 2 == 0) {
+        double2* p2 = reinterpret_cast<double2*>(p);
+#pragma unroll
+        for (int i = 0; i < CNT / 2; ++i) p2[i] = make_double2(src[2 * i], src[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; ++i) p[i] = src[i];
+    }
+}
+
+// ------------------------------------------------------------------ generic mid / top kernels
+template <class Op>
+__global__ void __launch_bounds__(kMidThreads)
+k_mid_up(const double* __restrict__ in, size_t istride, int n_in,
+         double* __restrict__ out, size_t ostride, int n_out, int T, int batch) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * n_out) return;
+    const int b = (int)(g / n_out), j2 = (int)(g % n_out);
+    const int j0 = j2 * T, j1 = min(n_in, j0 + T);
+    const size_t base = (size_t)b * n_in;
+    typename Op::Elem a, e;
+    soa_load(a, in, istride, base + j0);
+    for (int j = j0 + 1; j < j1; ++j) {
+        soa_load(e, in, istride, base + j);
+        Op::compose(a, a, e);
+    }
+    soa_store(a, out, ostride, (size_t)g);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(kMidThreads)
+k_mid_down(const double* __restrict__ agg, size_t astride, int n_in,
+           double* __restrict__ vals_in, size_t vistride,
+           const double* __restrict__ vals_out, size_t vostride, int n_out, int T, int batch) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * n_out) return;
+    const int b = (int)(g / n_out), j2 = (int)(g % n_out);
+    const int j0 = j2 * T, j1 = min(n_in, j0 + T);
+    const size_t base = (size_t)b * n_in;
+    typename Op::Val v;
+    typename Op::Elem e;
+    soa_load(v, vals_out, vostride, (size_t)g);
+    for (int j = j0; j < j1; ++j) {
+        soa_store(v, vals_in, vistride, base + j);
+        if (j + 1 < j1) {
+            soa_load(e, agg, astride, base + j);
+            Op::apply(v, e, v);
+        }
+    }
+}
+
+// One CTA per sequence.  vals[j] = value ENTERING aggregate j (i.e. after aggregates 0..j-1 were
+// applied to the seed).  Optionally writes the composition of all n aggregates to `total`
+// (component-major with stride `batch`) and/or skips the value pass (reduce_only).
+template <class Op>
+__global__ void __launch_bounds__(kTopThreads)
+k_top(const double* __restrict__ agg, size_t astride, int n, int batch,
+      const double* __restrict__ seed, double* __restrict__ vals, size_t vstride,
+      double* __restrict__ total, int reduce_only) {
+    using Elem = typename Op::Elem;
+    using Val = typename Op::Val;
+    constexpr int ESZ = sizeof(Elem) / sizeof(double);
+    constexpr int VSZ = sizeof(Val) / sizeof(double);
+    constexpr int MAXW = kTopThreads / 32;
+    __shared__ double s_w[MAXW][ESZ];
+    __shared__ double s_v[MAXW][VSZ];
+
+    const int b = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
+    const int lane = t & 31, w = t >> 5, nw = nt >> 5;
+    const int q = (n + nt - 1) / nt;
+    const size_t base = (size_t)b * n;
+    const int j0 = t * q, j1 = min(n, j0 + q);
+
+    Elem inc;
+    if (j0 < n) {
+        soa_load(inc, agg, astride, base + j0);
+        Elem e;
+        for (int j = j0 + 1; j < j1; ++j) {
+            soa_load(e, agg, astride, base + j);
+            Op::compose(inc, inc, e);
+        }
+    } else {
+        Op::identity(inc);
+    }
+    // warp-level inclusive scan (Kogge-Stone over shuffles)
+#pragma unroll 1
+    for (int delta = 1; delta < 32; delta <<= 1) {
+        Elem o = shfl_up_all(inc, delta);
+        if (lane >= delta) Op::compose(inc, o, inc);
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < ESZ; ++c) s_w[w][c] = inc.r[c];
+    }
+    __syncthreads();
+    if (w == 0) {
+        Elem wi;
+        if (lane < nw) {
+#pragma unroll
+            for (int c = 0; c < ESZ; ++c) wi.r[c] = s_w[lane][c];
+        } else {
+            Op::identity(wi);
+        }
+#pragma unroll 1
+        for (int delta = 1; delta < MAXW; delta <<= 1) {
+            Elem o = shfl_up_all(wi, delta);
+            if (lane >= delta) Op::compose(wi, o, wi);
+        }
+        if (total != nullptr && lane == nw - 1) soa_store(wi, total, (size_t)batch, (size_t)b);
+        if (!reduce_only && lane < nw) {
+            Val sd, o;
+            soa_load(sd, seed, (size_t)batch, (size_t)b);
+            Op::apply(o, wi, sd);
+#pragma unroll
+            for (int c = 0; c < VSZ; ++c) s_v[lane][c] = o.r[c];
+        }
+    }
+    if (reduce_only) return;
+    __syncthreads();
+    Val v;
+    if (w == 0) {
+        soa_load(v, seed, (size_t)batch, (size_t)b);
+    } else {
+#pragma unroll
+        for (int c = 0; c < VSZ; ++c) v.r[c] = s_v[w - 1][c];
+    }
+    {
+        Elem ex = shfl_up_all(inc, 1);
+        if (lane > 0) Op::apply(v, ex, v);
+    }
+    if (j0 < n) {
+        Elem e;
+        for (int j = j0; j < j1; ++j) {
+            soa_store(v, vals, vstride, base + j);
+            if (j + 1 < j1) {
+                soa_load(e, agg, astride, base + j);
+                Op::apply(v, e, v);
+            }
+        }
+    }
+}
+
+// Sequentially push a seed through `nprev` gathered segment aggregates (time-sharded mode):
+// seed_out = apply(carry[order[nprev-1]], ... apply(carry[order[0]], seed_in)).
+// carries are rank-major AoS: carry[r * ESZ + c].  first = index of the first aggregate to
+// apply, step = +1/-1, count = how many.
+template <class Op>
+__global__ void k_chain_seed(const double* __restrict__ carries, int first, int step, int count,
+                             const double* __restrict__ seed_in, double* __restrict__ seed_out) {
+    using Elem = typename Op::Elem;
+    using Val = typename Op::Val;
+    constexpr int ESZ = sizeof(Elem) / sizeof(double);
+    constexpr int VSZ = sizeof(Val) / sizeof(double);
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Val v;
+#pragma unroll
+    for (int c = 0; c < VSZ; ++c) v.r[c] = seed_in[c];
+    Elem e;
+    for (int i = 0, r = first; i < count; ++i, r += step) {
+#pragma unroll
+        for (int c = 0; c < ESZ; ++c) e.r[c] = carries[(size_t)r * ESZ + c];
+        Op::apply(v, e, v);
+    }
+#pragma unroll
+    for (int c = 0; c < VSZ; ++c) seed_out[c] = v.r[c];
+}
+
+// ------------------------------------------------------------------ K2 loaders
+// Newton mode: builds the LQT terms of `noc_to_lqt` (ref noc/par_interior_point_newton.py:50-84)
+// on the fly: U = R + reg I (:118); X^-1 M (:63); s = -(U - M'X^-1M)^-1 ru (:64); r = -X^-1 M s
+// (:65); then the tracking references are folded back into linear cost terms
+// q = -(X r + M s), p = -(U s + M' r)   (H = Z = I, c = 0, :72-80).
+template <int NX, int NU>
+struct NewtonLoader {
+    const double *fx, *fu, *ru, *Q, *R, *M, *reg;
+    int N;
+    IPOC_DEV void load(StepLQ<NX, NU>& s, int b, int k) const {
+        const size_t t = (size_t)b * N + k;
+        double Qf[NX][NX], Rf[NU][NU], ruv[NU];
+        ld_vec<NX * NX>(&s.A[0][0], fx + t * NX * NX);
+        ld_vec<NX * NU>(&s.B[0][0], fu + t * NX * NU);
+        ld_vec<NX * NX>(&Qf[0][0], Q + t * NX * NX);
+        ld_vec<NU * NU>(&Rf[0][0], R + t * NU * NU);
+        ld_vec<NX * NU>(&s.M[0][0], M + t * NX * NU);
+        ld_vec<NU>(ruv, ru + t * NU);
+        const double rg = __ldg(reg + b);
+#pragma unroll
+        for (int a = 0; a < NU; ++a)
+#pragma unroll
+            for (int c = 0; c < NU; ++c) s.U[a][c] = Rf[a][c] + ((a == c) ? rg : 0.0);
+        // X^-1 M
+        double W[NX][NX], XiM[NX][NU];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) W[i][j] = Qf[i][j];
+#pragma unroll
+            for (int a = 0; a < NU; ++a) XiM[i][a] = s.M[i][a];
+        }
+        lu_solve<NX, NU>(W, XiM);
+        double Sm[NU][NU], sv[NU][1];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+#pragma unroll
+            for (int c = 0; c < NU; ++c) {
+                double v = s.U[a][c];
+#pragma unroll
+                for (int i = 0; i < NX; ++i) v -= s.M[i][a] * XiM[i][c];
+                Sm[a][c] = v;
+            }
+            sv[a][0] = ruv[a];
+        }
+        small_solve<NU, 1>(Sm, sv);   // sv = (U - M'X^-1M)^-1 ru  = -s
+        double rr[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int a = 0; a < NU; ++a) v += XiM[i][a] * sv[a][0];   // r = -XiM s = XiM sv
+            rr[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) v += Qf[i][j] * rr[j];
+#pragma unroll
+            for (int a = 0; a < NU; ++a) v -= s.M[i][a] * sv[a][0];   // + M s
+            s.q[i] = -v;
+            s.c[i] = 0.0;
+#pragma unroll
+            for (int j = i; j < NX; ++j) s.X[Sym<NX>::at(i, j)] = 0.5 * (Qf[i][j] + Qf[j][i]);
+        }
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < NU; ++c) v -= s.U[a][c] * sv[c][0];   // U s
+#pragma unroll
+            for (int i = 0; i < NX; ++i) v += s.M[i][a] * rr[i];     // + M' r
+            s.p[a] = -v;
+        }
+    }
+};
+
+// LQT mode: effective terms given directly.
+template <int NX, int NU>
+struct LqtLoader {
+    const double *A, *B, *c, *X, *U, *M, *q, *p;
+    int N;
+    IPOC_DEV void load(StepLQ<NX, NU>& s, int b, int k) const {
+        const size_t t = (size_t)b * N + k;
+        double Xf[NX][NX], Uf[NU][NU];
+        ld_vec<NX * NX>(&s.A[0][0], A + t * NX * NX);
+        ld_vec<NX * NU>(&s.B[0][0], B + t * NX * NU);
+        ld_vec<NX * NX>(&Xf[0][0], X + t * NX * NX);
+        ld_vec<NU * NU>(&Uf[0][0], U + t * NU * NU);
+        ld_vec<NX * NU>(&s.M[0][0], M + t * NX * NU);
+        ld_vec<NX>(s.q, q + t * NX);
+        ld_vec<NU>(s.p, p + t * NU);
+        if (c != nullptr) {
+            ld_vec<NX>(s.c, c + t * NX);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) s.c[i] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+            for (int j = i; j < NX; ++j) s.X[Sym<NX>::at(i, j)] = 0.5 * (Xf[i][j] + Xf[j][i]);
+#pragma unroll
+        for (int a = 0; a < NU; ++a)
+#pragma unroll
+            for (int cidx = 0; cidx < NU; ++cidx) s.U[a][cidx] = 0.5 * (Uf[a][cidx] + Uf[cidx][a]);
+    }
+};
+
+// Terminal value function per problem -> SoA seed (stride = batch).
+// ST: full (nx,nx) matrix at ST + b*st_stride (symmetrised), vT at vT + b*nx (NULL = 0).
+template <int NX>
+__global__ void k_ric_seed(const double* __restrict__ ST, size_t st_stride,
+                           const double* __restrict__ vT, int batch, double* __restrict__ seed) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    RicVal<NX> v;
+    const double* s = ST + (size_t)b * st_stride;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+#pragma unroll
+        for (int j = i; j < NX; ++j) v.S(i, j) = 0.5 * (s[i * NX + j] + s[j * NX + i]);
+        v.v(i) = (vT != nullptr) ? vT[(size_t)b * NX + i] : 0.0;
+    }
+    soa_store(v, seed, (size_t)batch, (size_t)b);
+}
+
+// ------------------------------------------------------------------ K2 leaf kernels
+// Up-sweep: thread (b, c) folds steps [c*T0, min(N,(c+1)T0)) backwards in time into one
+// element; stored at scan index n1-1-c (the scan runs from the end of the horizon).
+template <int NX, int NU, class Loader>
+__global__ void __launch_bounds__(kLeafThreads)
+k_ric_leaf_up(Loader ld, int N, int T0, int n1, int batch, double* __restrict__ agg, size_t astride) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * n1) return;
+    const int b = (int)(g / n1), c = (int)(g % n1);
+    const int k0 = c * T0, k1 = min(N, k0 + T0);
+    StepLQ<NX, NU> s;
+    StepElem<NX, NU> e;
+    RicElem<NX> a;
+    ld.load(s, b, k1 - 1);
+    make_step_elem(e, s);
+    step_to_elem(a, e);
+    for (int k = k1 - 2; k >= k0; --k) {
+        ld.load(s, b, k);
+        make_step_elem(e, s);
+        ric_prepend_step(a, e);
+    }
+    soa_store(a, agg, astride, (size_t)b * n1 + (n1 - 1 - c));
+}
+
+// Down-sweep: seeded Riccati recursion over the chunk, gains out, pred/feasibility partials,
+// and the chunk's forward (closed-loop) affine aggregate for K3.
+template <int NX, int NU, class Loader>
+__global__ void __launch_bounds__(kLeafThreads)
+k_ric_leaf_down(Loader ld, int N, int T0, int n1, int batch,
+                const double* __restrict__ vals, size_t vstride,
+                double* __restrict__ Kx, double* __restrict__ d,
+                double* __restrict__ S_out, double* __restrict__ v_out,
+                double* __restrict__ pred_part, int* __restrict__ feas_part,
+                double* __restrict__ fagg, size_t fstride) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * n1) return;
+    const int b = (int)(g / n1), c = (int)(g % n1);
+    const int k0 = c * T0, k1 = min(N, k0 + T0);
+    RicVal<NX> val;
+    soa_load(val, vals, vstride, (size_t)b * n1 + (n1 - 1 - c));
+    AffElem<NX> fa;
+    AffOp<NX>::identity(fa);
+    double predsum = 0.0;
+    bool feas = true;
+    auto write_Sv = [&](int k) {
+        double* Sp = S_out + ((size_t)b * (N + 1) + k) * NX * NX;
+        double* vp = v_out + ((size_t)b * (N + 1) + k) * NX;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) Sp[i * NX + j] = val.S(i, j);
+            vp[i] = val.v(i);
+        }
+    };
+    if (S_out != nullptr && k1 == N) write_Sv(N);
+    StepLQ<NX, NU> s;
+    StepGain<NX, NU> gn;
+    for (int k = k1 - 1; k >= k0; --k) {
+        ld.load(s, b, k);
+        ric_step_back(val, gn, s);
+        const size_t t = (size_t)b * N + k;
+        st_vec<NU * NX>(Kx + t * NU * NX, &gn.Kx[0][0]);
+        st_vec<NU>(d + t * NU, gn.d);
+        predsum += gn.dGd;
+        feas = feas && gn.pd;
+        if (S_out != nullptr) write_Sv(k);
+        if (fagg != nullptr) {
+            // fa <- fa o step_k :  P <- P Fcl,  q <- P ccl + q
+            AffElem<NX> st;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+#pragma unroll
+                for (int j = 0; j < NX; ++j) st.F(i, j) = gn.Fcl[i][j];
+                st.c(i) = gn.ccl[i];
+            }
+            AffOp<NX>::compose(fa, st, fa);
+        }
+    }
+    pred_part[g] = predsum;
+    feas_part[g] = feas ? 1 : 0;
+    if (fagg != nullptr) soa_store(fa, fagg, fstride, (size_t)g);
+}
+
+// pred = -1/2 sum_k d'Gd, feasible = AND_k (G_k > 0); fixed-order tree per problem.
+__global__ void __launch_bounds__(256)
+k_finalize_pred(const double* __restrict__ pred_part, const int* __restrict__ feas_part, int n1,
+                double* __restrict__ pred, int32_t* __restrict__ feasible, int accumulate) {
+    __shared__ double sp[256];
+    __shared__ int sf[256];
+    const int b = blockIdx.x, t = threadIdx.x;
+    double acc = 0.0;
+    int f = 1;
+    for (int j = t; j < n1; j += 256) {
+        acc += pred_part[(size_t)b * n1 + j];
+        f &= feas_part[(size_t)b * n1 + j];
+    }
+    sp[t] = acc;
+    sf[t] = f;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (t < o) {
+            sp[t] += sp[t + o];
+            sf[t] &= sf[t + o];
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        pred[b] = -0.5 * sp[0];
+        feasible[b] = sf[0];
+    }
+}
+
+// ------------------------------------------------------------------ K3 leaf down
+template <int NX, int NU>
+__global__ void __launch_bounds__(kLeafThreads)
+k_fwd_leaf_down(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ cc,
+                const double* __restrict__ Kx, const double* __restrict__ d,
+                int N, int T0, int n1, int batch,
+                const double* __restrict__ xvals, size_t xstride,
+                double* __restrict__ x_out, double* __restrict__ u_out) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * n1) return;
+    const int b = (int)(g / n1), c = (int)(g % n1);
+    const int k0 = c * T0, k1 = min(N, k0 + T0);
+    AffVal<NX> xv;
+    soa_load(xv, xvals, xstride, (size_t)g);
+    double x[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = xv.r[i];
+    for (int k = k0; k < k1; ++k) {
+        const size_t t = (size_t)b * N + k;
+        double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU], cv[NX], u[NU], xn[NX];
+        ld_vec<NX * NX>(&Am[0][0], A + t * NX * NX);
+        ld_vec<NX * NU>(&Bm[0][0], B + t * NX * NU);
+        ld_vec<NU * NX>(&Km[0][0], Kx + t * NU * NX);
+        ld_vec<NU>(dv, d + t * NU);
+        if (cc != nullptr) {
+            ld_vec<NX>(cv, cc + t * NX);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) cv[i] = 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+            double v = dv[a];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) v -= Km[a][j] * x[j];
+            u[a] = v;
+        }
+        st_vec<NX>(x_out + ((size_t)b * (N + 1) + k) * NX, x);
+        st_vec<NU>(u_out + t * NU, u);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            double v = cv[i];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) v += Am[i][j] * x[j];
+#pragma unroll
+            for (int a = 0; a < NU; ++a) v += Bm[i][a] * u[a];
+            xn[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = xn[i];
+    }
+    if (k1 == N) st_vec<NX>(x_out + ((size_t)b * (N + 1) + N) * NX, x);
+}
+
+// K3 leaf up (only for the stand-alone par_fwd_pass API; the Newton step gets these aggregates
+// from K2's down-sweep).
+template <int NX, int NU>
+__global__ void __launch_bounds__(kLeafThreads)
+k_fwd_leaf_up(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ cc,
+              const double* __restrict__ Kx, const double* __restrict__ d,
+              int N, int T0, int n1, int batch, double* __restrict__ fagg, size_t fstride) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * n1) return;
+    const int b = (int)(g / n1), c = (int)(g % n1);
+    const int k0 = c * T0, k1 = min(N, k0 + T0);
+    AffElem<NX> fa;
+    AffOp<NX>::identity(fa);
+    for (int k = k0; k < k1; ++k) {
+        const size_t t = (size_t)b * N + k;
+        double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU];
+        AffElem<NX> st;
+        ld_vec<NX * NX>(&Am[0][0], A + t * NX * NX);
+        ld_vec<NX * NU>(&Bm[0][0], B + t * NX * NU);
+        ld_vec<NU * NX>(&Km[0][0], Kx + t * NU * NX);
+        ld_vec<NU>(dv, d + t * NU);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                double v = Am[i][j];
+#pragma unroll
+                for (int a = 0; a < NU; ++a) v -= Bm[i][a] * Km[a][j];
+                st.F(i, j) = v;
+            }
+            double v = (cc != nullptr) ? __ldg(cc + t * NX + i) : 0.0;
+#pragma unroll
+            for (int a = 0; a < NU; ++a) v += Bm[i][a] * dv[a];
+            st.c(i) = v;
+        }
+        AffOp<NX>::compose(fa, fa, st);
+    }
+    soa_store(fa, fagg, fstride, (size_t)g);
+}
+
+// ------------------------------------------------------------------ K1 (generic affine scan) leaves
+template <int NX>
+IPOC_DEV void load_affine_step(AffElem<NX>& st, const double* __restrict__ F, const double* __restrict__ c,
+                               size_t t, int transpose) {
+    double Fm[NX][NX], cv[NX];
+    ld_vec<NX * NX>(&Fm[0][0], F + t * NX * NX);
+    ld_vec<NX>(cv, c + t * NX);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) st.F(i, j) = transpose ? Fm[j][i] : Fm[i][j];
+        st.c(i) = cv[i];
+    }
+}
+
+template <int NX>
+__global__ void __launch_bounds__(kLeafThreads)
+k_aff_leaf_up(const double* __restrict__ F, const double* __restrict__ c, int reverse, int transpose,
+              int N, int T0, int n1, int batch, double* __restrict__ agg, size_t astride) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * n1) return;
+    const int b = (int)(g / n1), ch = (int)(g % n1);
+    const int k0 = ch * T0, k1 = min(N, k0 + T0);
+    AffElem<NX> a, st;
+    if (reverse) {
+        load_affine_step<NX>(a, F, c, (size_t)b * N + (k1 - 1), transpose);
+        for (int k = k1 - 2; k >= k0; --k) {
+            load_affine_step<NX>(st, F, c, (size_t)b * N + k, transpose);
+            AffOp<NX>::compose(a, a, st);
+        }
+        soa_store(a, agg, astride, (size_t)b * n1 + (n1 - 1 - ch));
+    } else {
+        load_affine_step<NX>(a, F, c, (size_t)b * N + k0, transpose);
+        for (int k = k0 + 1; k < k1; ++k) {
+            load_affine_step<NX>(st, F, c, (size_t)b * N + k, transpose);
+            AffOp<NX>::compose(a, a, st);
+        }
+        soa_store(a, agg, astride, (size_t)g);
+    }
+}
+
+template <int NX>
+__global__ void __launch_bounds__(kLeafThreads)
+k_aff_leaf_down(const double* __restrict__ F, const double* __restrict__ c, int reverse, int transpose,
+                int N, int T0, int n1, int batch,
+                const double* __restrict__ vals, size_t vstride, double* __restrict__ out) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * n1) return;
+    const int b = (int)(g / n1), ch = (int)(g % n1);
+    const int k0 = ch * T0, k1 = min(N, k0 + T0);
+    AffVal<NX> x;
+    AffElem<NX> st;
+    double* ob = out + (size_t)b * (N + 1) * NX;
+    if (reverse) {
+        soa_load(x, vals, vstride, (size_t)b * n1 + (n1 - 1 - ch));
+        if (k1 == N) st_vec<NX>(ob + (size_t)N * NX, x.r);
+        for (int k = k1 - 1; k >= k0; --k) {
+            load_affine_step<NX>(st, F, c, (size_t)b * N + k, transpose);
+            AffOp<NX>::apply(x, st, x);
+            st_vec<NX>(ob + (size_t)k * NX, x.r);
+        }
+    } else {
+        soa_load(x, vals, vstride, (size_t)g);
+        if (k0 == 0) st_vec<NX>(ob, x.r);
+        for (int k = k0; k < k1; ++k) {
+            load_affine_step<NX>(st, F, c, (size_t)b * N + k, transpose);
+            AffOp<NX>::apply(x, st, x);
+            st_vec<NX>(ob + (size_t)(k + 1) * NX, x.r);
+        }
+    }
+}
+
+// AoS (batch, nx) -> SoA seed planes (stride batch); NULL source = zeros.
+template <int NX>
+__global__ void k_aff_seed(const double* __restrict__ src, int batch, double* __restrict__ seed) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) seed[(size_t)i * batch + b] = (src != nullptr) ? src[(size_t)b * NX + i] : 0.0;
+}
+
+// SoA planes (stride `stride`, index idx) -> AoS carry (time-sharded mode)
+__global__ void k_soa_to_aos(const double* __restrict__ soa, size_t stride, size_t idx, int sz,
+                             double* __restrict__ aos) {
+    const int c = threadIdx.x;
+    if (c < sz) aos[c] = soa[(size_t)c * stride + idx];
+}
+
+// ------------------------------------------------------------------ K4 reductions + A8 update
+__global__ void __launch_bounds__(256)
+k_reductions(const double* __restrict__ ru, const double* __restrict__ cu, const double* __restrict__ cons,
+             int N, int nu, int nc, double* __restrict__ hu_norm, double* __restrict__ cu_norm,
+             int32_t* __restrict__ traj_feasible) {
+    __shared__ double s_max[256];
+    __shared__ double s_sq[256];
+    __shared__ int s_ok[256];
+    const int b = blockIdx.x, t = threadIdx.x;
+    double mx = 0.0, sq = 0.0;
+    int ok = 1, nan_seen = 0;
+    if (ru != nullptr) {
+        const double* p = ru + (size_t)b * N * nu;
+        for (long long i = t; i < (long long)N * nu; i += 256) {
+            const double v = fabs(p[i]);
+            if (v != v) nan_seen = 1;
+            mx = fmax(mx, v);
+        }
+    }
+    if (cu != nullptr) {
+        const double* p = cu + (size_t)b * N * nu;
+        for (long long i = t; i < (long long)N * nu; i += 256) sq += p[i] * p[i];
+    }
+    if (cons != nullptr) {
+        const double* p = cons + (size_t)b * N * nc;
+        for (long long i = t; i < (long long)N * nc; i += 256) ok &= (p[i] <= 0.0) ? 1 : 0;
+    }
+    s_max[t] = nan_seen ? __longlong_as_double(0x7ff8000000000000LL) : mx;
+    s_sq[t] = sq;
+    s_ok[t] = ok;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (t < o) {
+            const double a = s_max[t], c = s_max[t + o];
+            s_max[t] = (a != a || c != c) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(a, c);
+            s_sq[t] += s_sq[t + o];
+            s_ok[t] &= s_ok[t + o];
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        if (ru != nullptr) hu_norm[b] = s_max[0];
+        if (cu != nullptr) cu_norm[b] = sqrt(s_sq[0]);
+        if (cons != nullptr) traj_feasible[b] = s_ok[0];
+    }
+}
+
+__global__ void k_accept_update(int batch, const double* __restrict__ cost, const double* __restrict__ new_cost,
+                                const int32_t* __restrict__ traj_feasible, const double* __restrict__ pred,
+                                const int32_t* __restrict__ bwd_feasible, const int32_t* __restrict__ active,
+                                double* __restrict__ rp, double* __restrict__ r_inc,
+                                int32_t* __restrict__ success, double* __restrict__ gain_ratio) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    if (active != nullptr && !active[b]) return;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double nc = traj_feasible[b] ? new_cost[b] : inf;
+    const double rho = (nc - cost[b]) / pred[b];
+    const bool ok = (rho > 0.0) && (bwd_feasible[b] != 0);
+    double r = rp[b], ri = r_inc[b];
+    if (ok) {
+        const double tq = 2.0 * rho - 1.0;
+        r = r * fmax(1.0 / 3.0, 1.0 - tq * tq * tq);
+        ri = 2.0;
+    } else {
+        r = r * ri;
+        ri = 2.0 * ri;
+    }
+    r = fmin(fmax(r, 1e-16), 1e16);
+    rp[b] = r;
+    r_inc[b] = ri;
+    success[b] = ok ? 1 : 0;
+    if (gain_ratio != nullptr) gain_ratio[b] = rho;
+}
+
+// =================================================================== host side
+constexpr int MAXLEV = 8;
+struct Plan {
+    int N, batch, T0, n1, nlev;
+    int n[MAXLEV];   // aggregates per sequence at level l (n[0] = n1)
+    int T[MAXLEV];   // fan-in from level l to l+1
+};
+
+static Plan make_plan(int N, int batch) {
+    Plan p{};
+    p.N = N;
+    p.batch = batch;
+    const int top_max = g_tune.top_max > 0 ? g_tune.top_max : 512;
+    const int mid = g_tune.mid_fanin > 1 ? g_tune.mid_fanin : 8;
+    int T0 = g_tune.leaf_chunk;
+    if (T0 <= 0) {
+        const long long total = (long long)N * batch;
+        if (batch >= kTargetThreads / 4) {
+            T0 = N;   // enough independent problems: one pass, no scan
+        } else {
+            long long t = (total + kTargetThreads - 1) / kTargetThreads;
+            T0 = (int)(t < 4 ? 4 : t);
+        }
+    }
+    if (T0 > N) T0 = N;
+    if (T0 < 1) T0 = 1;
+    p.T0 = T0;
+    p.n1 = (N + T0 - 1) / T0;
+    p.nlev = 0;
+    if (p.n1 > 1) {
+        p.n[0] = p.n1;
+        p.nlev = 1;
+        while (p.n[p.nlev - 1] > top_max && p.nlev < MAXLEV) {
+            p.T[p.nlev - 1] = mid;
+            p.n[p.nlev] = (p.n[p.nlev - 1] + mid - 1) / mid;
+            p.nlev++;
+        }
+    }
+    return p;
+}
+
+struct Bump {
+    char* base;
+    size_t off, cap;
+    bool dry;
+    template <class T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* r = dry ? nullptr : reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+};
+
+struct ScanWs {   // workspace of one hierarchical scan
+    double* agg[MAXLEV];
+    double* val[MAXLEV];
+    double* seed;
+    double* total;
+};
+
+static void carve_scan(Bump& bp, const Plan& p, int esz, int vsz, ScanWs& w) {
+    for (int l = 0; l < p.nlev; ++l) {
+        w.agg[l] = bp.take<double>((size_t)esz * p.batch * p.n[l]);
+        w.val[l] = bp.take<double>((size_t)vsz * p.batch * p.n[l]);
+    }
+    w.seed = bp.take<double>((size_t)vsz * p.batch);
+    w.total = bp.take<double>((size_t)esz * p.batch);
+}
+
+struct NewtonWs {
+    ScanWs ric, aff;
+    double* pred_part;
+    int* feas_part;
+    double* scratch;   // misc small device scalars
+};
+
+template <int NX>
+static void carve_newton(Bump& bp, const Plan& p, NewtonWs& w) {
+    carve_scan(bp, p, RicElem<NX>::ESZ, RicVal<NX>::VSZ, w.ric);
+    carve_scan(bp, p, AffElem<NX>::ESZ, NX, w.aff);
+    w.pred_part = bp.take<double>((size_t)p.batch * p.n1);
+    w.feas_part = bp.take<int>((size_t)p.batch * p.n1);
+    w.scratch = bp.take<double>(256);
+}
+
+#define IPOC_LAUNCH_CHECK()                                   \
+    do {                                                      \
+        ++g_launches;                                         \
+        if (cudaPeekAtLastError() != cudaSuccess) return IPOC_ECUDA; \
+    } while (0)
+
+static inline unsigned grid_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+static inline int top_threads(int n) {
+    int t = ((n + 31) / 32) * 32;
+    return t > kTopThreads ? kTopThreads : t;
+}
+
+// up-sweep over the aggregate levels (level 0 already filled), top scan, down-sweep to level 0.
+// On return w.val[0] holds the value entering every leaf chunk.  If reduce_only, only the total
+// aggregate of each sequence is produced (w.total, SoA stride batch).
+template <class Op>
+static int run_levels(const Plan& p, const ScanWs& w, bool want_total, bool reduce_only, cudaStream_t st) {
+    const int L = p.nlev;
+    for (int l = 0; l + 1 < L; ++l) {
+        const long long cnt = (long long)p.batch * p.n[l + 1];
+        k_mid_up<Op><<<grid_for(cnt, kMidThreads), kMidThreads, 0, st>>>(
+            w.agg[l], (size_t)p.batch * p.n[l], p.n[l], w.agg[l + 1], (size_t)p.batch * p.n[l + 1], p.n[l + 1],
+            p.T[l], p.batch);
+        IPOC_LAUNCH_CHECK();
+    }
+    k_top<Op><<<p.batch, top_threads(p.n[L - 1]), 0, st>>>(
+        w.agg[L - 1], (size_t)p.batch * p.n[L - 1], p.n[L - 1], p.batch, w.seed, w.val[L - 1],
+        (size_t)p.batch * p.n[L - 1], (want_total || reduce_only) ? w.total : nullptr, reduce_only ? 1 : 0);
+    IPOC_LAUNCH_CHECK();
+    if (reduce_only) return IPOC_OK;
+    for (int l = L - 2; l >= 0; --l) {
+        const long long cnt = (long long)p.batch * p.n[l + 1];
+        k_mid_down<Op><<<grid_for(cnt, kMidThreads), kMidThreads, 0, st>>>(
+            w.agg[l], (size_t)p.batch * p.n[l], p.n[l], w.val[l], (size_t)p.batch * p.n[l], w.val[l + 1],
+            (size_t)p.batch * p.n[l + 1], p.n[l + 1], p.T[l], p.batch);
+        IPOC_LAUNCH_CHECK();
+    }
+    return IPOC_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- K2 (+K3 aggregates) for any loader ---------------------------------------------------
+template <int NX, int NU, class Loader>
+static int run_bwd(const Plan& p, const NewtonWs& w, const Loader& ld, double* Kx, double* d, double* S, double* v,
+                   double* pred, int32_t* feasible, bool want_fwd_agg, cudaStream_t st) {
+    using ROp = RicOp<NX>;
+    const long long chunks = (long long)p.batch * p.n1;
+    const double* leaf_vals;
+    size_t leaf_vstride;
+    if (p.nlev > 0) {
+        k_ric_leaf_up<NX, NU, Loader><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
+            ld, p.N, p.T0, p.n1, p.batch, w.ric.agg[0], (size_t)chunks);
+        IPOC_LAUNCH_CHECK();
+        int rc = run_levels<ROp>(p, w.ric, false, false, st);
+        if (rc) return rc;
+        leaf_vals = w.ric.val[0];
+        leaf_vstride = (size_t)chunks;
+    } else {
+        leaf_vals = w.ric.seed;
+        leaf_vstride = (size_t)p.batch;
+    }
+    double* fagg = nullptr;
+    size_t fstride = 0;
+    if (want_fwd_agg && p.nlev > 0) {
+        fagg = w.aff.agg[0];
+        fstride = (size_t)chunks;
+    }
+    k_ric_leaf_down<NX, NU, Loader><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
+        ld, p.N, p.T0, p.n1, p.batch, leaf_vals, leaf_vstride, Kx, d, S, v, w.pred_part, w.feas_part, fagg, fstride);
+    IPOC_LAUNCH_CHECK();
+    k_finalize_pred<<<p.batch, 256, 0, st>>>(w.pred_part, w.feas_part, p.n1, pred, feasible, 0);
+    IPOC_LAUNCH_CHECK();
+    return IPOC_OK;
+}
+
+// ---- K3 given leaf aggregates in w.aff.agg[0] (if nlev > 0) and seed in w.aff.seed ---------
+template <int NX, int NU>
+static int run_fwd_down(const Plan& p, const NewtonWs& w, const double* A, const double* B, const double* c,
+                        const double* Kx, const double* d, double* x, double* u, cudaStream_t st) {
+    const long long chunks = (long long)p.batch * p.n1;
+    const double* leaf_vals = w.aff.seed;
+    size_t leaf_vstride = (size_t)p.batch;
+    if (p.nlev > 0) {
+        int rc = run_levels<AffOp<NX>>(p, w.aff, false, false, st);
+        if (rc) return rc;
+        leaf_vals = w.aff.val[0];
+        leaf_vstride = (size_t)chunks;
+    }
+    k_fwd_leaf_down<NX, NU><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
+        A, B, c, Kx, d, p.N, p.T0, p.n1, p.batch, leaf_vals, leaf_vstride, x, u);
+    IPOC_LAUNCH_CHECK();
+    return IPOC_OK;
+}
+
+template <int NX, int NU>
+static int newton_step_impl(int N, int batch, const double* fx, const double* fu, const double* ru, const double* Q,
+                            const double* R, const double* M, const double* reg, double* dx, double* du, double* Kx,
+                            double* d, double* pred, int32_t* feasible, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const Plan p = make_plan(N, batch);
+    Bump bp{(char*)ws, 0, ws_bytes, false};
+    NewtonWs w;
+    carve_newton<NX>(bp, p, w);
+    if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
+    // terminal value function: XT = Q[0], HT = I, rT = 0 (ref noc/par_interior_point_newton.py:73-75)
+    k_ric_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(Q, (size_t)N * NX * NX, nullptr, batch, w.ric.seed);
+    IPOC_LAUNCH_CHECK();
+    k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(nullptr, batch, w.aff.seed);   // dx_0 = 0 (:122)
+    IPOC_LAUNCH_CHECK();
+    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg, N};
+    int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st);
+    if (rc) return rc;
+    return run_fwd_down<NX, NU>(p, w, fx, fu, nullptr, Kx, d, dx, du, st);
+}
+
+template <int NX, int NU>
+static int lqt_bwd_impl(int N, int batch, const double* A, const double* B, const double* c, const double* X,
+                        const double* U, const double* M, const double* q, const double* pp, const double* ST,
+                        const double* vT, double* Kx, double* d, double* S, double* v, double* pred,
+                        int32_t* feasible, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const Plan p = make_plan(N, batch);
+    Bump bp{(char*)ws, 0, ws_bytes, false};
+    NewtonWs w;
+    carve_newton<NX>(bp, p, w);
+    if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
+    k_ric_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(ST, (size_t)NX * NX, vT, batch, w.ric.seed);
+    IPOC_LAUNCH_CHECK();
+    LqtLoader<NX, NU> ld{A, B, c, X, U, M, q, pp, N};
+    return run_bwd<NX, NU>(p, w, ld, Kx, d, S, v, pred, feasible, false, st);
+}
+
+template <int NX, int NU>
+static int lqt_fwd_impl(int N, int batch, const double* A, const double* B, const double* c, const double* Kx,
+                        const double* d, const double* x0, double* u, double* x, void* ws, size_t ws_bytes,
+                        cudaStream_t st) {
+    const Plan p = make_plan(N, batch);
+    Bump bp{(char*)ws, 0, ws_bytes, false};
+    NewtonWs w;
+    carve_newton<NX>(bp, p, w);
+    if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
+    k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(x0, batch, w.aff.seed);
+    IPOC_LAUNCH_CHECK();
+    if (p.nlev > 0) {
+        const long long chunks = (long long)batch * p.n1;
+        k_fwd_leaf_up<NX, NU><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
+            A, B, c, Kx, d, N, p.T0, p.n1, batch, w.aff.agg[0], (size_t)chunks);
+        IPOC_LAUNCH_CHECK();
+    }
+    return run_fwd_down<NX, NU>(p, w, A, B, c, Kx, d, x, u, st);
+}
+
+template <int NX>
+static int affine_scan_impl(int reverse, int transpose, int N, int batch, const double* F, const double* c,
+                            const double* seed, double* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const Plan p = make_plan(N, batch);
+    Bump bp{(char*)ws, 0, ws_bytes, false};
+    ScanWs w;
+    carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
+    if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
+    k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(seed, batch, w.seed);
+    IPOC_LAUNCH_CHECK();
+    const long long chunks = (long long)batch * p.n1;
+    const double* leaf_vals = w.seed;
+    size_t leaf_vstride = (size_t)batch;
+    if (p.nlev > 0) {
+        k_aff_leaf_up<NX><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
+            F, c, reverse, transpose, N, p.T0, p.n1, batch, w.agg[0], (size_t)chunks);
+        IPOC_LAUNCH_CHECK();
+        int rc = run_levels<AffOp<NX>>(p, w, false, false, st);
+        if (rc) return rc;
+        leaf_vals = w.val[0];
+        leaf_vstride = (size_t)chunks;
+    }
+    k_aff_leaf_down<NX><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
+        F, c, reverse, transpose, N, p.T0, p.n1, batch, leaf_vals, leaf_vstride, out);
+    IPOC_LAUNCH_CHECK();
+    return IPOC_OK;
+}
+
+// ---- time-sharded split-phase implementations ----------------------------------------------
+// A segment always uses at least one aggregate level here (forced chunking) so that the
+// segment total falls out of the top scan.
+static Plan make_plan_sharded(int N) {
+    Plan p = make_plan(N, 1);
+    if (p.nlev == 0) {   // single chunk: make it a one-aggregate level so k_top produces the total
+        p.n[0] = 1;
+        p.nlev = 1;
+    }
+    return p;
+}
+
+template <int NX, int NU>
+static int newton_bwd_reduce_impl(int N, const double* fx, const double* fu, const double* ru, const double* Q,
+                                  const double* R, const double* M, const double* reg, double* carry_out, void* ws,
+                                  size_t ws_bytes, cudaStream_t st) {
+    const Plan p = make_plan_sharded(N);
+    Bump bp{(char*)ws, 0, ws_bytes, false};
+    NewtonWs w;
+    carve_newton<NX>(bp, p, w);
+    if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
+    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg, N};
+    k_ric_leaf_up<NX, NU, NewtonLoader<NX, NU>><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(
+        ld, N, p.T0, p.n1, 1, w.ric.agg[0], (size_t)p.n1);
+    IPOC_LAUNCH_CHECK();
+    int rc = run_levels<RicOp<NX>>(p, w.ric, true, true, st);
+    if (rc) return rc;
+    k_soa_to_aos<<<1, 256, 0, st>>>(w.ric.total, 1, 0, RicElem<NX>::ESZ, carry_out);
+    IPOC_LAUNCH_CHECK();
+    return IPOC_OK;
+}
+
+template <int NX, int NU>
+static int newton_bwd_apply_impl(int N, int rank, int nranks, const double* fx, const double* fu, const double* ru,
+                                 const double* Q, const double* R, const double* M, const double* reg,
+                                 const double* carries, const double* ST, double* Kx, double* d, double* pred,
+                                 int32_t* feasible, double* fwd_carry_out, void* ws, size_t ws_bytes,
+                                 cudaStream_t st) {
+    const Plan p = make_plan_sharded(N);
+    Bump bp{(char*)ws, 0, ws_bytes, false};
+    NewtonWs w;
+    carve_newton<NX>(bp, p, w);
+    if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
+    // terminal seed of the whole horizon, then pushed back through the later ranks' aggregates
+    double* seed0 = w.scratch;   // RicVal packed
+    k_ric_seed<NX><<<1, 32, 0, st>>>(ST, (size_t)NX * NX, nullptr, 1, seed0);
+    IPOC_LAUNCH_CHECK();
+    k_chain_seed<RicOp<NX>><<<1, 32, 0, st>>>(carries, nranks - 1, -1, nranks - 1 - rank, seed0, w.ric.seed);
+    IPOC_LAUNCH_CHECK();
+    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg, N};
+    // the leaf aggregates of this segment were computed in the reduce phase with the same plan
+    // and are still in the workspace (same carve order) — the caller must pass the same ws.
+    using ROp = RicOp<NX>;
+    {
+        // recompute values from existing aggregates: top (not reduce-only) + mid downs
+        const int L = p.nlev;
+        k_top<ROp><<<1, top_threads(p.n[L - 1]), 0, st>>>(w.ric.agg[L - 1], (size_t)p.n[L - 1], p.n[L - 1], 1,
+                                                         w.ric.seed, w.ric.val[L - 1], (size_t)p.n[L - 1], nullptr, 0);
+        IPOC_LAUNCH_CHECK();
+        for (int l = L - 2; l >= 0; --l) {
+            k_mid_down<ROp><<<grid_for(p.n[l + 1], kMidThreads), kMidThreads, 0, st>>>(
+                w.ric.agg[l], (size_t)p.n[l], p.n[l], w.ric.val[l], (size_t)p.n[l], w.ric.val[l + 1],
+                (size_t)p.n[l + 1], p.n[l + 1], p.T[l], 1);
+            IPOC_LAUNCH_CHECK();
+        }
+    }
+    k_ric_leaf_down<NX, NU, NewtonLoader<NX, NU>><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(
+        ld, N, p.T0, p.n1, 1, w.ric.val[0], (size_t)p.n1, Kx, d, nullptr, nullptr, w.pred_part, w.feas_part,
+        w.aff.agg[0], (size_t)p.n1);
+    IPOC_LAUNCH_CHECK();
+    k_finalize_pred<<<1, 256, 0, st>>>(w.pred_part, w.feas_part, p.n1, pred, feasible, 0);
+    IPOC_LAUNCH_CHECK();
+    int rc = run_levels<AffOp<NX>>(p, w.aff, true, true, st);
+    if (rc) return rc;
+    k_soa_to_aos<<<1, 256, 0, st>>>(w.aff.total, 1, 0, AffElem<NX>::ESZ, fwd_carry_out);
+    IPOC_LAUNCH_CHECK();
+    return IPOC_OK;
+}
+
+template <int NX, int NU>
+static int newton_fwd_apply_impl(int N, int rank, int nranks, const double* fx, const double* fu, const double* Kx,
+                                 const double* d, const double* fwd_carries, double* dx, double* du, void* ws,
+                                 size_t ws_bytes, cudaStream_t st) {
+    const Plan p = make_plan_sharded(N);
+    Bump bp{(char*)ws, 0, ws_bytes, false};
+    NewtonWs w;
+    carve_newton<NX>(bp, p, w);
+    if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
+    double* seed0 = w.scratch;
+    k_aff_seed<NX><<<1, 32, 0, st>>>(nullptr, 1, seed0);
+    IPOC_LAUNCH_CHECK();
+    k_chain_seed<AffOp<NX>><<<1, 32, 0, st>>>(fwd_carries, 0, +1, rank, seed0, w.aff.seed);
+    IPOC_LAUNCH_CHECK();
+    using AOp = AffOp<NX>;
+    const int L = p.nlev;
+    k_top<AOp><<<1, top_threads(p.n[L - 1]), 0, st>>>(w.aff.agg[L - 1], (size_t)p.n[L - 1], p.n[L - 1], 1, w.aff.seed,
+                                                     w.aff.val[L - 1], (size_t)p.n[L - 1], nullptr, 0);
+    IPOC_LAUNCH_CHECK();
+    for (int l = L - 2; l >= 0; --l) {
+        k_mid_down<AOp><<<grid_for(p.n[l + 1], kMidThreads), kMidThreads, 0, st>>>(
+            w.aff.agg[l], (size_t)p.n[l], p.n[l], w.aff.val[l], (size_t)p.n[l], w.aff.val[l + 1], (size_t)p.n[l + 1],
+            p.n[l + 1], p.T[l], 1);
+        IPOC_LAUNCH_CHECK();
+    }
+    k_fwd_leaf_down<NX, NU><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(
+        fx, fu, nullptr, Kx, d, N, p.T0, p.n1, 1, w.aff.val[0], (size_t)p.n1, dx, du);
+    IPOC_LAUNCH_CHECK();
+    return IPOC_OK;
+}
+
+template <int NX>
+static int affine_reduce_impl(int reverse, int transpose, int N, const double* F, const double* c, double* carry_out,
+                              void* ws, size_t ws_bytes, cudaStream_t st) {
+    const Plan p = make_plan_sharded(N);
+    Bump bp{(char*)ws, 0, ws_bytes, false};
+    ScanWs w;
+    carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
+    if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
+    k_aff_leaf_up<NX><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(F, c, reverse, transpose, N, p.T0, p.n1,
+                                                                            1, w.agg[0], (size_t)p.n1);
+    IPOC_LAUNCH_CHECK();
+    int rc = run_levels<AffOp<NX>>(p, w, true, true, st);
+    if (rc) return rc;
+    k_soa_to_aos<<<1, 256, 0, st>>>(w.total, 1, 0, AffElem<NX>::ESZ, carry_out);
+    IPOC_LAUNCH_CHECK();
+    return IPOC_OK;
+}
+
+template <int NX>
+static int affine_apply_impl(int reverse, int transpose, int N, int rank, int nranks, const double* F,
+                             const double* c, const double* carries, const double* seed, double* out, void* ws,
+                             size_t ws_bytes, cudaStream_t st) {
+    const Plan p = make_plan_sharded(N);
+    Bump bp{(char*)ws, 0, ws_bytes, false};
+    ScanWs w;
+    carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
+    if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
+    using AOp = AffOp<NX>;
+    if (reverse)
+        k_chain_seed<AOp><<<1, 32, 0, st>>>(carries, nranks - 1, -1, nranks - 1 - rank, seed, w.seed);
+    else
+        k_chain_seed<AOp><<<1, 32, 0, st>>>(carries, 0, +1, rank, seed, w.seed);
+    IPOC_LAUNCH_CHECK();
+    const int L = p.nlev;
+    k_top<AOp><<<1, top_threads(p.n[L - 1]), 0, st>>>(w.agg[L - 1], (size_t)p.n[L - 1], p.n[L - 1], 1, w.seed,
+                                                     w.val[L - 1], (size_t)p.n[L - 1], nullptr, 0);
+    IPOC_LAUNCH_CHECK();
+    for (int l = L - 2; l >= 0; --l) {
+        k_mid_down<AOp><<<grid_for(p.n[l + 1], kMidThreads), kMidThreads, 0, st>>>(
+            w.agg[l], (size_t)p.n[l], p.n[l], w.val[l], (size_t)p.n[l], w.val[l + 1], (size_t)p.n[l + 1], p.n[l + 1],
+            p.T[l], 1);
+        IPOC_LAUNCH_CHECK();
+    }
+    k_aff_leaf_down<NX><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(F, c, reverse, transpose, N, p.T0,
+                                                                              p.n1, 1, w.val[0], (size_t)p.n1, out);
+    IPOC_LAUNCH_CHECK();
+    return IPOC_OK;
+}
+
+template <int NX>
+static size_t ws_bytes_impl(int kind, int N, int batch, bool sharded) {
+    const Plan p = sharded ? make_plan_sharded(N) : make_plan(N, batch);
+    Bump bp{nullptr, 0, 0, true};
+    if (kind == IPOC_WS_AFFINE_SCAN) {
+        ScanWs w;
+        carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
+    } else {
+        NewtonWs w;
+        carve_newton<NX>(bp, p, w);
+    }
+    return bp.off + 256;
+}
+
+}  // namespace ipoc
+
+// =================================================================== C ABI
+using namespace ipoc;
+
+#define IPOC_FOR_DIMS(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(4, 1) X(4, 2) X(6, 1) X(8, 1)
+#define IPOC_FOR_NX(X) X(1) X(2) X(3) X(4) X(6) X(8)
+
+extern "C" {
+
+const char* ipoc_strerror(int code) {
+    switch (code) {
+        case IPOC_OK: return "ok";
+        case IPOC_EUNSUPPORTED_DIM: return "unsupported (nx, nu): no kernel instantiated and there is no CPU fallback";
+        case IPOC_EWORKSPACE: return "workspace too small (see ipoc_workspace_bytes)";
+        case IPOC_ECUDA: return "CUDA error at kernel launch";
+        case IPOC_ENCCL: return "NCCL error";
+        case IPOC_EINVAL: return "invalid argument";
+        case IPOC_EALIGN: return "pointer not 16-byte aligned";
+        default: return "unknown ipoc error";
+    }
+}
+
+int ipoc_version(void) { return 100; }
+
+int ipoc_supported(int nx, int nu) {
+#define X(a, b) if (nx == a && nu == b) return 1;
+    IPOC_FOR_DIMS(X)
+#undef X
+    return 0;
+}
+
+void ipoc_set_tuning(int leaf_chunk, int mid_fanin, int top_max) {
+    g_tune.leaf_chunk = leaf_chunk;
+    g_tune.mid_fanin = mid_fanin;
+    g_tune.top_max = top_max;
+}
+
+unsigned long long ipoc_launch_count(void) { return g_launches; }
+
+int ipoc_carry_doubles(int kind, int nx) {
+    if (nx < 1 || nx > 8) return 0;
+    const int sy = nx * (nx + 1) / 2;
+    return kind == IPOC_CARRY_RICCATI ? nx * nx + 2 * nx + 2 * sy : nx * nx + nx;
+}
+
+size_t ipoc_workspace_bytes(int kind, int N, int nx, int nu, int batch) {
+    (void)nu;
+    if (N < 1 || batch < 1) return 0;
+    // the sharded entry points use the same formula with batch = 1 and forced chunking; take the max
+#define X(a) if (nx == a) { size_t s1 = ws_bytes_impl<a>(kind, N, batch, false); \
+                            size_t s2 = batch == 1 ? ws_bytes_impl<a>(kind, N, 1, true) : 0; return s1 > s2 ? s1 : s2; }
+    IPOC_FOR_NX(X)
+#undef X
+    return 0;
+}
+
+#define CHECK_ARGS(cond) do { if (!(cond)) return IPOC_EINVAL; } while (0)
+#define CHECK_ALIGN(p) do { if ((p) != nullptr && !aligned16(p)) return IPOC_EALIGN; } while (0)
+
+int ipoc_newton_step_f64(int N, int nx, int nu, int batch, const double* fx, const double* fu, const double* ru,
+                         const double* Q, const double* R, const double* M, const double* reg, double* dx, double* du,
+                         double* Kx, double* d, double* pred, int32_t* feasible, void* ws, size_t ws_bytes,
+                         ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && fx && fu && ru && Q && R && M && reg && dx && du && Kx && d && pred && feasible && ws);
+    CHECK_ALIGN(fx); CHECK_ALIGN(fu); CHECK_ALIGN(ru); CHECK_ALIGN(Q); CHECK_ALIGN(R); CHECK_ALIGN(M);
+    CHECK_ALIGN(dx); CHECK_ALIGN(du); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(ws);
+#define X(a, b) if (nx == a && nu == b) return newton_step_impl<a, b>(N, batch, fx, fu, ru, Q, R, M, reg, dx, du, Kx, d, pred, feasible, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_DIMS(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_lqt_bwd_f64(int N, int nx, int nu, int batch, const double* A, const double* B, const double* c,
+                     const double* Xm, const double* U, const double* M, const double* q, const double* p,
+                     const double* ST, const double* vT, double* Kx, double* d, double* S, double* v, double* pred,
+                     int32_t* feasible, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && A && B && Xm && U && M && q && p && ST && Kx && d && pred && feasible && ws);
+    CHECK_ARGS((S == nullptr) == (v == nullptr));
+    CHECK_ALIGN(A); CHECK_ALIGN(B); CHECK_ALIGN(c); CHECK_ALIGN(Xm); CHECK_ALIGN(U); CHECK_ALIGN(M); CHECK_ALIGN(q);
+    CHECK_ALIGN(p); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(ws);
+#define X(a, b) if (nx == a && nu == b) return lqt_bwd_impl<a, b>(N, batch, A, B, c, Xm, U, M, q, p, ST, vT, Kx, d, S, v, pred, feasible, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_DIMS(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_lqt_fwd_f64(int N, int nx, int nu, int batch, const double* A, const double* B, const double* c,
+                     const double* Kx, const double* d, const double* x0, double* u, double* x, void* ws,
+                     size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && A && B && Kx && d && u && x && ws);
+    CHECK_ALIGN(A); CHECK_ALIGN(B); CHECK_ALIGN(c); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(u); CHECK_ALIGN(x);
+    CHECK_ALIGN(ws);
+#define X(a, b) if (nx == a && nu == b) return lqt_fwd_impl<a, b>(N, batch, A, B, c, Kx, d, x0, u, x, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_DIMS(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_affine_scan_f64(int reverse, int transpose, int N, int nx, int batch, const double* F, const double* c,
+                         const double* seed, double* out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && F && c && out && ws);
+    CHECK_ALIGN(F); CHECK_ALIGN(c); CHECK_ALIGN(out); CHECK_ALIGN(ws);
+#define X(a) if (nx == a) return affine_scan_impl<a>(reverse, transpose, N, batch, F, c, seed, out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_reductions_f64(int N, int nu, int nc, int batch, const double* ru, const double* cu, const double* cons,
+                        double* hu_norm, double* cu_norm, int32_t* traj_feasible, void* ws, size_t ws_bytes,
+                        ipoc_stream_t stream) {
+    (void)ws; (void)ws_bytes;
+    CHECK_ARGS(N >= 1 && batch >= 1);
+    CHECK_ARGS((ru == nullptr || hu_norm) && (cu == nullptr || cu_norm) && (cons == nullptr || traj_feasible));
+    k_reductions<<<batch, 256, 0, (cudaStream_t)stream>>>(ru, cu, cons, N, nu, nc, hu_norm, cu_norm, traj_feasible);
+    IPOC_LAUNCH_CHECK();
+    return IPOC_OK;
+}
+
+int ipoc_accept_update_f64(int batch, const double* cost, const double* new_cost, const int32_t* traj_feasible,
+                           const double* pred, const int32_t* bwd_feasible, const int32_t* active, double* rp,
+                           double* r_inc, int32_t* success, double* gain_ratio, ipoc_stream_t stream) {
+    CHECK_ARGS(batch >= 1 && cost && new_cost && traj_feasible && pred && bwd_feasible && rp && r_inc && success);
+    k_accept_update<<<grid_for(batch, 128), 128, 0, (cudaStream_t)stream>>>(batch, cost, new_cost, traj_feasible, pred,
+                                                                            bwd_feasible, active, rp, r_inc, success,
+                                                                            gain_ratio);
+    IPOC_LAUNCH_CHECK();
+    return IPOC_OK;
+}
+
+int ipoc_newton_bwd_reduce_f64(int N, int nx, int nu, const double* fx, const double* fu, const double* ru,
+                               const double* Q, const double* R, const double* M, const double* reg,
+                               double* carry_out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && fx && fu && ru && Q && R && M && reg && carry_out && ws);
+#define X(a, b) if (nx == a && nu == b) return newton_bwd_reduce_impl<a, b>(N, fx, fu, ru, Q, R, M, reg, carry_out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_DIMS(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_newton_bwd_apply_f64(int N, int nx, int nu, int rank, int nranks, const double* fx, const double* fu,
+                              const double* ru, const double* Q, const double* R, const double* M, const double* reg,
+                              const double* carries, const double* ST, double* Kx, double* d, double* pred,
+                              int32_t* feasible, double* fwd_carry_out, void* ws, size_t ws_bytes,
+                              ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && carries && ST && Kx && d && pred && feasible && fwd_carry_out && ws);
+#define X(a, b) if (nx == a && nu == b) return newton_bwd_apply_impl<a, b>(N, rank, nranks, fx, fu, ru, Q, R, M, reg, carries, ST, Kx, d, pred, feasible, fwd_carry_out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_DIMS(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_newton_fwd_apply_f64(int N, int nx, int nu, int rank, int nranks, const double* fx, const double* fu,
+                              const double* Kx, const double* d, const double* fwd_carries, double* dx, double* du,
+                              void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && fx && fu && Kx && d && fwd_carries && dx && du && ws);
+#define X(a, b) if (nx == a && nu == b) return newton_fwd_apply_impl<a, b>(N, rank, nranks, fx, fu, Kx, d, fwd_carries, dx, du, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_DIMS(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_affine_reduce_f64(int reverse, int transpose, int N, int nx, const double* F, const double* c,
+                           double* carry_out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && F && c && carry_out && ws);
+#define X(a) if (nx == a) return affine_reduce_impl<a>(reverse, transpose, N, F, c, carry_out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_affine_apply_f64(int reverse, int transpose, int N, int nx, int rank, int nranks, const double* F,
+                          const double* c, const double* carries, const double* seed, double* out, void* ws,
+                          size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && F && c && carries && seed && out && ws);
+#define X(a) if (nx == a) return affine_apply_impl<a>(reverse, transpose, N, rank, nranks, F, c, carries, seed, out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+size_t ipoc_newton_step_host_scratch_bytes(int N, int nx, int nu, int batch) {
+    const size_t per = (size_t)nx * nx * 2 + (size_t)nx * nu * 2 + (size_t)nu * nu + nu;   // inputs
+    const size_t outs = (size_t)nx + nu + (size_t)nu * nx + nu;
+    size_t b = ((size_t)N * per + (size_t)(N + 1) * outs) * batch * sizeof(double) + 64 * 256;
+    b += ipoc_workspace_bytes(IPOC_WS_NEWTON_STEP, N, nx, nu, batch) + 4096 * (size_t)batch;
+    return b;
+}
+
+int ipoc_newton_step_host_f64(int N, int nx, int nu, int batch, const double* fx, const double* fu, const double* ru,
+                              const double* Q, const double* R, const double* M, const double* reg, double* dx,
+                              double* du, double* pred, int32_t* feasible, void* dws, size_t dws_bytes,
+                              ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && dws);
+    if (dws_bytes < ipoc_newton_step_host_scratch_bytes(N, nx, nu, batch)) return IPOC_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    Bump bp{(char*)dws, 0, dws_bytes, false};
+    const size_t T = (size_t)N * batch;
+    double* dfx = bp.take<double>(T * nx * nx);
+    double* dfu = bp.take<double>(T * nx * nu);
+    double* dru = bp.take<double>(T * nu);
+    double* dQ = bp.take<double>(T * nx * nx);
+    double* dR = bp.take<double>(T * nu * nu);
+    double* dM = bp.take<double>(T * nx * nu);
+    double* dreg = bp.take<double>(batch);
+    double* ddx = bp.take<double>((size_t)(N + 1) * batch * nx);
+    double* ddu = bp.take<double>(T * nu);
+    double* dKx = bp.take<double>(T * nu * nx);
+    double* dd = bp.take<double>(T * nu);
+    double* dpred = bp.take<double>(batch);
+    int32_t* dfeas = bp.take<int32_t>(batch);
+    const size_t wsb = ipoc_workspace_bytes(IPOC_WS_NEWTON_STEP, N, nx, nu, batch);
+    void* ws = bp.take<char>(wsb);
+    if (bp.off > dws_bytes) return IPOC_EWORKSPACE;
+    const size_t D = sizeof(double);
+    bool ok = true;
+    ok &= cudaMemcpyAsync(dfx, fx, T * nx * nx * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dfu, fu, T * nx * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dru, ru, T * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dQ, Q, T * nx * nx * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dR, R, T * nu * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dM, M, T * nx * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dreg, reg, batch * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (!ok) return IPOC_ECUDA;
+    int rc = ipoc_newton_step_f64(N, nx, nu, batch, dfx, dfu, dru, dQ, dR, dM, dreg, ddx, ddu, dKx, dd, dpred, dfeas, ws,
+                                  wsb, stream);
+    if (rc) return rc;
+    ok &= cudaMemcpyAsync(dx, ddx, (size_t)(N + 1) * batch * nx * D, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(du, ddu, T * nu * D, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(pred, dpred, batch * D, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(feasible, dfeas, batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    return ok ? IPOC_OK : IPOC_ECUDA;
+}
+
+}  // extern "C"

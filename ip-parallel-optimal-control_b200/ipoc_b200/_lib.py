@@ -1,0 +1,118 @@
+"""ctypes binding of the C ABI in include/ipoc.h (libipoc.so, built in-tree by
+`__graft_entry__.build()`).  There is NO CPU fallback: if the shared library is missing or a
+tensor is not on a CUDA device, the call fails loudly."""
+import ctypes
+import os
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libipoc.so")
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_SZ = ctypes.c_size_t
+
+_SIGS = {
+    "ipoc_strerror": (ctypes.c_char_p, [_I]),
+    "ipoc_version": (_I, []),
+    "ipoc_supported": (_I, [_I, _I]),
+    "ipoc_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "ipoc_set_tuning": (None, [_I, _I, _I]),
+    "ipoc_launch_count": (ctypes.c_ulonglong, []),
+    "ipoc_carry_doubles": (_I, [_I, _I]),
+    "ipoc_newton_step_f64": (_I, [_I] * 4 + [_P] * 13 + [_P, _SZ, _P]),
+    "ipoc_lqt_bwd_f64": (_I, [_I] * 4 + [_P] * 16 + [_P, _SZ, _P]),
+    "ipoc_lqt_fwd_f64": (_I, [_I] * 4 + [_P] * 8 + [_P, _SZ, _P]),
+    "ipoc_affine_scan_f64": (_I, [_I] * 5 + [_P] * 4 + [_P, _SZ, _P]),
+    "ipoc_reductions_f64": (_I, [_I] * 4 + [_P] * 6 + [_P, _SZ, _P]),
+    "ipoc_accept_update_f64": (_I, [_I] + [_P] * 10 + [_P]),
+    "ipoc_newton_bwd_reduce_f64": (_I, [_I] * 3 + [_P] * 8 + [_P, _SZ, _P]),
+    "ipoc_newton_bwd_apply_f64": (_I, [_I] * 5 + [_P] * 14 + [_P, _SZ, _P]),
+    "ipoc_newton_fwd_apply_f64": (_I, [_I] * 5 + [_P] * 7 + [_P, _SZ, _P]),
+    "ipoc_affine_reduce_f64": (_I, [_I] * 4 + [_P] * 3 + [_P, _SZ, _P]),
+    "ipoc_affine_apply_f64": (_I, [_I] * 6 + [_P] * 5 + [_P, _SZ, _P]),
+    "ipoc_newton_step_host_scratch_bytes": (_SZ, [_I] * 4),
+    "ipoc_newton_step_host_f64": (_I, [_I] * 4 + [_P] * 11 + [_P, _SZ, _P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+WS_NEWTON_STEP, WS_LQT_BWD, WS_LQT_FWD, WS_AFFINE_SCAN, WS_REDUCTIONS = range(5)
+CARRY_RICCATI, CARRY_AFFINE = 0, 1
+
+_lib = None
+
+
+class IpocError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IpocError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  This package has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise IpocError(f"ipoc error {rc}: {lib().ipoc_strerror(rc).decode()}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous float64/int32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise IpocError("ipoc kernels need CUDA tensors; there is no CPU fallback")
+    if not t.is_contiguous():
+        raise IpocError("ipoc kernels need contiguous tensors")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def dev_f64(t, device=None):
+    """float64, contiguous, 16-byte aligned CUDA view/copy of t."""
+    t = torch.as_tensor(t)
+    if device is not None and t.device != torch.device(device):
+        t = t.to(device)
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_ws_cache = {}
+
+
+def workspace(kind, N, nx, nu, batch, device):
+    """Per-device scratch tensor, grown on demand and reused (the C library owns nothing)."""
+    need = lib().ipoc_workspace_bytes(kind, N, nx, nu, batch)
+    if need == 0:
+        raise IpocError(f"unsupported problem size (nx={nx}, nu={nu}): no kernel instantiated, no CPU fallback")
+    key = (torch.device(device).index or 0, kind)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf, need
+
+
+def require_supported(nx, nu):
+    if not lib().ipoc_supported(nx, nu):
+        raise IpocError(f"unsupported (nx={nx}, nu={nu}): no kernel instantiated and there is no CPU fallback")

@@ -1,0 +1,224 @@
+"""Host-side mirror of the reference's par IP-Newton interface
+(ref noc/par_interior_point_newton.py, noc/costates.py): same function names, argument meaning
+and return values, with torch CUDA tensors in place of jnp arrays.
+
+What runs where
+  * user functions (dynamics, costs, constraints) and their derivatives: the host framework
+    (`torch.func` vmapped autodiff on the GPU) — as in the reference, where JAX does it;
+  * everything the reference does with `lax.associative_scan` (costates, Riccati scan + gains,
+    forward scan) plus the accept/reject reductions: the sm_100a kernels behind include/ipoc.h.
+There is no CPU fallback; CPU tensors raise.
+"""
+import ctypes
+import torch
+from torch.func import vmap, grad, hessian, jacrev
+from . import _lib as L
+from .optimal_control_problem import OCP, Derivatives
+from .paroc import LQT, par_bwd_pass, par_fwd_pass  # noqa: F401  (re-exported, as the reference imports them)
+from .utils import rollout
+
+
+# ------------------------------------------------------------------ A1: derivatives (host framework)
+def compute_derivatives(ocp: OCP, states: torch.Tensor, controls: torch.Tensor, bp: float) -> Derivatives:
+    """ref noc/par_interior_point_newton.py:13-28.  Index order (output, wrt_1, wrt_2)."""
+    def body(x, u):
+        cx_k, cu_k = grad(ocp.stage_cost, (0, 1))(x, u, bp)
+        cxx_k = hessian(ocp.stage_cost, 0)(x, u, bp)
+        cuu_k = hessian(ocp.stage_cost, 1)(x, u, bp)
+        cxu_k = jacrev(jacrev(ocp.stage_cost, 0), 1)(x, u, bp)
+        fx_k, fu_k = jacrev(ocp.dynamics, (0, 1))(x, u)
+        fxx_k = jacrev(jacrev(ocp.dynamics, 0), 0)(x, u)
+        fuu_k = jacrev(jacrev(ocp.dynamics, 1), 1)(x, u)
+        fxu_k = jacrev(jacrev(ocp.dynamics, 0), 1)(x, u)
+        return cx_k, cu_k, cxx_k, cuu_k, cxu_k, fx_k, fu_k, fxx_k, fuu_k, fxu_k
+
+    return Derivatives(*(t.contiguous() for t in vmap(body)(states[:-1], controls)))
+
+
+# ------------------------------------------------------------------ A3: LQ parameters (host framework)
+def compute_lqr_params(lagrange_multipliers: torch.Tensor, d: Derivatives):
+    """ref noc/par_interior_point_newton.py:31-42 (tensordot contracts the OUTPUT index)."""
+    l = lagrange_multipliers[1:]
+    ru = d.cu + torch.einsum("tou,to->tu", d.fu, l)
+    Q = d.cxx + torch.einsum("to,toij->tij", l, d.fxx)
+    R = d.cuu + torch.einsum("to,toij->tij", l, d.fuu)
+    M = d.cxu + torch.einsum("to,toij->tij", l, d.fxu)
+    return ru.contiguous(), Q.contiguous(), R.contiguous(), M.contiguous()
+
+
+def check_traj_feasibility(ocp: OCP, x: torch.Tensor, u: torch.Tensor):
+    """ref noc/par_interior_point_newton.py:45-47 — `all(cons <= 0)` reduced by K4."""
+    cons = vmap(ocp.constraints)(x[:-1], u)
+    cons = L.dev_f64(cons.reshape(cons.shape[0], -1))
+    _, _, feas = reductions(cons=cons)
+    return feas[0] != 0
+
+
+# ------------------------------------------------------------------ K1: costates
+def affine_scan(F, c, seed, reverse=False, transpose=False):
+    """out[0]=seed, out[k+1]=F_k out[k]+c_k  (reverse: out[N]=seed, out[k]=F_k(') out[k+1]+c_k)."""
+    F, c = L.dev_f64(F), L.dev_f64(c)
+    seed = L.dev_f64(seed, F.device)
+    batched = F.dim() == 4
+    if not batched:
+        F, c, seed = F.unsqueeze(0), c.unsqueeze(0), seed.unsqueeze(0)
+    Bn, N, nx = F.shape[0], F.shape[1], F.shape[2]
+    out = torch.empty(Bn, N + 1, nx, dtype=torch.float64, device=F.device)
+    ws, nbytes = L.workspace(L.WS_AFFINE_SCAN, N, nx, 1, Bn, F.device)
+    with torch.cuda.device(F.device):
+        L.check(L.lib().ipoc_affine_scan_f64(int(reverse), int(transpose), N, nx, Bn, L.ptr(F), L.ptr(c),
+                                             L.ptr(seed.contiguous()), L.ptr(out), L.ptr(ws), nbytes, L.stream_ptr()))
+    return out if batched else out[0]
+
+
+def par_costates(ocp: OCP, final_state: torch.Tensor, d: Derivatives):
+    """ref noc/costates.py:34-40: lambda_N = grad final_cost(x_N), lambda_k = cx_k + fx_k' lambda_{k+1}."""
+    lamda_T = grad(ocp.final_cost)(final_state)
+    return affine_scan(d.fx, d.cx, lamda_T, reverse=True, transpose=True)
+
+
+# ------------------------------------------------------------------ A4 (API completeness)
+def noc_to_lqt(ru, Q, R, M, A, B) -> LQT:
+    """ref noc/par_interior_point_newton.py:50-84.  `par_Newton` below does NOT call this (the fused
+    kernel forms r, s per step in registers and never materialises the identity stacks); it exists so
+    that code written against the reference's helper keeps working."""
+    T, nx, nu = Q.shape[0], Q.shape[1], R.shape[1]
+    X_inv_M = torch.linalg.solve(Q, M)
+    s = -torch.linalg.solve(R - M.transpose(1, 2) @ X_inv_M, ru.unsqueeze(-1)).squeeze(-1)
+    r = -(X_inv_M @ s.unsqueeze(-1)).squeeze(-1)
+    o = dict(dtype=Q.dtype, device=Q.device)
+    eye = lambda n: torch.eye(n, **o).expand(T, n, n).contiguous()
+    return LQT(A, B, torch.zeros(T, nx, **o), Q[0], torch.eye(nx, **o), torch.zeros(nx, **o),
+               Q, eye(nx), r, R, eye(nu), s, M)
+
+
+# ------------------------------------------------------------------ K4 / A8
+def reductions(ru=None, cu=None, cons=None):
+    """(max|ru|, ||cu||_F, all(cons<=0)) per problem — ref :158, :116, :45-47.  Inputs (N,·) or (B,N,·)."""
+    ref = next(t for t in (ru, cu, cons) if t is not None)
+    dev = ref.device
+    batched = ref.dim() == 3
+    prep = lambda t: None if t is None else (L.dev_f64(t) if batched else L.dev_f64(t).unsqueeze(0))
+    ru, cu, cons = prep(ru), prep(cu), prep(cons)
+    ref = next(t for t in (ru, cu, cons) if t is not None)
+    Bn, N = ref.shape[0], ref.shape[1]
+    nu = (ru if ru is not None else cu).shape[2] if (ru is not None or cu is not None) else 1
+    nc = cons.shape[2] if cons is not None else 1
+    hu = torch.zeros(Bn, dtype=torch.float64, device=dev)
+    cn = torch.zeros(Bn, dtype=torch.float64, device=dev)
+    fe = torch.ones(Bn, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().ipoc_reductions_f64(N, nu, nc, Bn, L.ptr(ru), L.ptr(cu), L.ptr(cons), L.ptr(hu), L.ptr(cn),
+                                            L.ptr(fe), None, 0, L.stream_ptr()))
+    return hu, cn, fe
+
+
+def accept_update(cost, new_cost, traj_feasible, pred, bwd_feasible, rp, r_inc, active=None):
+    """In-place device update of (rp, r_inc); returns (success int32, gain_ratio) — ref :159-173."""
+    Bn = rp.numel()
+    dev = rp.device
+    success = torch.zeros(Bn, dtype=torch.int32, device=dev)
+    gain = torch.zeros(Bn, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().ipoc_accept_update_f64(Bn, L.ptr(cost), L.ptr(new_cost), L.ptr(traj_feasible), L.ptr(pred),
+                                               L.ptr(bwd_feasible), L.ptr(active), L.ptr(rp), L.ptr(r_inc),
+                                               L.ptr(success), L.ptr(gain), L.stream_ptr()))
+    return success, gain
+
+
+# ------------------------------------------------------------------ K2 + K3: the Newton step
+def newton_step(fx, fu, ru, Q, R, M, reg):
+    """Fused device Newton step on LQ data; `reg` is a device tensor (one value per problem).
+    -> dx, du, Kx, d, pred (B,), feasible (B,) int32.  Accepts (N,...) or (B,N,...)."""
+    fx, fu, ru, Q, R, M = (L.dev_f64(t) for t in (fx, fu, ru, Q, R, M))
+    dev = fx.device
+    batched = fx.dim() == 4
+    if not batched:
+        fx, fu, ru, Q, R, M = (t.unsqueeze(0) for t in (fx, fu, ru, Q, R, M))
+    Bn, N, nx = fx.shape[0], fx.shape[1], fx.shape[2]
+    nu = fu.shape[-1]
+    L.require_supported(nx, nu)
+    reg = L.dev_f64(reg, dev).reshape(-1)
+    if reg.numel() != Bn:
+        reg = reg.expand(Bn).contiguous()
+    o = dict(dtype=torch.float64, device=dev)
+    dx = torch.empty(Bn, N + 1, nx, **o)
+    du = torch.empty(Bn, N, nu, **o)
+    Kx = torch.empty(Bn, N, nu, nx, **o)
+    d = torch.empty(Bn, N, nu, **o)
+    pred = torch.empty(Bn, **o)
+    feas = torch.empty(Bn, dtype=torch.int32, device=dev)
+    ws, nbytes = L.workspace(L.WS_NEWTON_STEP, N, nx, nu, Bn, dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().ipoc_newton_step_f64(N, nx, nu, Bn, L.ptr(fx), L.ptr(fu), L.ptr(ru), L.ptr(Q), L.ptr(R),
+                                             L.ptr(M), L.ptr(reg), L.ptr(dx), L.ptr(du), L.ptr(Kx), L.ptr(d),
+                                             L.ptr(pred), L.ptr(feas), L.ptr(ws), nbytes, L.stream_ptr()))
+    if not batched:
+        return dx[0], du[0], Kx[0], d[0], pred, feas
+    return dx, du, Kx, d, pred, feas
+
+
+def par_Newton(nominal_states, d: Derivatives, reg_param, ru, Q, R, M):
+    """ref noc/par_interior_point_newton.py:107-124 -> (dx, du, pred_reduction, feasible, ru).
+    `nominal_states` is only used for its shape in the reference (:122); the initial deviation is 0."""
+    _, cu_norm, _ = reductions(cu=d.cu)                      # :116
+    reg = torch.as_tensor(reg_param, dtype=torch.float64, device=cu_norm.device) * cu_norm   # :117
+    dx, du, _, _, pred, feas = newton_step(d.fx, d.fu, ru, Q, R, M, reg)    # :118-123
+    return dx, du, pred[0], feas[0] != 0, ru
+
+
+# ------------------------------------------------------------------ driver loops
+def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, barrier_param: float, trace=None,
+              stage: int = 0):
+    """ref noc/par_interior_point_newton.py:127-225 -> (opt_x, opt_u, iterations).
+    The scalar accept/reject state (rp, r_inc, success) lives on the device; the host reads one
+    small record per attempt to steer the Python loop."""
+    dev = controls.device
+    u = L.dev_f64(controls)
+    x = rollout(ocp.dynamics, u, initial_state.to(dev))                 # :133
+    o = dict(dtype=torch.float64, device=dev)
+    rp = torch.ones(1, **o)                                              # :134
+    r_inc = torch.full((1,), 2.0, **o)                                   # :135
+    iteration, Hu_norm = 0, 1.0
+    while not (Hu_norm < 1e-4 or iteration > 1000):                      # :199-202
+        cost = ocp.total_cost(x, u, barrier_param).reshape(1)            # :142
+        d = compute_derivatives(ocp, x, u, barrier_param)                # :145
+        lam = par_costates(ocp, x[-1], d)                                # :147
+        ru, Q, R, M = compute_lqr_params(lam, d)                         # :149
+        hu, cu_norm, _ = reductions(ru=ru, cu=d.cu)                      # :158 (pre-step ru), :116
+        success, inner = False, 0
+        tx, tu = x, u
+        while not (success or inner > 500):                              # :177-182
+            dx, du, _, _, pred, bwd_feas = newton_step(d.fx, d.fu, ru, Q, R, M, rp * cu_norm)   # :153
+            tu = u + du                                                  # :156
+            tx = x + dx                                                  # :157
+            cons = vmap(ocp.constraints)(tx[:-1], tu)                    # :160
+            _, _, traj_feas = reductions(cons=cons.reshape(cons.shape[0], -1))
+            new_cost = ocp.total_cost(tx, tu, barrier_param).reshape(1)  # :161 (masked to inf by A8)
+            rp_before = rp.clone() if trace is not None else None
+            succ, gain = accept_update(cost, new_cost, traj_feas, pred, bwd_feas, rp, r_inc)    # :159-173
+            inner += 1                                                   # :174
+            rec = torch.stack((succ[0].to(torch.float64), hu[0])).cpu()  # the one host read per attempt
+            success, Hu_norm = bool(rec[0] != 0), float(rec[1])
+            if trace is not None:
+                trace.append(dict(stage=stage, iteration=iteration, attempt=inner, cost=float(cost),
+                                  new_cost=float(new_cost) if bool(traj_feas[0]) else float("inf"),
+                                  pred=float(pred), gain_ratio=float(gain), success=success,
+                                  rp=float(rp_before), Hu_norm=Hu_norm))
+        x, u = tx, tu                                                    # :184 (taken even if never successful)
+        iteration += 1                                                   # :194
+    return x, u, iteration
+
+
+def par_interior_point_optimal_control(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, trace=None):
+    """ref noc/par_interior_point_newton.py:228-254 -> (opt_u, N_iterations)."""
+    if not controls.is_cuda:
+        raise L.IpocError("par_interior_point_optimal_control needs CUDA tensors; there is no CPU fallback")
+    u = controls
+    bp, total, stage = 0.1, 0, 0                                         # :233
+    while bp > 1e-4:                                                     # :243-245
+        _, u, its = newton_oc(ocp, u, initial_state, bp, trace, stage)   # :237
+        bp = bp / 5                                                      # :238
+        total += its                                                     # :239
+        stage += 1
+    return u, total

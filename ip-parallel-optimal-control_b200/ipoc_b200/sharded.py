@@ -1,0 +1,132 @@
+"""Multi-GPU modes (no reference counterpart — the reference is single-device).
+
+time-sharded: a long horizon is cut into P contiguous segments, one per rank.  Each scan is
+    local reduce  ->  all-gather of the P segment aggregates (NCCL over NVLink; <= 448 B per rank
+    for nx = 4, i.e. latency-bound)  ->  local seeded scan.
+    The exchange is injected as a callable so that the same code runs with torch.distributed
+    (NCCL on the GPU box, gloo in CPU tests of the plumbing) or with P "virtual ranks" on one GPU.
+batch-sharded: independent OCPs are split across ranks with no communication at all
+    (`shard_batch`).
+"""
+import torch
+from . import _lib as L
+
+
+def carry_doubles(kind, nx):
+    return L.lib().ipoc_carry_doubles(kind, nx)
+
+
+class SegmentNewton:
+    """One rank's share of a time-sharded Newton step (K2 + K3) on its contiguous segment."""
+
+    def __init__(self, fx, fu, ru, Q, R, M, rank, nranks):
+        self.fx, self.fu, self.ru, self.Q, self.R, self.M = (L.dev_f64(t) for t in (fx, fu, ru, Q, R, M))
+        self.rank, self.nranks = rank, nranks
+        self.N, self.nx = self.fx.shape[0], self.fx.shape[1]
+        self.nu = self.fu.shape[-1]
+        L.require_supported(self.nx, self.nu)
+        self.dev = self.fx.device
+        need = L.lib().ipoc_workspace_bytes(L.WS_NEWTON_STEP, self.N, self.nx, self.nu, 1)
+        # private workspace: the leaf aggregates of phase 1 are reused by phase 2
+        self.ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        self.nbytes = need
+        o = dict(dtype=torch.float64, device=self.dev)
+        self.Kx = torch.empty(self.N, self.nu, self.nx, **o)
+        self.d = torch.empty(self.N, self.nu, **o)
+        self.dx = torch.empty(self.N + 1, self.nx, **o)
+        self.du = torch.empty(self.N, self.nu, **o)
+        self.pred = torch.empty(1, **o)
+        self.feas = torch.empty(1, dtype=torch.int32, device=self.dev)
+
+    def bwd_reduce(self, reg):
+        self.reg = L.dev_f64(reg, self.dev).reshape(1)
+        carry = torch.empty(carry_doubles(L.CARRY_RICCATI, self.nx), dtype=torch.float64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().ipoc_newton_bwd_reduce_f64(
+                self.N, self.nx, self.nu, L.ptr(self.fx), L.ptr(self.fu), L.ptr(self.ru), L.ptr(self.Q), L.ptr(self.R),
+                L.ptr(self.M), L.ptr(self.reg), L.ptr(carry), L.ptr(self.ws), self.nbytes, L.stream_ptr()))
+        return carry
+
+    def bwd_apply(self, carries, ST):
+        """carries (P, ESZ) gathered aggregates; ST (nx,nx) terminal weight of the whole horizon."""
+        fwd_carry = torch.empty(carry_doubles(L.CARRY_AFFINE, self.nx), dtype=torch.float64, device=self.dev)
+        carries, ST = L.dev_f64(carries, self.dev), L.dev_f64(ST, self.dev)
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().ipoc_newton_bwd_apply_f64(
+                self.N, self.nx, self.nu, self.rank, self.nranks, L.ptr(self.fx), L.ptr(self.fu), L.ptr(self.ru),
+                L.ptr(self.Q), L.ptr(self.R), L.ptr(self.M), L.ptr(self.reg), L.ptr(carries), L.ptr(ST),
+                L.ptr(self.Kx), L.ptr(self.d), L.ptr(self.pred), L.ptr(self.feas), L.ptr(fwd_carry), L.ptr(self.ws),
+                self.nbytes, L.stream_ptr()))
+        return fwd_carry
+
+    def fwd_apply(self, fwd_carries):
+        fwd_carries = L.dev_f64(fwd_carries, self.dev)
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().ipoc_newton_fwd_apply_f64(
+                self.N, self.nx, self.nu, self.rank, self.nranks, L.ptr(self.fx), L.ptr(self.fu), L.ptr(self.Kx),
+                L.ptr(self.d), L.ptr(fwd_carries), L.ptr(self.dx), L.ptr(self.du), L.ptr(self.ws), self.nbytes,
+                L.stream_ptr()))
+        return self.dx, self.du
+
+
+def newton_step_time_sharded(seg: SegmentNewton, reg, ST, all_gather):
+    """Collective Newton step.  `all_gather(t)` returns the (P, len) stack of every rank's `t`.
+    `ST`: terminal weight (= Q[0] of the global horizon, ref noc/par_interior_point_newton.py:73),
+    identical on all ranks.  Returns this rank's (dx, du, pred_total, feasible_all)."""
+    carries = all_gather(seg.bwd_reduce(reg))                    # exchange 1: Riccati aggregates
+    fwd_carry = seg.bwd_apply(carries, ST)
+    scal = torch.cat((fwd_carry, seg.pred, seg.feas.to(torch.float64)))
+    gathered = all_gather(scal)                                  # exchange 2: forward aggregates + scalars
+    na = fwd_carry.numel()
+    dx, du = seg.fwd_apply(gathered[:, :na].contiguous())
+    pred = gathered[:, na].sum()                                 # fixed rank order -> deterministic
+    feas = bool(torch.all(gathered[:, na + 1] != 0))
+    return dx, du, pred, feas
+
+
+def dist_all_gather(group=None):
+    """all_gather callable on torch.distributed (NCCL on GPUs, gloo for CPU plumbing tests)."""
+    import torch.distributed as dist
+
+    def gather(t):
+        P = dist.get_world_size(group)
+        out = torch.empty((P,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        return out
+
+    return gather
+
+
+def segment_bounds(N, nranks):
+    """Contiguous, near-equal time segments [lo, hi) per rank."""
+    base, rem = divmod(N, nranks)
+    bounds, lo = [], 0
+    for r in range(nranks):
+        hi = lo + base + (1 if r < rem else 0)
+        bounds.append((lo, hi))
+        lo = hi
+    return bounds
+
+
+def shard_batch(batch, rank, nranks):
+    """[lo, hi) of the independent problems owned by `rank` (no data-path collective needed)."""
+    return segment_bounds(batch, nranks)[rank]
+
+
+def newton_step_virtual_ranks(fx, fu, ru, Q, R, M, reg, nranks):
+    """Run the time-sharded algorithm with `nranks` virtual ranks on ONE GPU (sequentially, fake
+    all-gather) — the single-GPU test of the multi-GPU path."""
+    N = fx.shape[0]
+    segs = [SegmentNewton(fx[lo:hi], fu[lo:hi], ru[lo:hi], Q[lo:hi], R[lo:hi], M[lo:hi], r, nranks)
+            for r, (lo, hi) in enumerate(segment_bounds(N, nranks))]
+    ST = Q[0]
+    carries = torch.stack([s.bwd_reduce(reg) for s in segs])
+    fwd = torch.stack([s.bwd_apply(carries, ST) for s in segs])
+    outs = [s.fwd_apply(fwd) for s in segs]
+    dx = torch.cat([o[0][:-1] for o in outs[:-1]] + [outs[-1][0]])
+    du = torch.cat([o[1] for o in outs])
+    pred = torch.stack([s.pred[0] for s in segs]).sum()
+    feas = all(bool(s.feas[0] != 0) for s in segs)
+    Kx = torch.cat([s.Kx for s in segs])
+    d = torch.cat([s.d for s in segs])
+    return dx, du, Kx, d, pred, feas

@@ -1,0 +1,302 @@
+"""GPU parity tests proper: the sm_100a kernels (through the C ABI / ctypes) against the CPU
+oracle on the same seeded inputs, against the golden fixtures produced by the reference's own
+source, and — at full size — through size-independent properties (KKT residuals of the Newton
+step, agreement of differently-chunked scans).
+
+Tolerances: the north-star asks for <= 1e-9 relative on states, controls and cost and an identical
+Newton iteration count.  Kernel-vs-oracle comparisons here are held to much tighter bounds
+(1e-11 .. 1e-12) where the conditioning allows."""
+import ctypes
+import numpy as np
+import pytest
+import torch
+
+from helpers import STEP_FIXTURES, derivs_from_golden, relerr, random_lq
+from oracle import noc_np, paroc_np
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)
+
+
+def N_(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(autouse=True)
+def _reset_tuning():
+    from ipoc_b200 import _lib
+    _lib.lib().ipoc_set_tuning(0, 0, 0)
+    yield
+    _lib.lib().ipoc_set_tuning(0, 0, 0)
+
+
+def oracle_newton(fx, fu, ru, Q, R, M, reg):
+    nu = R.shape[1]
+    lqt = noc_np.noc_to_lqt(ru, Q, R + reg * np.eye(nu)[None], M, fx, fu)
+    Kx, d, S, v, pred, feas = paroc_np.par_bwd_pass(lqt)
+    du, dx = paroc_np.par_fwd_pass(lqt, np.zeros(fx.shape[1]), Kx, d)
+    return dx, du, Kx, d, pred, feas
+
+
+def test_library_loaded_and_supported():
+    from ipoc_b200 import _lib
+    L = _lib.lib()
+    assert L.ipoc_version() >= 100
+    assert L.ipoc_supported(2, 1) and L.ipoc_supported(4, 1) and not L.ipoc_supported(5, 3)
+    assert b"no CPU fallback" in L.ipoc_strerror(-1)
+
+
+@pytest.mark.parametrize("nx,nu", [(2, 1), (4, 1), (3, 1), (2, 2), (4, 2), (1, 1), (6, 1), (8, 1)])
+@pytest.mark.parametrize("N", [1, 2, 3, 31, 32, 33, 500])
+def test_newton_step_vs_oracle(nx, nu, N):
+    from ipoc_b200 import noc
+    rng = np.random.default_rng(1000 * nx + 100 * nu + N)
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu)
+    reg = 0.37
+    dxo, duo, Kxo, do, predo, feaso = oracle_newton(fx, fu, ru, Q, R, M, reg)
+    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), torch.tensor([reg], device=DEV))
+    tol = 1e-11 if nx <= 4 else 1e-10
+    assert relerr(N_(Kx), Kxo) < tol and relerr(N_(d), do) < tol
+    assert relerr(N_(dx), dxo) < tol and relerr(N_(du), duo) < tol
+    assert abs(float(pred) - predo) <= tol * abs(predo)
+    assert bool(feas[0]) == bool(feaso)
+
+
+@pytest.mark.parametrize("tuning", [(1, 2, 4), (3, 3, 8), (4, 4, 32), (16, 8, 64), (0, 0, 0)])
+@pytest.mark.parametrize("nx,nu,N", [(2, 1, 1000), (4, 1, 10000), (4, 2, 777)])
+def test_newton_step_all_hierarchy_shapes(tuning, nx, nu, N):
+    """Every way of cutting the horizon (leaf chunk / mid fan-in / top width) gives the same step."""
+    from ipoc_b200 import noc, _lib
+    rng = np.random.default_rng(7 * nx + N)
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu)
+    dxo, duo, Kxo, do, predo, feaso = oracle_newton(fx, fu, ru, Q, R, M, 0.05)
+    _lib.lib().ipoc_set_tuning(*tuning)
+    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), torch.tensor([0.05], device=DEV))
+    assert relerr(N_(dx), dxo) < 1e-10 and relerr(N_(du), duo) < 1e-10
+    assert relerr(N_(Kx), Kxo) < 1e-10 and relerr(N_(d), do) < 1e-10
+    assert abs(float(pred) - predo) <= 1e-10 * abs(predo) and bool(feas[0]) == bool(feaso)
+
+
+@pytest.mark.parametrize("name", STEP_FIXTURES)
+def test_newton_step_vs_reference_fixtures(golden, name):
+    """Real pendulum / cartpole linearisations; expected values computed by the reference's own
+    sequential Newton step (ref noc/seq_interior_point_newton.py:42-90) run from its source."""
+    from ipoc_b200 import noc
+    from ipoc_b200.optimal_control_problem import Derivatives
+    g = golden(name)
+    d = Derivatives(*(T(g["d_" + f]) for f in Derivatives._fields))
+    dx, du, pred, feas, ru = noc.par_Newton(T(g["states"]), d, float(g["reg_param"]), T(g["ref_ru"]), T(g["ref_Q"]),
+                                            T(g["ref_R"]), T(g["ref_M"]))
+    assert relerr(N_(dx), g["ref_seq_dx"]) < 1e-9 and relerr(N_(du), g["ref_seq_du"]) < 1e-9
+    assert relerr(N_(dx), g["refp_dx"]) < 1e-10 and relerr(N_(du), g["refp_du"]) < 1e-10
+    assert abs(float(pred) - float(g["ref_seq_dV"])) <= 1e-10 * abs(float(g["ref_seq_dV"]))
+    assert bool(feas) == bool(g["ref_seq_convex"])
+    # costates (K1) and LQ parameters
+    lam = noc.affine_scan(d.fx, d.cx, T(g["ref_lamT"]), reverse=True, transpose=True)
+    assert relerr(N_(lam), g["ref_costates_par"]) < 1e-12
+    ru2, Q2, R2, M2 = noc.compute_lqr_params(lam, d)
+    assert relerr(N_(Q2), g["ref_Q"]) < 1e-12 and relerr(N_(ru2), g["ref_ru"]) < 1e-12
+    # K4 reductions on the stepped trajectory
+    hu, cn, fe = noc.reductions(ru=T(g["ref_ru"]), cu=d.cu, cons=T(g["ref_new_cons"]))
+    assert float(hu) == float(np.max(np.abs(g["ref_ru"])))
+    assert abs(float(cn) - np.linalg.norm(g["d_cu"].ravel())) < 1e-13 * float(cn)
+    assert bool(fe[0]) == bool(g["ref_new_feasible"])
+
+
+@pytest.mark.parametrize("reverse,transpose", [(False, False), (True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("nx,N", [(2, 1), (2, 500), (4, 33), (4, 10001), (3, 257), (8, 100)])
+def test_affine_scan_vs_serial(reverse, transpose, nx, N):
+    from ipoc_b200 import noc
+    rng = np.random.default_rng(nx + N)
+    F = np.eye(nx) + (2.0 / max(N, 8)) * rng.standard_normal((N, nx, nx))
+    c = rng.standard_normal((N, nx))
+    seed = rng.standard_normal(nx)
+    out = np.zeros((N + 1, nx))
+    Fe = np.swapaxes(F, 1, 2) if transpose else F
+    if reverse:
+        out[N] = seed
+        for k in range(N - 1, -1, -1):
+            out[k] = Fe[k] @ out[k + 1] + c[k]
+    else:
+        out[0] = seed
+        for k in range(N):
+            out[k + 1] = Fe[k] @ out[k] + c[k]
+    got = noc.affine_scan(T(F), T(c), T(seed), reverse=reverse, transpose=transpose)
+    assert relerr(N_(got), out) < 1e-11
+
+
+@pytest.mark.parametrize("nx,nu,N", [(2, 1, 5), (2, 1, 600), (4, 1, 129), (4, 2, 64), (3, 1, 40)])
+def test_raw_lqt_api_vs_oracle(nx, nu, N):
+    """`par_bwd_pass` / `par_fwd_pass` with everything switched on: c != 0, rT != 0, r, s != 0,
+    x0 != 0, non-identity H and Z."""
+    from ipoc_b200.paroc import LQT, par_bwd_pass, par_fwd_pass
+    rng = np.random.default_rng(nx * 31 + nu * 7 + N)
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu)
+    H = np.eye(nx) + 0.1 * rng.standard_normal((N, nx, nx))
+    Z = np.eye(nu) + 0.1 * rng.standard_normal((N, nu, nu))
+    lq = paroc_np.LQT(fx, fu, 0.05 * rng.standard_normal((N, nx)), Q[0] + np.eye(nx),
+                      np.eye(nx) + 0.1 * rng.standard_normal((nx, nx)), rng.standard_normal(nx), Q, H,
+                      rng.standard_normal((N, nx)), R, Z, rng.standard_normal((N, nu)), M)
+    Kxo, do, So, vo, predo, feaso = paroc_np.par_bwd_pass(lq)
+    x0 = rng.standard_normal(nx)
+    uo, xo = paroc_np.par_fwd_pass(lq, x0, Kxo, do)
+    lqt = LQT(*(T(a) for a in lq))
+    Kx, d, S, v, pred, feas = par_bwd_pass(lqt)
+    u, x = par_fwd_pass(lqt, T(x0), Kx, d)
+    for got, exp in ((Kx, Kxo), (d, do), (S, So), (v, vo), (u, uo), (x, xo)):
+        assert relerr(N_(got), exp) < 1e-10
+    assert abs(float(pred) - predo) <= 1e-10 * abs(predo) and bool(feas) == bool(feaso)
+
+
+def test_mpc_example_par_equals_seq():
+    """BASELINE config 3 as written (ref examples/linear_mpc_parallel.py:24-81): receding-horizon
+    loop of par_bwd_pass + par_fwd_pass, T = 5; the reference's intent is par == seq."""
+    from ipoc_b200 import problems
+    from ipoc_b200.paroc import LQT, par_bwd_pass, par_fwd_pass
+    fields, x0 = problems.make_mpc_lqt_terms(T=5, device=DEV)
+    lqt = LQT(*fields)
+    lq_np = paroc_np.LQT(*(N_(f) for f in fields))
+    steps = 300
+    x, xs_par, us_par = x0, [], []
+    for _ in range(steps):
+        Kx, d, _, _, _, _ = par_bwd_pass(lqt)
+        u_par, x_par = par_fwd_pass(lqt, x, Kx, d)
+        x = x_par[1]
+        xs_par.append(x)
+        us_par.append(u_par[0])
+    xs_par, us_par = N_(torch.stack(xs_par)), N_(torch.stack(us_par))
+    xk, xs_seq, us_seq = N_(x0), [], []
+    Kxs, ds, _, _ = paroc_np.seq_bwd_pass(lq_np)
+    for _ in range(steps):
+        u_seq, x_seq = paroc_np.seq_fwd_pass(lq_np, xk, Kxs, ds)
+        xk = x_seq[1]
+        xs_seq.append(xk)
+        us_seq.append(u_seq[0])
+    assert relerr(xs_par, np.array(xs_seq)) < 1e-10 and relerr(us_par, np.array(us_seq)) < 1e-10
+
+
+@pytest.mark.parametrize("nx,nu,N,B", [(2, 1, 100, 7), (4, 1, 64, 33), (2, 1, 1000, 40000)])
+def test_batched_equals_unbatched(nx, nu, N, B):
+    """Independent OCPs stacked on a batch axis give each problem the result of solving it alone."""
+    from ipoc_b200 import noc
+    rng = np.random.default_rng(B)
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu, batch=B)
+    reg = 0.1 + rng.random(B)
+    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), T(reg))
+    for b in list(range(min(B, 3))) + [B - 1]:
+        dxo, duo, Kxo, do, predo, feaso = oracle_newton(fx[b], fu[b], ru[b], Q[b], R[b], M[b], reg[b])
+        assert relerr(N_(dx[b]), dxo) < 1e-10 and relerr(N_(du[b]), duo) < 1e-10
+        assert abs(float(pred[b]) - predo) <= 1e-10 * abs(predo) and bool(feas[b]) == bool(feaso)
+        dx1, du1, _, _, pred1, _ = noc.newton_step(T(fx[b]), T(fu[b]), T(ru[b]), T(Q[b]), T(R[b]), T(M[b]),
+                                                   T(reg[b:b + 1]))
+        assert relerr(N_(dx[b]), N_(dx1)) < 1e-11 and relerr(N_(du[b]), N_(du1)) < 1e-11
+
+
+@pytest.mark.parametrize("P", [2, 3, 8])
+@pytest.mark.parametrize("nx,nu,N", [(4, 1, 1003), (2, 1, 64)])
+def test_time_sharded_virtual_ranks(P, nx, nu, N):
+    """The multi-GPU time-sharded algorithm (reduce -> exchange carries -> seeded scan) run with P
+    virtual ranks on one GPU equals the single-device scan."""
+    from ipoc_b200 import noc, sharded
+    rng = np.random.default_rng(P + N)
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu)
+    reg = torch.tensor([0.2], device=DEV)
+    args = [T(a) for a in (fx, fu, ru, Q, R, M)]
+    dx1, du1, Kx1, d1, pred1, feas1 = noc.newton_step(*args, reg)
+    dx, du, Kx, d, pred, feas = sharded.newton_step_virtual_ranks(*args, reg, P)
+    assert relerr(N_(Kx), N_(Kx1)) < 1e-11 and relerr(N_(d), N_(d1)) < 1e-11
+    assert relerr(N_(dx), N_(dx1)) < 1e-11 and relerr(N_(du), N_(du1)) < 1e-11
+    assert abs(float(pred) - float(pred1)) <= 1e-11 * abs(float(pred1)) and feas == bool(feas1[0])
+
+
+def _kkt_residuals(fx, fu, ru, Q, R, M, reg, dx, du):
+    """Size-independent check: (dx, du) solves the regularised LQ Newton system
+    (dynamics + stationarity with costates p_k = Q dx + M du + fx' p_{k+1}, p_N = Q[0] dx_N)."""
+    N, nu = fx.shape[0], R.shape[1]
+    dyn = dx[1:] - np.einsum("tij,tj->ti", fx, dx[:-1]) - np.einsum("tij,tj->ti", fu, du)
+    p = Q[0] @ dx[N]
+    stat = np.zeros((N, nu))
+    for k in range(N - 1, -1, -1):
+        stat[k] = ru[k] + (R[k] + reg * np.eye(nu)) @ du[k] + M[k].T @ dx[k] + fu[k].T @ p
+        p = Q[k] @ dx[k] + M[k] @ du[k] + fx[k].T @ p
+    scale = max(1.0, np.max(np.abs(ru)))
+    return np.max(np.abs(dyn)), np.max(np.abs(stat)) / scale, np.max(np.abs(dx[0]))
+
+
+@pytest.mark.parametrize("nx,nu,N", [(4, 1, 100000), (2, 1, 300000)])
+def test_newton_step_kkt_at_full_size(nx, nu, N):
+    from ipoc_b200 import noc
+    rng = np.random.default_rng(N)
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu, dt=1e-3)
+    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), torch.tensor([0.3], device=DEV))
+    r_dyn, r_stat, r_x0 = _kkt_residuals(fx, fu, ru, Q, R, M, 0.3, N_(dx), N_(du))
+    assert r_x0 == 0.0 and r_dyn < 1e-9 and r_stat < 1e-8
+    assert bool(feas[0]) and float(pred) < 0
+
+
+def test_nonconvex_and_nan_are_data_not_errors():
+    from ipoc_b200 import noc
+    rng = np.random.default_rng(3)
+    fx, fu, ru, Q, R, M = random_lq(rng, 50, 2, 1)
+    R[17] = -5.0   # G < 0 at one step -> infeasible flag, no exception
+    _, _, _, _, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), torch.tensor([0.0], device=DEV))
+    assert not bool(feas[0])
+    ru[3] = np.nan
+    _, du, _, _, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), torch.tensor([0.0], device=DEV))
+    assert np.isnan(float(pred))
+
+
+def test_accept_update_matches_reference_rule():
+    from ipoc_b200 import noc
+    cost = T([10.0, 10.0, 10.0, 10.0, 10.0])
+    new = T([9.0, 11.0, 9.0, 9.5, np.nan])
+    traj = torch.tensor([1, 1, 0, 1, 1], dtype=torch.int32, device=DEV)
+    pred = T([-2.0, -2.0, -2.0, -0.4, -1.0])
+    bwd = torch.tensor([1, 1, 1, 0, 1], dtype=torch.int32, device=DEV)
+    rp = T([1.0, 1.0, 1.0, 1.0, 1.0])
+    ri = T([2.0, 2.0, 4.0, 2.0, 2.0])
+    succ, gain = noc.accept_update(cost, new, traj, pred, bwd, rp, ri)
+    exp_rp, exp_ri, exp_s = [], [], []
+    for c, n, t, p, b, r, i in zip([10.0] * 5, [9.0, 11.0, 9.0, 9.5, np.nan], [1, 1, 0, 1, 1],
+                                   [-2.0, -2.0, -2.0, -0.4, -1.0], [1, 1, 1, 0, 1], [1.0] * 5, [2.0, 2.0, 4.0, 2.0, 2.0]):
+        nc = n if t else np.inf
+        rho = (nc - c) / p
+        ok = bool(rho > 0) and bool(b)
+        r2 = r * max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3) if ok else r * i
+        exp_rp.append(min(max(r2, 1e-16), 1e16))
+        exp_ri.append(2.0 if ok else 2 * i)
+        exp_s.append(int(ok))
+    assert N_(succ).tolist() == exp_s
+    assert np.allclose(N_(rp), exp_rp, rtol=1e-15) and np.allclose(N_(ri), exp_ri, rtol=0)
+
+
+@pytest.mark.parametrize("name", ["solve_pendulum_N20", "solve_linear_N40", "solve_cartpole_N40",
+                                  "solve_pendulum_N100", "solve_pendulum_N500"])
+def test_full_solve_matches_reference(golden, name):
+    """End to end through the reference-facing API: same optimal controls (<= 1e-9 relative) and the
+    SAME Newton iteration count as the reference's driver run from its own source (BASELINE config 1
+    is solve_pendulum_N500)."""
+    from ipoc_b200 import noc, problems
+    g = golden(name)
+    N = g["u0"].shape[0]
+    if "pendulum" in name:
+        ocp = problems.make_pendulum(1.0 / N)
+    elif "cartpole" in name:
+        ocp = problems.make_cartpole(1.0 / N)
+    else:
+        ocp = problems.make_linear_demo(0.1)
+    u, its = noc.par_interior_point_optimal_control(ocp, T(g["u0"]), T(g["x0"]))
+    assert its == int(g["refp_iterations"])
+    assert relerr(N_(u), g["refp_opt_u"]) < 1e-9
+
+
+def test_cpu_tensors_are_rejected():
+    from ipoc_b200 import noc, _lib
+    rng = np.random.default_rng(0)
+    fx, fu, ru, Q, R, M = (torch.as_tensor(a) for a in random_lq(rng, 8, 2, 1))
+    with pytest.raises(_lib.IpocError):
+        noc.newton_step(fx, fu, ru, Q, R, M, torch.tensor([0.1]))
