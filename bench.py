@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the par IP-Newton hot path.
+
+A "step" is ONE pass of the hot path over one Newton iteration of the workload:
+    K1 costate scan + K4 reductions (max|ru|, ||cu||, reg) + K2 Riccati scan/gains + K3 forward scan
+    + K4 constraint reduction + A8 accept/regularisation update          (all kernels of libipoc.so)
+on the LQ tensors of BASELINE.json configs[1]: constrained cartpole, nx=4, nu=1, N=10^4, float64.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`value` : whole-job Newton steps/s with inputs resident in HBM (CUDA-graph replay of one pass, L2
+          flushed between timed steps); N > 1: every rank runs its own independent OCP (batch-sharded
+          mode, no data-path collective) -> weak scaling, value = sum over ranks.
+`e2e`   : same metric through the C-ABI host wrapper (ipoc_newton_step_host_f64): pinned HOST buffers,
+          H2D + kernels + D2H inside the timed region.
+`--impl reference`: the reference path on the host CPU.  The reference itself (JAX + paroc) cannot be
+          installed here, so this times the NumPy oracle port (oracle/), labelled kind="port".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "ip-parallel-optimal-control_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+NX, NU, NC = 4, 1, 2
+N_HEADLINE = 10_000
+METRIC = "ip_newton_step_throughput_cartpole_N1e4"
+UNIT = "newton_steps/s"
+
+
+def alg_bytes(N, nx=NX, nu=NU, nc=NC):
+    k1 = 8 * (nx * nx + 2 * nx) * N
+    k2 = 8 * (2 * nx * nx + 3 * nx * nu + nu * nu + 2 * nu) * N
+    k3 = 8 * (nx * nx + 2 * nx * nu + nx + 2 * nu) * N
+    k4 = 8 * (2 * nu + nc) * N
+    return dict(K1=k1, K2=k2, K3=k3, K4=k4, total=k1 + k2 + k3 + k4)
+
+
+PHASE_OF = {
+    "k_aff_seed": "K1", "k_aff_leaf_up": "K1", "k_aff_leaf_down": "K1",
+    "k_ric_seed": "K2", "k_ric_leaf_up": "K2", "k_mid_up_ric": "K2", "k_top_ric": "K2", "k_mid_down_ric": "K2",
+    "k_ric_leaf_down": "K2", "k_finalize_pred": "K2",
+    "k_fwd_leaf_down": "K3", "k_fwd_leaf_up": "K3",
+    "ipoc_reductions_f64": "K4", "ipoc_accept_update_f64": "K4",
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_inputs(N, seed=1):
+    """Same workload as the GPU arm, computed entirely on the CPU (oracle evaluator)."""
+    from ipoc_b200 import problems, workloads
+    from oracle.autodiff import Evaluator
+    from oracle import noc_np
+    Ts = 1.0 / N
+    ocp = problems.make_cartpole(Ts)
+    x0 = problems.cartpole_x0().numpy()
+    u0 = 0.1 * np.random.default_rng(seed).standard_normal((N, 1))
+    xs = workloads.cartpole_rollout_np(u0, x0, Ts)
+    ev = Evaluator(ocp)
+    d = ev.derivatives(xs, u0, 0.1)
+    lamT = ev.final_cost_grad(xs[-1])
+    lam = noc_np.par_costates(lamT, d)
+    ru, Q, R, M = noc_np.compute_lqr_params(lam, d)
+    return dict(d=d, lamT=lamT, ru=ru, Q=Q, R=R, M=M, cons=ev.constraints(xs, u0))
+
+
+def cpu_pass(inp):
+    """One hot-path pass with the NumPy oracle (ref noc/costates.py:34-40, par_Newton :107-124,
+    reductions :45-47,:158)."""
+    from oracle import noc_np
+    d = inp["d"]
+    noc_np.par_costates(inp["lamT"], d)
+    hu = np.max(np.abs(inp["ru"]))
+    out = noc_np.par_Newton(NX, d, 1.0, inp["ru"], inp["Q"], inp["R"], inp["M"])
+    feas = bool(np.all(inp["cons"] <= 0))
+    return out, hu, feas
+
+
+def time_cpu(inp, steps, warmup):
+    for _ in range(warmup):
+        cpu_pass(inp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pass(inp)
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    inp = cpu_inputs(N_HEADLINE)
+    dt = time_cpu(inp, args.steps, args.warmup)
+    val = 1.0 / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cartpole nx=4 nu=1 N=10000 f64: one par IP-Newton hot-path pass (K1+K2+K3+K4)",
+                   "note": "reference (JAX+paroc) not installable here: NumPy oracle port on host CPU"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full passes at N=10000 after {args.warmup} warm-up; NumPy "
+                                   f"(batched LAPACK small solves, threads as NumPy/OpenBLAS chooses; {cores} cores)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ our arm (GPU)
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ipoc_b200 import _lib, workloads
+    from ipoc_b200.runner import NewtonPass
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    hbm_peak, peak_src = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def make_pass(N, seed):
+        w = workloads.newton_inputs("cartpole", N, dev, seed=seed, x0_noise=0.0 if seed == 1 else 0.01)
+        return w, NewtonPass(w["fx"], w["fu"], w["cx"], w["cu"], w["lamT"], w["ru"], w["Q"], w["R"], w["M"], w["cons"])
+
+    def time_steps(fn, steps, warmup, do_flush=True):
+        for _ in range(warmup):
+            fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for a, b in evs:
+            if do_flush:
+                flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        return [a.elapsed_time(b) for a, b in evs]   # ms
+
+    # ---- headline workload: every rank its own OCP (rank 0 = the BASELINE config-2 inputs, seed 1)
+    w, npass = make_pass(N_HEADLINE, seed=1 + rank)
+    launches_per_pass = npass.launches_per_pass()
+    npass.capture()
+    clocks = Clocks(local) if rank == 0 else None
+    ms = time_steps(npass.replay, args.steps, args.warmup, do_flush=True)
+    clk = clocks.stop() if clocks else None
+    ms_step = float(np.mean(ms))
+    ms_plain = float(np.mean(time_steps(npass.run, args.steps, args.warmup, do_flush=True)))
+    ms_warm = float(np.mean(time_steps(npass.replay, args.steps, args.warmup, do_flush=False)))
+
+    # ---- per-launch profile (CUDA events after every launch, on the launching stream), L2 flushed
+    def profile_pass(p, reps):
+        acc = {}
+        for _ in range(reps):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            for name, t in p.profile():
+                acc.setdefault(name, []).append(t)
+        return acc
+
+    prof = profile_pass(npass, max(3, min(args.steps, 10)))
+    kern = {k: (float(np.mean(v)) * (len(v) / max(3, min(args.steps, 10)))) for k, v in prof.items()}   # ms per pass
+    phases = {}
+    for k, t in kern.items():
+        phases[PHASE_OF.get(k, "other")] = phases.get(PHASE_OF.get(k, "other"), 0.0) + t
+    ab = alg_bytes(N_HEADLINE)
+    dom = max(("K1", "K2", "K3"), key=lambda ph: phases.get(ph, 0.0))
+    dom_ms = phases[dom]
+    achieved = ab[dom] / (dom_ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C ABI call (pinned host memory)
+    N = N_HEADLINE
+    host = {k: w[k].detach().cpu().contiguous().pin_memory() for k in ("fx", "fu", "ru", "Q", "R", "M")}
+    reg_h = torch.tensor([float(npass.cu_norm[0])], dtype=torch.float64).pin_memory()
+    dx_h = torch.empty(N + 1, NX, dtype=torch.float64).pin_memory()
+    du_h = torch.empty(N, NU, dtype=torch.float64).pin_memory()
+    pred_h = torch.empty(1, dtype=torch.float64).pin_memory()
+    feas_h = torch.empty(1, dtype=torch.int32).pin_memory()
+    scratch_bytes = lib.ipoc_newton_step_host_scratch_bytes(N, NX, NU, 1)
+    scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+    import ctypes
+    hp = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def e2e_step():
+        _lib.check(lib.ipoc_newton_step_host_f64(N, NX, NU, 1, hp(host["fx"]), hp(host["fu"]), hp(host["ru"]),
+                                                 hp(host["Q"]), hp(host["R"]), hp(host["M"]), hp(reg_h), hp(dx_h),
+                                                 hp(du_h), hp(pred_h), hp(feas_h), hp(scratch), scratch_bytes,
+                                                 _lib.stream_ptr()))
+
+    ms_e2e = float(np.mean(time_steps(e2e_step, args.steps, args.warmup, do_flush=True)))
+    h2d = sum(t.numel() * 8 for t in host.values()) + 8
+    d2h = dx_h.numel() * 8 + du_h.numel() * 8 + 8 + 4
+    torch.cuda.synchronize(dev)
+    dx_check = float((dx_h.to(dev) - npass.dx[0]).abs().max())   # same step as the resident path (rp=1 at first pass only)
+
+    # ---- max over ranks, aggregate
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    ms_step_all, ms_e2e_all = allmax(ms_step), allmax(ms_e2e)
+    value = world / (ms_step_all * 1e-3)
+    e2e_value = world / (ms_e2e_all * 1e-3)
+
+    # ---- horizon sweep (single GPU): Newton-step time and HBM fraction at N = 1e5, 1e6
+    sweep = []
+    if rank == 0 and not args.no_sweep:
+        for Ns in (100_000, 1_000_000):
+            try:
+                t0 = time.time()
+                ws_, ps_ = make_pass(Ns, seed=1)
+                ps_.capture()
+                m = float(np.mean(_time_local(torch, ps_.replay, flush, 5, 3, dev)))
+                pr = {}
+                for _ in range(3):
+                    flush.zero_()
+                    torch.cuda.synchronize(dev)
+                    for name, t in ps_.profile():
+                        pr[name] = pr.get(name, 0.0) + t / 3
+                ph = {}
+                for k, t in pr.items():
+                    ph[PHASE_OF.get(k, "other")] = ph.get(PHASE_OF.get(k, "other"), 0.0) + t
+                abs_ = alg_bytes(Ns)
+                sweep.append({"N": Ns, "ms_per_step": m,
+                              "hbm_frac_step": abs_["total"] / (m * 1e-3) / 1e9 / hbm_peak,
+                              "phase_ms": {k: round(v, 4) for k, v in ph.items()},
+                              "hbm_frac_K2": abs_["K2"] / (ph.get("K2", 1e9) * 1e-3) / 1e9 / hbm_peak,
+                              "hbm_frac_K1": abs_["K1"] / (ph.get("K1", 1e9) * 1e-3) / 1e9 / hbm_peak,
+                              "hbm_frac_K3": abs_["K3"] / (ph.get("K3", 1e9) * 1e-3) / 1e9 / hbm_peak,
+                              "setup_s": round(time.time() - t0, 1)})
+                del ws_, ps_
+                torch.cuda.empty_cache()
+            except Exception as e:   # the sweep must never take the headline line down
+                sweep.append({"N": Ns, "error": repr(e)[:200]})
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload with the oracle port
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        inp = cpu_inputs(N_HEADLINE)
+        n_cpu = 20
+        dt = time_cpu(inp, n_cpu, 2)
+        cores = os.cpu_count() or 1
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} full passes at N=10000 (NumPy oracle: JAX-order associative scans, batched small "
+                         f"solves), {cores} host cores available, ms_per_step={dt * 1e3:.1f}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step_all, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cartpole nx=4 nu=1 nc=2 N=10000 f64 (BASELINE configs[1]): one par IP-Newton "
+                                   "hot-path pass K1+K2+K3+K4 per step; N>1: one independent OCP per GPU "
+                                   "(batch-sharded, no collective)",
+                       "l2": "L2 flushed (256 MiB memset) before every timed step",
+                       "launch": "CUDA-graph replay of one pass", "seed": 1},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e_all, "api": "ipoc_newton_step_host_f64 (K2+K3, pinned host buffers)",
+                    "check_max_abs_dx_diff_vs_resident": dx_check},
+            "gpu_launches": launches_per_pass * args.steps,
+            "launches_per_step": launches_per_pass,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None,
+                         "kernel": f"{dom} phase (all its launches)", "peak_source": peak_src,
+                         "algorithmic_bytes": ab[dom], "duration_ms": dom_ms,
+                         "note": "N=1e4 moves 8 MB: latency regime, see sweep for N>=1e5"},
+            "kernels_ms_per_step": {k: round(v, 5) for k, v in sorted(kern.items(), key=lambda kv: -kv[1])},
+            "phases_ms_per_step": {k: round(v, 5) for k, v in phases.items()},
+            "ms_per_step_plain_launch": ms_plain, "ms_per_step_l2_warm": ms_warm,
+            "sweep": sweep,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _time_local(torch, fn, flush, steps, warmup, dev):
+    for _ in range(warmup):
+        fn()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize(dev)
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize(dev)
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

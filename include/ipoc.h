@@ -123,12 +123,14 @@ int ipoc_affine_scan_f64(int reverse, int transpose, int N, int nx, int batch,
  * (ref noc/par_interior_point_newton.py:45-47 `all(cons <= 0)`, :116 `norm(d.cu)`, :158
  * `max|ru|`).  Any input pointer may be NULL (its output is then left untouched).
  *   in : ru (N,nu) cu (N,nu) cons (N,nc);  out per problem: hu_norm, cu_norm, traj_feasible
+ * If `rp` and `reg` are given (with cu), also reg = rp * ||cu||_F (:117) — the device scalar that
+ * ipoc_newton_step_f64 consumes, so the regularisation never visits the host.
  * Fixed reduction order -> bit-reproducible run to run.
  */
 int ipoc_reductions_f64(int N, int nu, int nc, int batch,
                         const double* ru, const double* cu, const double* cons,
                         double* hu_norm, double* cu_norm, int32_t* traj_feasible,
-                        void* ws, size_t ws_bytes, ipoc_stream_t stream);
+                        const double* rp, double* reg, ipoc_stream_t stream);
 
 /* ---- A8: scalar accept / regularisation update, on device --------------------------------
  * (ref noc/par_interior_point_newton.py:159-173) for `batch` independent problems:
@@ -201,6 +203,14 @@ int ipoc_newton_step_host_f64(int N, int nx, int nu, int batch,
 
 /* Number of kernels the library has launched since load (for launch accounting in bench.py). */
 unsigned long long ipoc_launch_count(void);
+
+/* Optional per-launch profiler (bench.py's roofline): after ipoc_profile_begin, a CUDA event is
+ * recorded on the launching stream after every kernel launch of this library;
+ * ipoc_profile_end synchronises the last event and returns the number of launches seen, their
+ * device durations in ms (event-to-event) and a comma-separated list of kernel names.
+ * Not thread-safe; never armed unless asked. */
+int ipoc_profile_begin(ipoc_stream_t stream);
+int ipoc_profile_end(char* names, size_t names_len, float* ms, int max_entries);
 
 #ifdef __cplusplus
 }

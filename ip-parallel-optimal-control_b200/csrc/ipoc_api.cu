@@ -1,0 +1,406 @@
+// C ABI of libipoc.so (include/ipoc.h): argument checks, dispatch on the runtime state dimension to
+// the per-NX translation units (ipoc_nx.cu), the dimension-independent kernels (K4 reductions, A8
+// accept/update), the host-buffer wrapper and the optional per-launch CUDA-event profiler.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include "../../include/ipoc.h"
+#include "ipoc_dispatch.h"
+
+namespace ipoc {
+
+struct Tuning {
+    int leaf_chunk, mid_fanin, top_max;
+};
+unsigned long long g_launches = 0;
+Tuning g_tune = {0, 0, 0};
+
+// ---- per-launch profiler: one CUDA event after every kernel launch, on the launching stream ----
+constexpr int kMaxProf = 256;
+struct Prof {
+    bool armed = false, created = false;
+    int n = 0;
+    cudaEvent_t ev[kMaxProf];
+    const char* name[kMaxProf];
+};
+static Prof g_prof;
+void prof_mark(const char* name, cudaStream_t st) {
+    if (!g_prof.armed || g_prof.n >= kMaxProf) return;
+    cudaEventRecord(g_prof.ev[g_prof.n], st);
+    g_prof.name[g_prof.n++] = name;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct Bump {
+    char* base;
+    size_t off, cap;
+    bool dry;
+    template <class T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* r = dry ? nullptr : reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+};
+
+#define IPOC_API_LAUNCH_CHECK(st)                                   \
+    do {                                                            \
+        ++g_launches;                                               \
+        prof_mark(__func__, st);                                    \
+        if (cudaPeekAtLastError() != cudaSuccess) return IPOC_ECUDA; \
+    } while (0)
+
+// ------------------------------------------------------------------ K4 reductions + A8 update
+static __global__ void __launch_bounds__(256)
+k_reductions(const double* __restrict__ ru, const double* __restrict__ cu, const double* __restrict__ cons,
+             int N, int nu, int nc, double* __restrict__ hu_norm, double* __restrict__ cu_norm,
+             int32_t* __restrict__ traj_feasible, const double* __restrict__ rp, double* __restrict__ reg) {
+    __shared__ double s_max[256];
+    __shared__ double s_sq[256];
+    __shared__ int s_ok[256];
+    const int b = blockIdx.x, t = threadIdx.x;
+    double mx = 0.0, sq = 0.0;
+    int ok = 1, nan_seen = 0;
+    if (ru != nullptr) {
+        const double* p = ru + (size_t)b * N * nu;
+        for (long long i = t; i < (long long)N * nu; i += 256) {
+            const double v = fabs(p[i]);
+            if (v != v) nan_seen = 1;
+            mx = fmax(mx, v);
+        }
+    }
+    if (cu != nullptr) {
+        const double* p = cu + (size_t)b * N * nu;
+        for (long long i = t; i < (long long)N * nu; i += 256) sq += p[i] * p[i];
+    }
+    if (cons != nullptr) {
+        const double* p = cons + (size_t)b * N * nc;
+        for (long long i = t; i < (long long)N * nc; i += 256) ok &= (p[i] <= 0.0) ? 1 : 0;
+    }
+    s_max[t] = nan_seen ? __longlong_as_double(0x7ff8000000000000LL) : mx;
+    s_sq[t] = sq;
+    s_ok[t] = ok;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (t < o) {
+            const double a = s_max[t], c = s_max[t + o];
+            s_max[t] = (a != a || c != c) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(a, c);
+            s_sq[t] += s_sq[t + o];
+            s_ok[t] &= s_ok[t + o];
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        if (ru != nullptr) hu_norm[b] = s_max[0];
+        if (cu != nullptr) {
+            const double nrm = sqrt(s_sq[0]);
+            cu_norm[b] = nrm;
+            if (rp != nullptr && reg != nullptr) reg[b] = rp[b] * nrm;   // ref :117
+        }
+        if (cons != nullptr) traj_feasible[b] = s_ok[0];
+    }
+}
+
+static __global__ void k_accept_update(int batch, const double* __restrict__ cost, const double* __restrict__ new_cost,
+                                const int32_t* __restrict__ traj_feasible, const double* __restrict__ pred,
+                                const int32_t* __restrict__ bwd_feasible, const int32_t* __restrict__ active,
+                                double* __restrict__ rp, double* __restrict__ r_inc,
+                                int32_t* __restrict__ success, double* __restrict__ gain_ratio) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    if (active != nullptr && !active[b]) return;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double nc = traj_feasible[b] ? new_cost[b] : inf;
+    const double rho = (nc - cost[b]) / pred[b];
+    const bool ok = (rho > 0.0) && (bwd_feasible[b] != 0);
+    double r = rp[b], ri = r_inc[b];
+    if (ok) {
+        const double tq = 2.0 * rho - 1.0;
+        r = r * fmax(1.0 / 3.0, 1.0 - tq * tq * tq);
+        ri = 2.0;
+    } else {
+        r = r * ri;
+        ri = 2.0 * ri;
+    }
+    r = fmin(fmax(r, 1e-16), 1e16);
+    rp[b] = r;
+    r_inc[b] = ri;
+    success[b] = ok ? 1 : 0;
+    if (gain_ratio != nullptr) gain_ratio[b] = rho;
+}
+
+}  // namespace ipoc
+
+// =================================================================== C ABI
+using namespace ipoc;
+
+#define IPOC_FOR_NX(X) X(1) X(2) X(3) X(4) X(6) X(8)
+
+extern "C" {
+
+const char* ipoc_strerror(int code) {
+    switch (code) {
+        case IPOC_OK: return "ok";
+        case IPOC_EUNSUPPORTED_DIM: return "unsupported (nx, nu): no kernel instantiated and there is no CPU fallback";
+        case IPOC_EWORKSPACE: return "workspace too small (see ipoc_workspace_bytes)";
+        case IPOC_ECUDA: return "CUDA error at kernel launch";
+        case IPOC_ENCCL: return "NCCL error";
+        case IPOC_EINVAL: return "invalid argument";
+        case IPOC_EALIGN: return "pointer not 16-byte aligned";
+        default: return "unknown ipoc error";
+    }
+}
+
+int ipoc_version(void) { return 100; }
+
+int ipoc_supported(int nx, int nu) {
+#define X(a) if (nx == a) return nx_supported<a>(nu);
+    IPOC_FOR_NX(X)
+#undef X
+    return 0;
+}
+
+void ipoc_set_tuning(int leaf_chunk, int mid_fanin, int top_max) {
+    g_tune.leaf_chunk = leaf_chunk;
+    g_tune.mid_fanin = mid_fanin;
+    g_tune.top_max = top_max;
+}
+
+unsigned long long ipoc_launch_count(void) { return g_launches; }
+
+int ipoc_carry_doubles(int kind, int nx) {
+    if (nx < 1 || nx > 8) return 0;
+    const int sy = nx * (nx + 1) / 2;
+    return kind == IPOC_CARRY_RICCATI ? nx * nx + 2 * nx + 2 * sy : nx * nx + nx;
+}
+
+size_t ipoc_workspace_bytes(int kind, int N, int nx, int nu, int batch) {
+    (void)nu;
+    if (N < 1 || batch < 1) return 0;
+    // the sharded entry points use the same formula with batch = 1 and forced chunking; take the max
+#define X(a) if (nx == a) { size_t s1 = nx_ws_bytes<a>(kind, N, batch, false); \
+                            size_t s2 = batch == 1 ? nx_ws_bytes<a>(kind, N, 1, true) : 0; return s1 > s2 ? s1 : s2; }
+    IPOC_FOR_NX(X)
+#undef X
+    return 0;
+}
+
+#define CHECK_ARGS(cond) do { if (!(cond)) return IPOC_EINVAL; } while (0)
+#define CHECK_ALIGN(p) do { if ((p) != nullptr && !aligned16(p)) return IPOC_EALIGN; } while (0)
+
+int ipoc_newton_step_f64(int N, int nx, int nu, int batch, const double* fx, const double* fu, const double* ru,
+                         const double* Q, const double* R, const double* M, const double* reg, double* dx, double* du,
+                         double* Kx, double* d, double* pred, int32_t* feasible, void* ws, size_t ws_bytes,
+                         ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && fx && fu && ru && Q && R && M && reg && dx && du && Kx && d && pred && feasible && ws);
+    CHECK_ALIGN(fx); CHECK_ALIGN(fu); CHECK_ALIGN(ru); CHECK_ALIGN(Q); CHECK_ALIGN(R); CHECK_ALIGN(M);
+    CHECK_ALIGN(dx); CHECK_ALIGN(du); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(ws);
+#define X(a) if (nx == a) return nx_newton_step<a>(nu, N, batch, fx, fu, ru, Q, R, M, reg, dx, du, Kx, d, pred, feasible, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_lqt_bwd_f64(int N, int nx, int nu, int batch, const double* A, const double* B, const double* c,
+                     const double* Xm, const double* U, const double* M, const double* q, const double* p,
+                     const double* ST, const double* vT, double* Kx, double* d, double* S, double* v, double* pred,
+                     int32_t* feasible, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && A && B && Xm && U && M && q && p && ST && Kx && d && pred && feasible && ws);
+    CHECK_ARGS((S == nullptr) == (v == nullptr));
+    CHECK_ALIGN(A); CHECK_ALIGN(B); CHECK_ALIGN(c); CHECK_ALIGN(Xm); CHECK_ALIGN(U); CHECK_ALIGN(M); CHECK_ALIGN(q);
+    CHECK_ALIGN(p); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(ws);
+#define X(a) if (nx == a) return nx_lqt_bwd<a>(nu, N, batch, A, B, c, Xm, U, M, q, p, ST, vT, Kx, d, S, v, pred, feasible, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_lqt_fwd_f64(int N, int nx, int nu, int batch, const double* A, const double* B, const double* c,
+                     const double* Kx, const double* d, const double* x0, double* u, double* x, void* ws,
+                     size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && A && B && Kx && d && u && x && ws);
+    CHECK_ALIGN(A); CHECK_ALIGN(B); CHECK_ALIGN(c); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(u); CHECK_ALIGN(x);
+    CHECK_ALIGN(ws);
+#define X(a) if (nx == a) return nx_lqt_fwd<a>(nu, N, batch, A, B, c, Kx, d, x0, u, x, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_affine_scan_f64(int reverse, int transpose, int N, int nx, int batch, const double* F, const double* c,
+                         const double* seed, double* out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && F && c && out && ws);
+    CHECK_ALIGN(F); CHECK_ALIGN(c); CHECK_ALIGN(out); CHECK_ALIGN(ws);
+#define X(a) if (nx == a) return nx_affine_scan<a>(reverse, transpose, N, batch, F, c, seed, out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_reductions_f64(int N, int nu, int nc, int batch, const double* ru, const double* cu, const double* cons,
+                        double* hu_norm, double* cu_norm, int32_t* traj_feasible, const double* rp, double* reg,
+                        ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1);
+    CHECK_ARGS((ru == nullptr || hu_norm) && (cu == nullptr || cu_norm) && (cons == nullptr || traj_feasible));
+    cudaStream_t st_ = (cudaStream_t)stream;
+    k_reductions<<<batch, 256, 0, st_>>>(ru, cu, cons, N, nu, nc, hu_norm, cu_norm, traj_feasible, rp, reg);
+    IPOC_API_LAUNCH_CHECK(st_);
+    return IPOC_OK;
+}
+
+int ipoc_accept_update_f64(int batch, const double* cost, const double* new_cost, const int32_t* traj_feasible,
+                           const double* pred, const int32_t* bwd_feasible, const int32_t* active, double* rp,
+                           double* r_inc, int32_t* success, double* gain_ratio, ipoc_stream_t stream) {
+    CHECK_ARGS(batch >= 1 && cost && new_cost && traj_feasible && pred && bwd_feasible && rp && r_inc && success);
+    cudaStream_t st_ = (cudaStream_t)stream;
+    k_accept_update<<<(batch + 127) / 128, 128, 0, st_>>>(batch, cost, new_cost, traj_feasible, pred,
+                                                                            bwd_feasible, active, rp, r_inc, success,
+                                                                            gain_ratio);
+    IPOC_API_LAUNCH_CHECK(st_);
+    return IPOC_OK;
+}
+
+int ipoc_newton_bwd_reduce_f64(int N, int nx, int nu, const double* fx, const double* fu, const double* ru,
+                               const double* Q, const double* R, const double* M, const double* reg,
+                               double* carry_out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && fx && fu && ru && Q && R && M && reg && carry_out && ws);
+#define X(a) if (nx == a) return nx_newton_bwd_reduce<a>(nu, N, fx, fu, ru, Q, R, M, reg, carry_out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_newton_bwd_apply_f64(int N, int nx, int nu, int rank, int nranks, const double* fx, const double* fu,
+                              const double* ru, const double* Q, const double* R, const double* M, const double* reg,
+                              const double* carries, const double* ST, double* Kx, double* d, double* pred,
+                              int32_t* feasible, double* fwd_carry_out, void* ws, size_t ws_bytes,
+                              ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && carries && ST && Kx && d && pred && feasible && fwd_carry_out && ws);
+#define X(a) if (nx == a) return nx_newton_bwd_apply<a>(nu, N, rank, nranks, fx, fu, ru, Q, R, M, reg, carries, ST, Kx, d, pred, feasible, fwd_carry_out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_newton_fwd_apply_f64(int N, int nx, int nu, int rank, int nranks, const double* fx, const double* fu,
+                              const double* Kx, const double* d, const double* fwd_carries, double* dx, double* du,
+                              void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && fx && fu && Kx && d && fwd_carries && dx && du && ws);
+#define X(a) if (nx == a) return nx_newton_fwd_apply<a>(nu, N, rank, nranks, fx, fu, Kx, d, fwd_carries, dx, du, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_affine_reduce_f64(int reverse, int transpose, int N, int nx, const double* F, const double* c,
+                           double* carry_out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && F && c && carry_out && ws);
+#define X(a) if (nx == a) return nx_affine_reduce<a>(reverse, transpose, N, F, c, carry_out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+int ipoc_affine_apply_f64(int reverse, int transpose, int N, int nx, int rank, int nranks, const double* F,
+                          const double* c, const double* carries, const double* seed, double* out, void* ws,
+                          size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && F && c && carries && seed && out && ws);
+#define X(a) if (nx == a) return nx_affine_apply<a>(reverse, transpose, N, rank, nranks, F, c, carries, seed, out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_NX(X)
+#undef X
+    return IPOC_EUNSUPPORTED_DIM;
+}
+
+size_t ipoc_newton_step_host_scratch_bytes(int N, int nx, int nu, int batch) {
+    const size_t per = (size_t)nx * nx * 2 + (size_t)nx * nu * 2 + (size_t)nu * nu + nu;   // inputs
+    const size_t outs = (size_t)nx + nu + (size_t)nu * nx + nu;
+    size_t b = ((size_t)N * per + (size_t)(N + 1) * outs) * batch * sizeof(double) + 64 * 256;
+    b += ipoc_workspace_bytes(IPOC_WS_NEWTON_STEP, N, nx, nu, batch) + 4096 * (size_t)batch;
+    return b;
+}
+
+int ipoc_newton_step_host_f64(int N, int nx, int nu, int batch, const double* fx, const double* fu, const double* ru,
+                              const double* Q, const double* R, const double* M, const double* reg, double* dx,
+                              double* du, double* pred, int32_t* feasible, void* dws, size_t dws_bytes,
+                              ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && dws);
+    if (dws_bytes < ipoc_newton_step_host_scratch_bytes(N, nx, nu, batch)) return IPOC_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    Bump bp{(char*)dws, 0, dws_bytes, false};
+    const size_t T = (size_t)N * batch;
+    double* dfx = bp.take<double>(T * nx * nx);
+    double* dfu = bp.take<double>(T * nx * nu);
+    double* dru = bp.take<double>(T * nu);
+    double* dQ = bp.take<double>(T * nx * nx);
+    double* dR = bp.take<double>(T * nu * nu);
+    double* dM = bp.take<double>(T * nx * nu);
+    double* dreg = bp.take<double>(batch);
+    double* ddx = bp.take<double>((size_t)(N + 1) * batch * nx);
+    double* ddu = bp.take<double>(T * nu);
+    double* dKx = bp.take<double>(T * nu * nx);
+    double* dd = bp.take<double>(T * nu);
+    double* dpred = bp.take<double>(batch);
+    int32_t* dfeas = bp.take<int32_t>(batch);
+    const size_t wsb = ipoc_workspace_bytes(IPOC_WS_NEWTON_STEP, N, nx, nu, batch);
+    void* ws = bp.take<char>(wsb);
+    if (bp.off > dws_bytes) return IPOC_EWORKSPACE;
+    const size_t D = sizeof(double);
+    bool ok = true;
+    ok &= cudaMemcpyAsync(dfx, fx, T * nx * nx * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dfu, fu, T * nx * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dru, ru, T * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dQ, Q, T * nx * nx * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dR, R, T * nu * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dM, M, T * nx * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(dreg, reg, batch * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (!ok) return IPOC_ECUDA;
+    int rc = ipoc_newton_step_f64(N, nx, nu, batch, dfx, dfu, dru, dQ, dR, dM, dreg, ddx, ddu, dKx, dd, dpred, dfeas, ws,
+                                  wsb, stream);
+    if (rc) return rc;
+    ok &= cudaMemcpyAsync(dx, ddx, (size_t)(N + 1) * batch * nx * D, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(du, ddu, T * nu * D, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(pred, dpred, batch * D, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(feasible, dfeas, batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    return ok ? IPOC_OK : IPOC_ECUDA;
+}
+
+
+int ipoc_profile_begin(ipoc_stream_t stream) {
+    if (!g_prof.created) {
+        for (int i = 0; i < kMaxProf; ++i)
+            if (cudaEventCreate(&g_prof.ev[i]) != cudaSuccess) return IPOC_ECUDA;
+        g_prof.created = true;
+    }
+    g_prof.n = 0;
+    g_prof.armed = true;
+    prof_mark("begin", (cudaStream_t)stream);
+    return IPOC_OK;
+}
+
+int ipoc_profile_end(char* names, size_t names_len, float* ms, int max_entries) {
+    g_prof.armed = false;
+    if (g_prof.n < 1) return 0;
+    if (cudaEventSynchronize(g_prof.ev[g_prof.n - 1]) != cudaSuccess) return IPOC_ECUDA;
+    int cnt = 0;
+    size_t pos = 0;
+    if (names && names_len) names[0] = 0;
+    for (int i = 1; i < g_prof.n && cnt < max_entries; ++i, ++cnt) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, g_prof.ev[i - 1], g_prof.ev[i]);
+        ms[cnt] = t;
+        if (names) {
+            const size_t l = strlen(g_prof.name[i]);
+            if (pos + l + 2 < names_len) {
+                memcpy(names + pos, g_prof.name[i], l);
+                pos += l;
+                names[pos++] = ',';
+                names[pos] = 0;
+            }
+        }
+    }
+    return cnt;
+}
+
+}  // extern "C"

@@ -1,4 +1,6 @@
-// Hand-written sm_100a FP64 kernels + C ABI for the par IP-Newton hot path.
+#pragma once
+// Hand-written sm_100a FP64 kernels for the par IP-Newton hot path (templated on NX, NU).
+// Instantiated once per NX by ipoc_nx.cu; the C ABI lives in ipoc_api.cu.
 //
 // Scan organisation (all three scans: K1 costates, K2 Riccati, K3 forward):
 //   a hierarchical reduce / seeded-rescan.  A leaf thread folds `T0` consecutive time steps
@@ -19,14 +21,17 @@
 #include <stdio.h>
 #include "ipoc_math.cuh"
 #include "../../include/ipoc.h"
+#include "ipoc_dispatch.h"
 
 namespace ipoc {
 
-static unsigned long long g_launches = 0;
 struct Tuning {
     int leaf_chunk, mid_fanin, top_max;
 };
-static Tuning g_tune = {0, 0, 0};
+// shared, defined in ipoc_api.cu
+extern unsigned long long g_launches;
+extern Tuning g_tune;
+void prof_mark(const char* name, cudaStream_t st);   // no-op unless profiling is armed
 
 constexpr int kLeafThreads = 128;
 constexpr int kMidThreads = 128;
@@ -452,7 +457,7 @@ k_ric_leaf_down(Loader ld, int N, int T0, int n1, int batch,
 }
 
 // pred = -1/2 sum_k d'Gd, feasible = AND_k (G_k > 0); fixed-order tree per problem.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_finalize_pred(const double* __restrict__ pred_part, const int* __restrict__ feas_part, int n1,
                 double* __restrict__ pred, int32_t* __restrict__ feasible, int accumulate) {
     __shared__ double sp[256];
@@ -656,85 +661,10 @@ __global__ void k_aff_seed(const double* __restrict__ src, int batch, double* __
 }
 
 // SoA planes (stride `stride`, index idx) -> AoS carry (time-sharded mode)
-__global__ void k_soa_to_aos(const double* __restrict__ soa, size_t stride, size_t idx, int sz,
+static __global__ void k_soa_to_aos(const double* __restrict__ soa, size_t stride, size_t idx, int sz,
                              double* __restrict__ aos) {
     const int c = threadIdx.x;
     if (c < sz) aos[c] = soa[(size_t)c * stride + idx];
-}
-
-// ------------------------------------------------------------------ K4 reductions + A8 update
-__global__ void __launch_bounds__(256)
-k_reductions(const double* __restrict__ ru, const double* __restrict__ cu, const double* __restrict__ cons,
-             int N, int nu, int nc, double* __restrict__ hu_norm, double* __restrict__ cu_norm,
-             int32_t* __restrict__ traj_feasible) {
-    __shared__ double s_max[256];
-    __shared__ double s_sq[256];
-    __shared__ int s_ok[256];
-    const int b = blockIdx.x, t = threadIdx.x;
-    double mx = 0.0, sq = 0.0;
-    int ok = 1, nan_seen = 0;
-    if (ru != nullptr) {
-        const double* p = ru + (size_t)b * N * nu;
-        for (long long i = t; i < (long long)N * nu; i += 256) {
-            const double v = fabs(p[i]);
-            if (v != v) nan_seen = 1;
-            mx = fmax(mx, v);
-        }
-    }
-    if (cu != nullptr) {
-        const double* p = cu + (size_t)b * N * nu;
-        for (long long i = t; i < (long long)N * nu; i += 256) sq += p[i] * p[i];
-    }
-    if (cons != nullptr) {
-        const double* p = cons + (size_t)b * N * nc;
-        for (long long i = t; i < (long long)N * nc; i += 256) ok &= (p[i] <= 0.0) ? 1 : 0;
-    }
-    s_max[t] = nan_seen ? __longlong_as_double(0x7ff8000000000000LL) : mx;
-    s_sq[t] = sq;
-    s_ok[t] = ok;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (t < o) {
-            const double a = s_max[t], c = s_max[t + o];
-            s_max[t] = (a != a || c != c) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(a, c);
-            s_sq[t] += s_sq[t + o];
-            s_ok[t] &= s_ok[t + o];
-        }
-        __syncthreads();
-    }
-    if (t == 0) {
-        if (ru != nullptr) hu_norm[b] = s_max[0];
-        if (cu != nullptr) cu_norm[b] = sqrt(s_sq[0]);
-        if (cons != nullptr) traj_feasible[b] = s_ok[0];
-    }
-}
-
-__global__ void k_accept_update(int batch, const double* __restrict__ cost, const double* __restrict__ new_cost,
-                                const int32_t* __restrict__ traj_feasible, const double* __restrict__ pred,
-                                const int32_t* __restrict__ bwd_feasible, const int32_t* __restrict__ active,
-                                double* __restrict__ rp, double* __restrict__ r_inc,
-                                int32_t* __restrict__ success, double* __restrict__ gain_ratio) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= batch) return;
-    if (active != nullptr && !active[b]) return;
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    const double nc = traj_feasible[b] ? new_cost[b] : inf;
-    const double rho = (nc - cost[b]) / pred[b];
-    const bool ok = (rho > 0.0) && (bwd_feasible[b] != 0);
-    double r = rp[b], ri = r_inc[b];
-    if (ok) {
-        const double tq = 2.0 * rho - 1.0;
-        r = r * fmax(1.0 / 3.0, 1.0 - tq * tq * tq);
-        ri = 2.0;
-    } else {
-        r = r * ri;
-        ri = 2.0 * ri;
-    }
-    r = fmin(fmax(r, 1e-16), 1e16);
-    rp[b] = r;
-    r_inc[b] = ri;
-    success[b] = ok ? 1 : 0;
-    if (gain_ratio != nullptr) gain_ratio[b] = rho;
 }
 
 // =================================================================== host side
@@ -823,11 +753,13 @@ static void carve_newton(Bump& bp, const Plan& p, NewtonWs& w) {
     w.scratch = bp.take<double>(256);
 }
 
-#define IPOC_LAUNCH_CHECK()                                   \
-    do {                                                      \
-        ++g_launches;                                         \
+#define IPOC_LAUNCH_CHECK_N(name, st)                              \
+    do {                                                           \
+        ++g_launches;                                              \
+        prof_mark(name, st);                                       \
         if (cudaPeekAtLastError() != cudaSuccess) return IPOC_ECUDA; \
     } while (0)
+#define IPOC_LAUNCH_CHECK() IPOC_LAUNCH_CHECK_N("kernel", st)
 
 static inline unsigned grid_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 static inline int top_threads(int n) {
@@ -846,19 +778,19 @@ static int run_levels(const Plan& p, const ScanWs& w, bool want_total, bool redu
         k_mid_up<Op><<<grid_for(cnt, kMidThreads), kMidThreads, 0, st>>>(
             w.agg[l], (size_t)p.batch * p.n[l], p.n[l], w.agg[l + 1], (size_t)p.batch * p.n[l + 1], p.n[l + 1],
             p.T[l], p.batch);
-        IPOC_LAUNCH_CHECK();
+        IPOC_LAUNCH_CHECK_N(Op::tag_mid_up, st);
     }
     k_top<Op><<<p.batch, top_threads(p.n[L - 1]), 0, st>>>(
         w.agg[L - 1], (size_t)p.batch * p.n[L - 1], p.n[L - 1], p.batch, w.seed, w.val[L - 1],
         (size_t)p.batch * p.n[L - 1], (want_total || reduce_only) ? w.total : nullptr, reduce_only ? 1 : 0);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N(Op::tag_top, st);
     if (reduce_only) return IPOC_OK;
     for (int l = L - 2; l >= 0; --l) {
         const long long cnt = (long long)p.batch * p.n[l + 1];
         k_mid_down<Op><<<grid_for(cnt, kMidThreads), kMidThreads, 0, st>>>(
             w.agg[l], (size_t)p.batch * p.n[l], p.n[l], w.val[l], (size_t)p.batch * p.n[l], w.val[l + 1],
             (size_t)p.batch * p.n[l + 1], p.n[l + 1], p.T[l], p.batch);
-        IPOC_LAUNCH_CHECK();
+        IPOC_LAUNCH_CHECK_N(Op::tag_mid_down, st);
     }
     return IPOC_OK;
 }
@@ -876,7 +808,7 @@ static int run_bwd(const Plan& p, const NewtonWs& w, const Loader& ld, double* K
     if (p.nlev > 0) {
         k_ric_leaf_up<NX, NU, Loader><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
             ld, p.N, p.T0, p.n1, p.batch, w.ric.agg[0], (size_t)chunks);
-        IPOC_LAUNCH_CHECK();
+        IPOC_LAUNCH_CHECK_N("k_ric_leaf_up", st);
         int rc = run_levels<ROp>(p, w.ric, false, false, st);
         if (rc) return rc;
         leaf_vals = w.ric.val[0];
@@ -893,9 +825,9 @@ static int run_bwd(const Plan& p, const NewtonWs& w, const Loader& ld, double* K
     }
     k_ric_leaf_down<NX, NU, Loader><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
         ld, p.N, p.T0, p.n1, p.batch, leaf_vals, leaf_vstride, Kx, d, S, v, w.pred_part, w.feas_part, fagg, fstride);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_ric_leaf_down", st);
     k_finalize_pred<<<p.batch, 256, 0, st>>>(w.pred_part, w.feas_part, p.n1, pred, feasible, 0);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_finalize_pred", st);
     return IPOC_OK;
 }
 
@@ -914,7 +846,7 @@ static int run_fwd_down(const Plan& p, const NewtonWs& w, const double* A, const
     }
     k_fwd_leaf_down<NX, NU><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
         A, B, c, Kx, d, p.N, p.T0, p.n1, p.batch, leaf_vals, leaf_vstride, x, u);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_fwd_leaf_down", st);
     return IPOC_OK;
 }
 
@@ -929,9 +861,9 @@ static int newton_step_impl(int N, int batch, const double* fx, const double* fu
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     // terminal value function: XT = Q[0], HT = I, rT = 0 (ref noc/par_interior_point_newton.py:73-75)
     k_ric_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(Q, (size_t)N * NX * NX, nullptr, batch, w.ric.seed);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
     k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(nullptr, batch, w.aff.seed);   // dx_0 = 0 (:122)
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
     NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg, N};
     int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st);
     if (rc) return rc;
@@ -949,7 +881,7 @@ static int lqt_bwd_impl(int N, int batch, const double* A, const double* B, cons
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     k_ric_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(ST, (size_t)NX * NX, vT, batch, w.ric.seed);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
     LqtLoader<NX, NU> ld{A, B, c, X, U, M, q, pp, N};
     return run_bwd<NX, NU>(p, w, ld, Kx, d, S, v, pred, feasible, false, st);
 }
@@ -964,12 +896,12 @@ static int lqt_fwd_impl(int N, int batch, const double* A, const double* B, cons
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(x0, batch, w.aff.seed);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
     if (p.nlev > 0) {
         const long long chunks = (long long)batch * p.n1;
         k_fwd_leaf_up<NX, NU><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
             A, B, c, Kx, d, N, p.T0, p.n1, batch, w.aff.agg[0], (size_t)chunks);
-        IPOC_LAUNCH_CHECK();
+        IPOC_LAUNCH_CHECK_N("k_fwd_leaf_up", st);
     }
     return run_fwd_down<NX, NU>(p, w, A, B, c, Kx, d, x, u, st);
 }
@@ -983,14 +915,14 @@ static int affine_scan_impl(int reverse, int transpose, int N, int batch, const 
     carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(seed, batch, w.seed);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
     const long long chunks = (long long)batch * p.n1;
     const double* leaf_vals = w.seed;
     size_t leaf_vstride = (size_t)batch;
     if (p.nlev > 0) {
         k_aff_leaf_up<NX><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
             F, c, reverse, transpose, N, p.T0, p.n1, batch, w.agg[0], (size_t)chunks);
-        IPOC_LAUNCH_CHECK();
+        IPOC_LAUNCH_CHECK_N("k_aff_leaf_up", st);
         int rc = run_levels<AffOp<NX>>(p, w, false, false, st);
         if (rc) return rc;
         leaf_vals = w.val[0];
@@ -998,7 +930,7 @@ static int affine_scan_impl(int reverse, int transpose, int N, int batch, const 
     }
     k_aff_leaf_down<NX><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
         F, c, reverse, transpose, N, p.T0, p.n1, batch, leaf_vals, leaf_vstride, out);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_aff_leaf_down", st);
     return IPOC_OK;
 }
 
@@ -1026,11 +958,11 @@ static int newton_bwd_reduce_impl(int N, const double* fx, const double* fu, con
     NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg, N};
     k_ric_leaf_up<NX, NU, NewtonLoader<NX, NU>><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(
         ld, N, p.T0, p.n1, 1, w.ric.agg[0], (size_t)p.n1);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_ric_leaf_up", st);
     int rc = run_levels<RicOp<NX>>(p, w.ric, true, true, st);
     if (rc) return rc;
     k_soa_to_aos<<<1, 256, 0, st>>>(w.ric.total, 1, 0, RicElem<NX>::ESZ, carry_out);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_soa_to_aos", st);
     return IPOC_OK;
 }
 
@@ -1048,9 +980,9 @@ static int newton_bwd_apply_impl(int N, int rank, int nranks, const double* fx, 
     // terminal seed of the whole horizon, then pushed back through the later ranks' aggregates
     double* seed0 = w.scratch;   // RicVal packed
     k_ric_seed<NX><<<1, 32, 0, st>>>(ST, (size_t)NX * NX, nullptr, 1, seed0);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
     k_chain_seed<RicOp<NX>><<<1, 32, 0, st>>>(carries, nranks - 1, -1, nranks - 1 - rank, seed0, w.ric.seed);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_chain_seed_ric", st);
     NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg, N};
     // the leaf aggregates of this segment were computed in the reduce phase with the same plan
     // and are still in the workspace (same carve order) — the caller must pass the same ws.
@@ -1060,24 +992,24 @@ static int newton_bwd_apply_impl(int N, int rank, int nranks, const double* fx, 
         const int L = p.nlev;
         k_top<ROp><<<1, top_threads(p.n[L - 1]), 0, st>>>(w.ric.agg[L - 1], (size_t)p.n[L - 1], p.n[L - 1], 1,
                                                          w.ric.seed, w.ric.val[L - 1], (size_t)p.n[L - 1], nullptr, 0);
-        IPOC_LAUNCH_CHECK();
+        IPOC_LAUNCH_CHECK_N("k_top_ric", st);
         for (int l = L - 2; l >= 0; --l) {
             k_mid_down<ROp><<<grid_for(p.n[l + 1], kMidThreads), kMidThreads, 0, st>>>(
                 w.ric.agg[l], (size_t)p.n[l], p.n[l], w.ric.val[l], (size_t)p.n[l], w.ric.val[l + 1],
                 (size_t)p.n[l + 1], p.n[l + 1], p.T[l], 1);
-            IPOC_LAUNCH_CHECK();
+            IPOC_LAUNCH_CHECK_N("k_mid_down_ric", st);
         }
     }
     k_ric_leaf_down<NX, NU, NewtonLoader<NX, NU>><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(
         ld, N, p.T0, p.n1, 1, w.ric.val[0], (size_t)p.n1, Kx, d, nullptr, nullptr, w.pred_part, w.feas_part,
         w.aff.agg[0], (size_t)p.n1);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_ric_leaf_down", st);
     k_finalize_pred<<<1, 256, 0, st>>>(w.pred_part, w.feas_part, p.n1, pred, feasible, 0);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_finalize_pred", st);
     int rc = run_levels<AffOp<NX>>(p, w.aff, true, true, st);
     if (rc) return rc;
     k_soa_to_aos<<<1, 256, 0, st>>>(w.aff.total, 1, 0, AffElem<NX>::ESZ, fwd_carry_out);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_soa_to_aos", st);
     return IPOC_OK;
 }
 
@@ -1092,23 +1024,23 @@ static int newton_fwd_apply_impl(int N, int rank, int nranks, const double* fx, 
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     double* seed0 = w.scratch;
     k_aff_seed<NX><<<1, 32, 0, st>>>(nullptr, 1, seed0);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
     k_chain_seed<AffOp<NX>><<<1, 32, 0, st>>>(fwd_carries, 0, +1, rank, seed0, w.aff.seed);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_chain_seed_aff", st);
     using AOp = AffOp<NX>;
     const int L = p.nlev;
     k_top<AOp><<<1, top_threads(p.n[L - 1]), 0, st>>>(w.aff.agg[L - 1], (size_t)p.n[L - 1], p.n[L - 1], 1, w.aff.seed,
                                                      w.aff.val[L - 1], (size_t)p.n[L - 1], nullptr, 0);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_top_aff", st);
     for (int l = L - 2; l >= 0; --l) {
         k_mid_down<AOp><<<grid_for(p.n[l + 1], kMidThreads), kMidThreads, 0, st>>>(
             w.aff.agg[l], (size_t)p.n[l], p.n[l], w.aff.val[l], (size_t)p.n[l], w.aff.val[l + 1], (size_t)p.n[l + 1],
             p.n[l + 1], p.T[l], 1);
-        IPOC_LAUNCH_CHECK();
+        IPOC_LAUNCH_CHECK_N("k_mid_down_aff", st);
     }
     k_fwd_leaf_down<NX, NU><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(
         fx, fu, nullptr, Kx, d, N, p.T0, p.n1, 1, w.aff.val[0], (size_t)p.n1, dx, du);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_fwd_leaf_down", st);
     return IPOC_OK;
 }
 
@@ -1122,11 +1054,11 @@ static int affine_reduce_impl(int reverse, int transpose, int N, const double* F
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     k_aff_leaf_up<NX><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(F, c, reverse, transpose, N, p.T0, p.n1,
                                                                             1, w.agg[0], (size_t)p.n1);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_aff_leaf_up", st);
     int rc = run_levels<AffOp<NX>>(p, w, true, true, st);
     if (rc) return rc;
     k_soa_to_aos<<<1, 256, 0, st>>>(w.total, 1, 0, AffElem<NX>::ESZ, carry_out);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_soa_to_aos", st);
     return IPOC_OK;
 }
 
@@ -1144,20 +1076,20 @@ static int affine_apply_impl(int reverse, int transpose, int N, int rank, int nr
         k_chain_seed<AOp><<<1, 32, 0, st>>>(carries, nranks - 1, -1, nranks - 1 - rank, seed, w.seed);
     else
         k_chain_seed<AOp><<<1, 32, 0, st>>>(carries, 0, +1, rank, seed, w.seed);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_chain_seed_aff", st);
     const int L = p.nlev;
     k_top<AOp><<<1, top_threads(p.n[L - 1]), 0, st>>>(w.agg[L - 1], (size_t)p.n[L - 1], p.n[L - 1], 1, w.seed,
                                                      w.val[L - 1], (size_t)p.n[L - 1], nullptr, 0);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_top_aff", st);
     for (int l = L - 2; l >= 0; --l) {
         k_mid_down<AOp><<<grid_for(p.n[l + 1], kMidThreads), kMidThreads, 0, st>>>(
             w.agg[l], (size_t)p.n[l], p.n[l], w.val[l], (size_t)p.n[l], w.val[l + 1], (size_t)p.n[l + 1], p.n[l + 1],
             p.T[l], 1);
-        IPOC_LAUNCH_CHECK();
+        IPOC_LAUNCH_CHECK_N("k_mid_down_aff", st);
     }
     k_aff_leaf_down<NX><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(F, c, reverse, transpose, N, p.T0,
                                                                               p.n1, 1, w.val[0], (size_t)p.n1, out);
-    IPOC_LAUNCH_CHECK();
+    IPOC_LAUNCH_CHECK_N("k_aff_leaf_down", st);
     return IPOC_OK;
 }
 
@@ -1175,239 +1107,5 @@ static size_t ws_bytes_impl(int kind, int N, int batch, bool sharded) {
     return bp.off + 256;
 }
 
+
 }  // namespace ipoc
-
-// =================================================================== C ABI
-using namespace ipoc;
-
-#define IPOC_FOR_DIMS(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(4, 1) X(4, 2) X(6, 1) X(8, 1)
-#define IPOC_FOR_NX(X) X(1) X(2) X(3) X(4) X(6) X(8)
-
-extern "C" {
-
-const char* ipoc_strerror(int code) {
-    switch (code) {
-        case IPOC_OK: return "ok";
-        case IPOC_EUNSUPPORTED_DIM: return "unsupported (nx, nu): no kernel instantiated and there is no CPU fallback";
-        case IPOC_EWORKSPACE: return "workspace too small (see ipoc_workspace_bytes)";
-        case IPOC_ECUDA: return "CUDA error at kernel launch";
-        case IPOC_ENCCL: return "NCCL error";
-        case IPOC_EINVAL: return "invalid argument";
-        case IPOC_EALIGN: return "pointer not 16-byte aligned";
-        default: return "unknown ipoc error";
-    }
-}
-
-int ipoc_version(void) { return 100; }
-
-int ipoc_supported(int nx, int nu) {
-#define X(a, b) if (nx == a && nu == b) return 1;
-    IPOC_FOR_DIMS(X)
-#undef X
-    return 0;
-}
-
-void ipoc_set_tuning(int leaf_chunk, int mid_fanin, int top_max) {
-    g_tune.leaf_chunk = leaf_chunk;
-    g_tune.mid_fanin = mid_fanin;
-    g_tune.top_max = top_max;
-}
-
-unsigned long long ipoc_launch_count(void) { return g_launches; }
-
-int ipoc_carry_doubles(int kind, int nx) {
-    if (nx < 1 || nx > 8) return 0;
-    const int sy = nx * (nx + 1) / 2;
-    return kind == IPOC_CARRY_RICCATI ? nx * nx + 2 * nx + 2 * sy : nx * nx + nx;
-}
-
-size_t ipoc_workspace_bytes(int kind, int N, int nx, int nu, int batch) {
-    (void)nu;
-    if (N < 1 || batch < 1) return 0;
-    // the sharded entry points use the same formula with batch = 1 and forced chunking; take the max
-#define X(a) if (nx == a) { size_t s1 = ws_bytes_impl<a>(kind, N, batch, false); \
-                            size_t s2 = batch == 1 ? ws_bytes_impl<a>(kind, N, 1, true) : 0; return s1 > s2 ? s1 : s2; }
-    IPOC_FOR_NX(X)
-#undef X
-    return 0;
-}
-
-#define CHECK_ARGS(cond) do { if (!(cond)) return IPOC_EINVAL; } while (0)
-#define CHECK_ALIGN(p) do { if ((p) != nullptr && !aligned16(p)) return IPOC_EALIGN; } while (0)
-
-int ipoc_newton_step_f64(int N, int nx, int nu, int batch, const double* fx, const double* fu, const double* ru,
-                         const double* Q, const double* R, const double* M, const double* reg, double* dx, double* du,
-                         double* Kx, double* d, double* pred, int32_t* feasible, void* ws, size_t ws_bytes,
-                         ipoc_stream_t stream) {
-    CHECK_ARGS(N >= 1 && batch >= 1 && fx && fu && ru && Q && R && M && reg && dx && du && Kx && d && pred && feasible && ws);
-    CHECK_ALIGN(fx); CHECK_ALIGN(fu); CHECK_ALIGN(ru); CHECK_ALIGN(Q); CHECK_ALIGN(R); CHECK_ALIGN(M);
-    CHECK_ALIGN(dx); CHECK_ALIGN(du); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(ws);
-#define X(a, b) if (nx == a && nu == b) return newton_step_impl<a, b>(N, batch, fx, fu, ru, Q, R, M, reg, dx, du, Kx, d, pred, feasible, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_DIMS(X)
-#undef X
-    return IPOC_EUNSUPPORTED_DIM;
-}
-
-int ipoc_lqt_bwd_f64(int N, int nx, int nu, int batch, const double* A, const double* B, const double* c,
-                     const double* Xm, const double* U, const double* M, const double* q, const double* p,
-                     const double* ST, const double* vT, double* Kx, double* d, double* S, double* v, double* pred,
-                     int32_t* feasible, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
-    CHECK_ARGS(N >= 1 && batch >= 1 && A && B && Xm && U && M && q && p && ST && Kx && d && pred && feasible && ws);
-    CHECK_ARGS((S == nullptr) == (v == nullptr));
-    CHECK_ALIGN(A); CHECK_ALIGN(B); CHECK_ALIGN(c); CHECK_ALIGN(Xm); CHECK_ALIGN(U); CHECK_ALIGN(M); CHECK_ALIGN(q);
-    CHECK_ALIGN(p); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(ws);
-#define X(a, b) if (nx == a && nu == b) return lqt_bwd_impl<a, b>(N, batch, A, B, c, Xm, U, M, q, p, ST, vT, Kx, d, S, v, pred, feasible, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_DIMS(X)
-#undef X
-    return IPOC_EUNSUPPORTED_DIM;
-}
-
-int ipoc_lqt_fwd_f64(int N, int nx, int nu, int batch, const double* A, const double* B, const double* c,
-                     const double* Kx, const double* d, const double* x0, double* u, double* x, void* ws,
-                     size_t ws_bytes, ipoc_stream_t stream) {
-    CHECK_ARGS(N >= 1 && batch >= 1 && A && B && Kx && d && u && x && ws);
-    CHECK_ALIGN(A); CHECK_ALIGN(B); CHECK_ALIGN(c); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(u); CHECK_ALIGN(x);
-    CHECK_ALIGN(ws);
-#define X(a, b) if (nx == a && nu == b) return lqt_fwd_impl<a, b>(N, batch, A, B, c, Kx, d, x0, u, x, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_DIMS(X)
-#undef X
-    return IPOC_EUNSUPPORTED_DIM;
-}
-
-int ipoc_affine_scan_f64(int reverse, int transpose, int N, int nx, int batch, const double* F, const double* c,
-                         const double* seed, double* out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
-    CHECK_ARGS(N >= 1 && batch >= 1 && F && c && out && ws);
-    CHECK_ALIGN(F); CHECK_ALIGN(c); CHECK_ALIGN(out); CHECK_ALIGN(ws);
-#define X(a) if (nx == a) return affine_scan_impl<a>(reverse, transpose, N, batch, F, c, seed, out, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_NX(X)
-#undef X
-    return IPOC_EUNSUPPORTED_DIM;
-}
-
-int ipoc_reductions_f64(int N, int nu, int nc, int batch, const double* ru, const double* cu, const double* cons,
-                        double* hu_norm, double* cu_norm, int32_t* traj_feasible, void* ws, size_t ws_bytes,
-                        ipoc_stream_t stream) {
-    (void)ws; (void)ws_bytes;
-    CHECK_ARGS(N >= 1 && batch >= 1);
-    CHECK_ARGS((ru == nullptr || hu_norm) && (cu == nullptr || cu_norm) && (cons == nullptr || traj_feasible));
-    k_reductions<<<batch, 256, 0, (cudaStream_t)stream>>>(ru, cu, cons, N, nu, nc, hu_norm, cu_norm, traj_feasible);
-    IPOC_LAUNCH_CHECK();
-    return IPOC_OK;
-}
-
-int ipoc_accept_update_f64(int batch, const double* cost, const double* new_cost, const int32_t* traj_feasible,
-                           const double* pred, const int32_t* bwd_feasible, const int32_t* active, double* rp,
-                           double* r_inc, int32_t* success, double* gain_ratio, ipoc_stream_t stream) {
-    CHECK_ARGS(batch >= 1 && cost && new_cost && traj_feasible && pred && bwd_feasible && rp && r_inc && success);
-    k_accept_update<<<grid_for(batch, 128), 128, 0, (cudaStream_t)stream>>>(batch, cost, new_cost, traj_feasible, pred,
-                                                                            bwd_feasible, active, rp, r_inc, success,
-                                                                            gain_ratio);
-    IPOC_LAUNCH_CHECK();
-    return IPOC_OK;
-}
-
-int ipoc_newton_bwd_reduce_f64(int N, int nx, int nu, const double* fx, const double* fu, const double* ru,
-                               const double* Q, const double* R, const double* M, const double* reg,
-                               double* carry_out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
-    CHECK_ARGS(N >= 1 && fx && fu && ru && Q && R && M && reg && carry_out && ws);
-#define X(a, b) if (nx == a && nu == b) return newton_bwd_reduce_impl<a, b>(N, fx, fu, ru, Q, R, M, reg, carry_out, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_DIMS(X)
-#undef X
-    return IPOC_EUNSUPPORTED_DIM;
-}
-
-int ipoc_newton_bwd_apply_f64(int N, int nx, int nu, int rank, int nranks, const double* fx, const double* fu,
-                              const double* ru, const double* Q, const double* R, const double* M, const double* reg,
-                              const double* carries, const double* ST, double* Kx, double* d, double* pred,
-                              int32_t* feasible, double* fwd_carry_out, void* ws, size_t ws_bytes,
-                              ipoc_stream_t stream) {
-    CHECK_ARGS(N >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && carries && ST && Kx && d && pred && feasible && fwd_carry_out && ws);
-#define X(a, b) if (nx == a && nu == b) return newton_bwd_apply_impl<a, b>(N, rank, nranks, fx, fu, ru, Q, R, M, reg, carries, ST, Kx, d, pred, feasible, fwd_carry_out, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_DIMS(X)
-#undef X
-    return IPOC_EUNSUPPORTED_DIM;
-}
-
-int ipoc_newton_fwd_apply_f64(int N, int nx, int nu, int rank, int nranks, const double* fx, const double* fu,
-                              const double* Kx, const double* d, const double* fwd_carries, double* dx, double* du,
-                              void* ws, size_t ws_bytes, ipoc_stream_t stream) {
-    CHECK_ARGS(N >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && fx && fu && Kx && d && fwd_carries && dx && du && ws);
-#define X(a, b) if (nx == a && nu == b) return newton_fwd_apply_impl<a, b>(N, rank, nranks, fx, fu, Kx, d, fwd_carries, dx, du, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_DIMS(X)
-#undef X
-    return IPOC_EUNSUPPORTED_DIM;
-}
-
-int ipoc_affine_reduce_f64(int reverse, int transpose, int N, int nx, const double* F, const double* c,
-                           double* carry_out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
-    CHECK_ARGS(N >= 1 && F && c && carry_out && ws);
-#define X(a) if (nx == a) return affine_reduce_impl<a>(reverse, transpose, N, F, c, carry_out, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_NX(X)
-#undef X
-    return IPOC_EUNSUPPORTED_DIM;
-}
-
-int ipoc_affine_apply_f64(int reverse, int transpose, int N, int nx, int rank, int nranks, const double* F,
-                          const double* c, const double* carries, const double* seed, double* out, void* ws,
-                          size_t ws_bytes, ipoc_stream_t stream) {
-    CHECK_ARGS(N >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && F && c && carries && seed && out && ws);
-#define X(a) if (nx == a) return affine_apply_impl<a>(reverse, transpose, N, rank, nranks, F, c, carries, seed, out, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_NX(X)
-#undef X
-    return IPOC_EUNSUPPORTED_DIM;
-}
-
-size_t ipoc_newton_step_host_scratch_bytes(int N, int nx, int nu, int batch) {
-    const size_t per = (size_t)nx * nx * 2 + (size_t)nx * nu * 2 + (size_t)nu * nu + nu;   // inputs
-    const size_t outs = (size_t)nx + nu + (size_t)nu * nx + nu;
-    size_t b = ((size_t)N * per + (size_t)(N + 1) * outs) * batch * sizeof(double) + 64 * 256;
-    b += ipoc_workspace_bytes(IPOC_WS_NEWTON_STEP, N, nx, nu, batch) + 4096 * (size_t)batch;
-    return b;
-}
-
-int ipoc_newton_step_host_f64(int N, int nx, int nu, int batch, const double* fx, const double* fu, const double* ru,
-                              const double* Q, const double* R, const double* M, const double* reg, double* dx,
-                              double* du, double* pred, int32_t* feasible, void* dws, size_t dws_bytes,
-                              ipoc_stream_t stream) {
-    CHECK_ARGS(N >= 1 && batch >= 1 && dws);
-    if (dws_bytes < ipoc_newton_step_host_scratch_bytes(N, nx, nu, batch)) return IPOC_EWORKSPACE;
-    cudaStream_t st = (cudaStream_t)stream;
-    Bump bp{(char*)dws, 0, dws_bytes, false};
-    const size_t T = (size_t)N * batch;
-    double* dfx = bp.take<double>(T * nx * nx);
-    double* dfu = bp.take<double>(T * nx * nu);
-    double* dru = bp.take<double>(T * nu);
-    double* dQ = bp.take<double>(T * nx * nx);
-    double* dR = bp.take<double>(T * nu * nu);
-    double* dM = bp.take<double>(T * nx * nu);
-    double* dreg = bp.take<double>(batch);
-    double* ddx = bp.take<double>((size_t)(N + 1) * batch * nx);
-    double* ddu = bp.take<double>(T * nu);
-    double* dKx = bp.take<double>(T * nu * nx);
-    double* dd = bp.take<double>(T * nu);
-    double* dpred = bp.take<double>(batch);
-    int32_t* dfeas = bp.take<int32_t>(batch);
-    const size_t wsb = ipoc_workspace_bytes(IPOC_WS_NEWTON_STEP, N, nx, nu, batch);
-    void* ws = bp.take<char>(wsb);
-    if (bp.off > dws_bytes) return IPOC_EWORKSPACE;
-    const size_t D = sizeof(double);
-    bool ok = true;
-    ok &= cudaMemcpyAsync(dfx, fx, T * nx * nx * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
-    ok &= cudaMemcpyAsync(dfu, fu, T * nx * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
-    ok &= cudaMemcpyAsync(dru, ru, T * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
-    ok &= cudaMemcpyAsync(dQ, Q, T * nx * nx * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
-    ok &= cudaMemcpyAsync(dR, R, T * nu * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
-    ok &= cudaMemcpyAsync(dM, M, T * nx * nu * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
-    ok &= cudaMemcpyAsync(dreg, reg, batch * D, cudaMemcpyHostToDevice, st) == cudaSuccess;
-    if (!ok) return IPOC_ECUDA;
-    int rc = ipoc_newton_step_f64(N, nx, nu, batch, dfx, dfu, dru, dQ, dR, dM, dreg, ddx, ddu, dKx, dd, dpred, dfeas, ws,
-                                  wsb, stream);
-    if (rc) return rc;
-    ok &= cudaMemcpyAsync(dx, ddx, (size_t)(N + 1) * batch * nx * D, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-    ok &= cudaMemcpyAsync(du, ddu, T * nu * D, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-    ok &= cudaMemcpyAsync(pred, dpred, batch * D, cudaMemcpyDeviceToHost, st) == cudaSuccess;
-    ok &= cudaMemcpyAsync(feasible, dfeas, batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st) == cudaSuccess;
-    return ok ? IPOC_OK : IPOC_ECUDA;
-}
-
-}  // extern "C"

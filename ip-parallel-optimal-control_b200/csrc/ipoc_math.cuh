@@ -128,6 +128,9 @@ template <int NX>
 struct AffOp {
     using Elem = AffElem<NX>;
     using Val = AffVal<NX>;
+    static constexpr const char* tag_mid_up = "k_mid_up_aff";
+    static constexpr const char* tag_mid_down = "k_mid_down_aff";
+    static constexpr const char* tag_top = "k_top_aff";
     IPOC_DEV static void identity(Elem& e) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
@@ -206,6 +209,9 @@ template <int NX>
 struct RicOp {
     using Elem = RicElem<NX>;
     using Val = RicVal<NX>;
+    static constexpr const char* tag_mid_up = "k_mid_up_ric";
+    static constexpr const char* tag_mid_down = "k_mid_down_ric";
+    static constexpr const char* tag_top = "k_top_ric";
 
     IPOC_DEV static void identity(Elem& e) {
 #pragma unroll

@@ -24,7 +24,7 @@ _SIGS = {
     "ipoc_lqt_bwd_f64": (_I, [_I] * 4 + [_P] * 16 + [_P, _SZ, _P]),
     "ipoc_lqt_fwd_f64": (_I, [_I] * 4 + [_P] * 8 + [_P, _SZ, _P]),
     "ipoc_affine_scan_f64": (_I, [_I] * 5 + [_P] * 4 + [_P, _SZ, _P]),
-    "ipoc_reductions_f64": (_I, [_I] * 4 + [_P] * 6 + [_P, _SZ, _P]),
+    "ipoc_reductions_f64": (_I, [_I] * 4 + [_P] * 8 + [_P]),
     "ipoc_accept_update_f64": (_I, [_I] + [_P] * 10 + [_P]),
     "ipoc_newton_bwd_reduce_f64": (_I, [_I] * 3 + [_P] * 8 + [_P, _SZ, _P]),
     "ipoc_newton_bwd_apply_f64": (_I, [_I] * 5 + [_P] * 14 + [_P, _SZ, _P]),
@@ -33,6 +33,8 @@ _SIGS = {
     "ipoc_affine_apply_f64": (_I, [_I] * 6 + [_P] * 5 + [_P, _SZ, _P]),
     "ipoc_newton_step_host_scratch_bytes": (_SZ, [_I] * 4),
     "ipoc_newton_step_host_f64": (_I, [_I] * 4 + [_P] * 11 + [_P, _SZ, _P]),
+    "ipoc_profile_begin": (_I, [_P]),
+    "ipoc_profile_end": (_I, [ctypes.c_char_p, _SZ, ctypes.POINTER(ctypes.c_float), _I]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -84,6 +86,8 @@ def dev_f64(t, device=None):
     t = torch.as_tensor(t)
     if device is not None and t.device != torch.device(device):
         t = t.to(device)
+    if not t.is_cuda:
+        raise IpocError("ipoc kernels need CUDA tensors; there is no CPU fallback")
     if t.dtype != torch.float64:
         t = t.to(torch.float64)
     if not t.is_contiguous():

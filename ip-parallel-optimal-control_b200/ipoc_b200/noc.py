@@ -93,8 +93,9 @@ def noc_to_lqt(ru, Q, R, M, A, B) -> LQT:
 
 
 # ------------------------------------------------------------------ K4 / A8
-def reductions(ru=None, cu=None, cons=None):
-    """(max|ru|, ||cu||_F, all(cons<=0)) per problem — ref :158, :116, :45-47.  Inputs (N,·) or (B,N,·)."""
+def reductions(ru=None, cu=None, cons=None, rp=None, reg_out=None):
+    """(max|ru|, ||cu||_F, all(cons<=0)) per problem — ref :158, :116, :45-47.  Inputs (N,·) or (B,N,·).
+    With `rp` and `reg_out` (device, one per problem) also writes reg_out = rp * ||cu||_F (:117)."""
     ref = next(t for t in (ru, cu, cons) if t is not None)
     dev = ref.device
     batched = ref.dim() == 3
@@ -109,7 +110,7 @@ def reductions(ru=None, cu=None, cons=None):
     fe = torch.ones(Bn, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         L.check(L.lib().ipoc_reductions_f64(N, nu, nc, Bn, L.ptr(ru), L.ptr(cu), L.ptr(cons), L.ptr(hu), L.ptr(cn),
-                                            L.ptr(fe), None, 0, L.stream_ptr()))
+                                            L.ptr(fe), L.ptr(rp), L.ptr(reg_out), L.stream_ptr()))
     return hu, cn, fe
 
 

@@ -58,7 +58,7 @@ def test_newton_step_vs_oracle(nx, nu, N):
     fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu)
     reg = 0.37
     dxo, duo, Kxo, do, predo, feaso = oracle_newton(fx, fu, ru, Q, R, M, reg)
-    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), torch.tensor([reg], device=DEV))
+    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), T([reg]))
     tol = 1e-11 if nx <= 4 else 1e-10
     assert relerr(N_(Kx), Kxo) < tol and relerr(N_(d), do) < tol
     assert relerr(N_(dx), dxo) < tol and relerr(N_(du), duo) < tol
@@ -75,7 +75,7 @@ def test_newton_step_all_hierarchy_shapes(tuning, nx, nu, N):
     fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu)
     dxo, duo, Kxo, do, predo, feaso = oracle_newton(fx, fu, ru, Q, R, M, 0.05)
     _lib.lib().ipoc_set_tuning(*tuning)
-    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), torch.tensor([0.05], device=DEV))
+    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), T([0.05]))
     assert relerr(N_(dx), dxo) < 1e-10 and relerr(N_(du), duo) < 1e-10
     assert relerr(N_(Kx), Kxo) < 1e-10 and relerr(N_(d), do) < 1e-10
     assert abs(float(pred) - predo) <= 1e-10 * abs(predo) and bool(feas[0]) == bool(feaso)
@@ -204,7 +204,7 @@ def test_time_sharded_virtual_ranks(P, nx, nu, N):
     from ipoc_b200 import noc, sharded
     rng = np.random.default_rng(P + N)
     fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu)
-    reg = torch.tensor([0.2], device=DEV)
+    reg = T([0.2])
     args = [T(a) for a in (fx, fu, ru, Q, R, M)]
     dx1, du1, Kx1, d1, pred1, feas1 = noc.newton_step(*args, reg)
     dx, du, Kx, d, pred, feas = sharded.newton_step_virtual_ranks(*args, reg, P)
@@ -232,7 +232,7 @@ def test_newton_step_kkt_at_full_size(nx, nu, N):
     from ipoc_b200 import noc
     rng = np.random.default_rng(N)
     fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu, dt=1e-3)
-    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), torch.tensor([0.3], device=DEV))
+    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), T([0.3]))
     r_dyn, r_stat, r_x0 = _kkt_residuals(fx, fu, ru, Q, R, M, 0.3, N_(dx), N_(du))
     assert r_x0 == 0.0 and r_dyn < 1e-9 and r_stat < 1e-8
     assert bool(feas[0]) and float(pred) < 0
@@ -243,10 +243,10 @@ def test_nonconvex_and_nan_are_data_not_errors():
     rng = np.random.default_rng(3)
     fx, fu, ru, Q, R, M = random_lq(rng, 50, 2, 1)
     R[17] = -5.0   # G < 0 at one step -> infeasible flag, no exception
-    _, _, _, _, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), torch.tensor([0.0], device=DEV))
+    _, _, _, _, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), T([0.0]))
     assert not bool(feas[0])
     ru[3] = np.nan
-    _, du, _, _, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), torch.tensor([0.0], device=DEV))
+    _, du, _, _, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), T([0.0]))
     assert np.isnan(float(pred))
 
 
