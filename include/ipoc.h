@@ -125,12 +125,14 @@ int ipoc_affine_scan_f64(int reverse, int transpose, int N, int nx, int batch,
  *   in : ru (N,nu) cu (N,nu) cons (N,nc);  out per problem: hu_norm, cu_norm, traj_feasible
  * If `rp` and `reg` are given (with cu), also reg = rp * ||cu||_F (:117) — the device scalar that
  * ipoc_newton_step_f64 consumes, so the regularisation never visits the host.
- * Fixed reduction order -> bit-reproducible run to run.
+ * Two launches (per-slice partials, then a fixed-order fold) -> bit-reproducible run to run.
+ * Workspace: ipoc_workspace_bytes(IPOC_WS_REDUCTIONS, N, max(nu, nc), nu, batch).
  */
 int ipoc_reductions_f64(int N, int nu, int nc, int batch,
                         const double* ru, const double* cu, const double* cons,
                         double* hu_norm, double* cu_norm, int32_t* traj_feasible,
-                        const double* rp, double* reg, ipoc_stream_t stream);
+                        const double* rp, double* reg,
+                        void* ws, size_t ws_bytes, ipoc_stream_t stream);
 
 /* ---- A8: scalar accept / regularisation update, on device --------------------------------
  * (ref noc/par_interior_point_newton.py:159-173) for `batch` independent problems:

@@ -53,54 +53,107 @@ struct Bump {
     } while (0)
 
 // ------------------------------------------------------------------ K4 reductions + A8 update
-static __global__ void __launch_bounds__(256)
-k_reductions(const double* __restrict__ ru, const double* __restrict__ cu, const double* __restrict__ cons,
-             int N, int nu, int nc, double* __restrict__ hu_norm, double* __restrict__ cu_norm,
-             int32_t* __restrict__ traj_feasible, const double* __restrict__ rp, double* __restrict__ reg) {
-    __shared__ double s_max[256];
-    __shared__ double s_sq[256];
-    __shared__ int s_ok[256];
-    const int b = blockIdx.x, t = threadIdx.x;
+// K4, stage 1: grid (nblk, batch); block j of problem b reduces its contiguous slice of the three
+// arrays to (max|ru| [NaN-propagating], sum cu^2, all(cons<=0)) -> partials[(b*nblk + j)*3 ..].
+// Stage 2 (one block per problem) folds the nblk partials in index order -> bit-reproducible.
+constexpr int kRedThreads = 256;
+static __device__ __forceinline__ double nan_max(double a, double c) {
+    return (a != a || c != c) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(a, c);
+}
+static __global__ void __launch_bounds__(kRedThreads)
+k_reduce_partial(const double* __restrict__ ru, const double* __restrict__ cu, const double* __restrict__ cons,
+                 int N, int nu, int nc, int nblk, double* __restrict__ partials) {
+    __shared__ double s_max[kRedThreads];
+    __shared__ double s_sq[kRedThreads];
+    __shared__ int s_ok[kRedThreads];
+    const int b = blockIdx.y, j = blockIdx.x, t = threadIdx.x;
     double mx = 0.0, sq = 0.0;
-    int ok = 1, nan_seen = 0;
+    int ok = 1;
+    auto slice = [&](long long total, long long& lo, long long& hi) {
+        const long long per = (total + nblk - 1) / nblk;
+        lo = (long long)j * per;
+        hi = lo + per < total ? lo + per : total;
+    };
+    long long lo, hi;
     if (ru != nullptr) {
         const double* p = ru + (size_t)b * N * nu;
-        for (long long i = t; i < (long long)N * nu; i += 256) {
-            const double v = fabs(p[i]);
-            if (v != v) nan_seen = 1;
-            mx = fmax(mx, v);
-        }
+        slice((long long)N * nu, lo, hi);
+        for (long long i = lo + t; i < hi; i += kRedThreads) mx = nan_max(mx, fabs(p[i]));
     }
     if (cu != nullptr) {
         const double* p = cu + (size_t)b * N * nu;
-        for (long long i = t; i < (long long)N * nu; i += 256) sq += p[i] * p[i];
+        slice((long long)N * nu, lo, hi);
+        for (long long i = lo + t; i < hi; i += kRedThreads) sq += p[i] * p[i];
     }
     if (cons != nullptr) {
         const double* p = cons + (size_t)b * N * nc;
-        for (long long i = t; i < (long long)N * nc; i += 256) ok &= (p[i] <= 0.0) ? 1 : 0;
+        slice((long long)N * nc, lo, hi);
+        for (long long i = lo + t; i < hi; i += kRedThreads) ok &= (p[i] <= 0.0) ? 1 : 0;
     }
-    s_max[t] = nan_seen ? __longlong_as_double(0x7ff8000000000000LL) : mx;
+    s_max[t] = mx;
     s_sq[t] = sq;
     s_ok[t] = ok;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
         if (t < o) {
-            const double a = s_max[t], c = s_max[t + o];
-            s_max[t] = (a != a || c != c) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(a, c);
+            s_max[t] = nan_max(s_max[t], s_max[t + o]);
             s_sq[t] += s_sq[t + o];
             s_ok[t] &= s_ok[t + o];
         }
         __syncthreads();
     }
     if (t == 0) {
-        if (ru != nullptr) hu_norm[b] = s_max[0];
-        if (cu != nullptr) {
+        double* o = partials + ((size_t)b * nblk + j) * 3;
+        o[0] = s_max[0];
+        o[1] = s_sq[0];
+        o[2] = (double)s_ok[0];
+    }
+}
+
+static __global__ void __launch_bounds__(kRedThreads)
+k_reduce_final(const double* __restrict__ partials, int nblk, int has_ru, int has_cu, int has_cons,
+               double* __restrict__ hu_norm, double* __restrict__ cu_norm, int32_t* __restrict__ traj_feasible,
+               const double* __restrict__ rp, double* __restrict__ reg) {
+    __shared__ double s_max[kRedThreads];
+    __shared__ double s_sq[kRedThreads];
+    __shared__ int s_ok[kRedThreads];
+    const int b = blockIdx.x, t = threadIdx.x;
+    double mx = 0.0, sq = 0.0;
+    int ok = 1;
+    for (int j = t; j < nblk; j += kRedThreads) {
+        const double* p = partials + ((size_t)b * nblk + j) * 3;
+        mx = nan_max(mx, p[0]);
+        sq += p[1];
+        ok &= (p[2] != 0.0) ? 1 : 0;
+    }
+    s_max[t] = mx;
+    s_sq[t] = sq;
+    s_ok[t] = ok;
+    __syncthreads();
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+        if (t < o) {
+            s_max[t] = nan_max(s_max[t], s_max[t + o]);
+            s_sq[t] += s_sq[t + o];
+            s_ok[t] &= s_ok[t + o];
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        if (has_ru) hu_norm[b] = s_max[0];
+        if (has_cu) {
             const double nrm = sqrt(s_sq[0]);
             cu_norm[b] = nrm;
             if (rp != nullptr && reg != nullptr) reg[b] = rp[b] * nrm;   // ref :117
         }
-        if (cons != nullptr) traj_feasible[b] = s_ok[0];
+        if (has_cons) traj_feasible[b] = s_ok[0];
     }
+}
+
+static int reduce_blocks(int N, int width, int batch) {
+    long long per_problem = ((long long)N * width + 8191) / 8192;   // >= 8192 entries per block
+    long long cap = (148LL * 8 + batch - 1) / batch;                // fill the chip, not more
+    long long n = per_problem < cap ? per_problem : cap;
+    return (int)(n < 1 ? 1 : n);
 }
 
 static __global__ void k_accept_update(int batch, const double* __restrict__ cost, const double* __restrict__ new_cost,
@@ -177,8 +230,9 @@ int ipoc_carry_doubles(int kind, int nx) {
 }
 
 size_t ipoc_workspace_bytes(int kind, int N, int nx, int nu, int batch) {
-    (void)nu;
     if (N < 1 || batch < 1) return 0;
+    if (kind == IPOC_WS_REDUCTIONS)   // here `nx` carries max(nu, nc)
+        return (size_t)batch * reduce_blocks(N, nx > nu ? nx : nu, batch) * 3 * sizeof(double) + 256;
     // the sharded entry points use the same formula with batch = 1 and forced chunking; take the max
 #define X(a) if (nx == a) { size_t s1 = nx_ws_bytes<a>(kind, N, batch, false); \
                             size_t s2 = batch == 1 ? nx_ws_bytes<a>(kind, N, 1, true) : 0; return s1 > s2 ? s1 : s2; }
@@ -241,11 +295,18 @@ int ipoc_affine_scan_f64(int reverse, int transpose, int N, int nx, int batch, c
 
 int ipoc_reductions_f64(int N, int nu, int nc, int batch, const double* ru, const double* cu, const double* cons,
                         double* hu_norm, double* cu_norm, int32_t* traj_feasible, const double* rp, double* reg,
-                        ipoc_stream_t stream) {
-    CHECK_ARGS(N >= 1 && batch >= 1);
+                        void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && ws);
     CHECK_ARGS((ru == nullptr || hu_norm) && (cu == nullptr || cu_norm) && (cons == nullptr || traj_feasible));
+    const int width = nu > nc ? nu : nc;
+    const int nblk = reduce_blocks(N, width, batch);
+    if (ws_bytes < (size_t)batch * nblk * 3 * sizeof(double)) return IPOC_EWORKSPACE;
     cudaStream_t st_ = (cudaStream_t)stream;
-    k_reductions<<<batch, 256, 0, st_>>>(ru, cu, cons, N, nu, nc, hu_norm, cu_norm, traj_feasible, rp, reg);
+    double* partials = (double*)ws;
+    k_reduce_partial<<<dim3(nblk, batch), kRedThreads, 0, st_>>>(ru, cu, cons, N, nu, nc, nblk, partials);
+    IPOC_API_LAUNCH_CHECK(st_);
+    k_reduce_final<<<batch, kRedThreads, 0, st_>>>(partials, nblk, ru != nullptr, cu != nullptr, cons != nullptr,
+                                                   hu_norm, cu_norm, traj_feasible, rp, reg);
     IPOC_API_LAUNCH_CHECK(st_);
     return IPOC_OK;
 }

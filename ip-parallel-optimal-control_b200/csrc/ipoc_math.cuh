@@ -29,6 +29,7 @@ struct Sym {
 // the arrays stay in registers.
 template <int N, int R>
 IPOC_DEV void lu_solve(double (&W)[N][N], double (&X)[N][R]) {
+    double inv[N];   // reciprocal pivots: one FP64 reciprocal per column instead of a division per entry
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         if (k < N - 1) {
@@ -58,10 +59,10 @@ IPOC_DEV void lu_solve(double (&W)[N][N], double (&X)[N][R]) {
                 }
             }
         }
-        const double inv = 1.0 / W[k][k];
+        inv[k] = 1.0 / W[k][k];
 #pragma unroll
         for (int i = k + 1; i < N; ++i) {
-            const double m = W[i][k] * inv;
+            const double m = W[i][k] * inv[k];
 #pragma unroll
             for (int j = k + 1; j < N; ++j) W[i][j] -= m * W[k][j];
 #pragma unroll
@@ -75,7 +76,7 @@ IPOC_DEV void lu_solve(double (&W)[N][N], double (&X)[N][R]) {
             double s = X[k][j];
 #pragma unroll
             for (int i = k + 1; i < N; ++i) s -= W[k][i] * X[i][j];
-            X[k][j] = s / W[k][k];
+            X[k][j] = s * inv[k];
         }
     }
 }
@@ -378,8 +379,9 @@ struct StepLQ {
 template <int NU, int R>
 IPOC_DEV void small_solve(const double (&U)[NU][NU], double (&Y)[NU][R]) {
     if constexpr (NU == 1) {
+        const double inv = 1.0 / U[0][0];
 #pragma unroll
-        for (int j = 0; j < R; ++j) Y[0][j] = Y[0][j] / U[0][0];
+        for (int j = 0; j < R; ++j) Y[0][j] = Y[0][j] * inv;
     } else {
         double W[NU][NU];
 #pragma unroll

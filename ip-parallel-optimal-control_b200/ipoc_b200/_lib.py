@@ -24,7 +24,7 @@ _SIGS = {
     "ipoc_lqt_bwd_f64": (_I, [_I] * 4 + [_P] * 16 + [_P, _SZ, _P]),
     "ipoc_lqt_fwd_f64": (_I, [_I] * 4 + [_P] * 8 + [_P, _SZ, _P]),
     "ipoc_affine_scan_f64": (_I, [_I] * 5 + [_P] * 4 + [_P, _SZ, _P]),
-    "ipoc_reductions_f64": (_I, [_I] * 4 + [_P] * 8 + [_P]),
+    "ipoc_reductions_f64": (_I, [_I] * 4 + [_P] * 8 + [_P, _SZ, _P]),
     "ipoc_accept_update_f64": (_I, [_I] + [_P] * 10 + [_P]),
     "ipoc_newton_bwd_reduce_f64": (_I, [_I] * 3 + [_P] * 8 + [_P, _SZ, _P]),
     "ipoc_newton_bwd_apply_f64": (_I, [_I] * 5 + [_P] * 14 + [_P, _SZ, _P]),

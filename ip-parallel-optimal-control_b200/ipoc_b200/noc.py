@@ -108,9 +108,10 @@ def reductions(ru=None, cu=None, cons=None, rp=None, reg_out=None):
     hu = torch.zeros(Bn, dtype=torch.float64, device=dev)
     cn = torch.zeros(Bn, dtype=torch.float64, device=dev)
     fe = torch.ones(Bn, dtype=torch.int32, device=dev)
+    ws, nbytes = L.workspace(L.WS_REDUCTIONS, N, max(nu, nc), nu, Bn, dev)
     with torch.cuda.device(dev):
         L.check(L.lib().ipoc_reductions_f64(N, nu, nc, Bn, L.ptr(ru), L.ptr(cu), L.ptr(cons), L.ptr(hu), L.ptr(cn),
-                                            L.ptr(fe), L.ptr(rp), L.ptr(reg_out), L.stream_ptr()))
+                                            L.ptr(fe), L.ptr(rp), L.ptr(reg_out), L.ptr(ws), nbytes, L.stream_ptr()))
     return hu, cn, fe
 
 

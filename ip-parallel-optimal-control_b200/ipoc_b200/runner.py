@@ -44,6 +44,8 @@ class NewtonPass:
         lib = L.lib()
         self.ws_aff_bytes = lib.ipoc_workspace_bytes(L.WS_AFFINE_SCAN, N, nx, nu, B)
         self.ws_new_bytes = lib.ipoc_workspace_bytes(L.WS_NEWTON_STEP, N, nx, nu, B)
+        self.ws_red_bytes = lib.ipoc_workspace_bytes(L.WS_REDUCTIONS, N, max(nu, self.nc), nu, B)
+        self.ws_red = torch.empty(self.ws_red_bytes, dtype=torch.uint8, device=dev)
         self.ws_aff = torch.empty(self.ws_aff_bytes, dtype=torch.uint8, device=dev)
         self.ws_new = torch.empty(self.ws_new_bytes, dtype=torch.uint8, device=dev)
         self.graph = None
@@ -76,11 +78,11 @@ class NewtonPass:
         p, lib, s = L.ptr, L.lib(), L.stream_ptr()
         self.costates()
         L.check(lib.ipoc_reductions_f64(self.N, self.nu, self.nc, self.B, p(self.ru), p(self.cu), None, p(self.hu),
-                                        p(self.cu_norm), None, p(self.rp), p(self.reg), s))
+                                        p(self.cu_norm), None, p(self.rp), p(self.reg), p(self.ws_red), self.ws_red_bytes, s))
         self.newton()
         if self.cons is not None:
             L.check(lib.ipoc_reductions_f64(self.N, self.nu, self.nc, self.B, None, None, p(self.cons), None, None,
-                                            p(self.traj_feas), None, None, s))
+                                            p(self.traj_feas), None, None, p(self.ws_red), self.ws_red_bytes, s))
         L.check(lib.ipoc_accept_update_f64(self.B, p(self.cost), p(self.new_cost), p(self.traj_feas), p(self.pred),
                                            p(self.bwd_feas), None, p(self.rp), p(self.r_inc), p(self.success),
                                            p(self.gain), s))
