@@ -2,17 +2,24 @@
 // Hand-written sm_100a FP64 kernels for the par IP-Newton hot path (templated on NX, NU).
 // Instantiated once per NX by ipoc_nx.cu; the C ABI lives in ipoc_api.cu.
 //
-// Scan organisation (all three scans: K1 costates, K2 Riccati, K3 forward):
-//   a hierarchical reduce / seeded-rescan.  A leaf thread folds `T0` consecutive time steps
-//   sequentially (work-optimal, no idle lanes), mid levels fold `Tm` aggregates per thread, a
-//   single CTA per sequence scans the few hundred top-level aggregates (warp-shuffle
-//   Kogge-Stone + shared-memory warp carries), and the way down only propagates VALUES
-//   ((S, v) for K2, a state vector for K1/K3), which is roughly half the cost of combining
-//   full elements.  Aggregates live in SoA planes (component-major) so that neighbouring
-//   threads touch neighbouring addresses.  No spin-waiting between CTAs anywhere, so every call
-//   is graph-capturable and cannot hang.
-//   With enough independent problems (`batch`) the plan degenerates to one chunk per problem:
-//   a single pass, no up-sweep at all.
+// Scan organisation (all three scans: K1 costates, K2 Riccati, K3 forward): hierarchical
+// reduce / seeded re-scan.
+//   leaf-up   : a thread folds `T0` consecutive time steps sequentially (work-optimal); the 32
+//               thread aggregates of a warp are then scanned with shuffles (Kogge-Stone) inside
+//               the same kernel, where the latency hides behind the other resident warps; every
+//               thread stores its in-warp inclusive aggregate, every warp its total.
+//   levels    : warp totals are folded by mid kernels only when there are more than `top_max` of
+//               them; a single CTA per sequence scans the rest (shuffles + smem warp carries).
+//   leaf-down : only VALUES travel down ((S, v) for K2, a state vector for K1/K3): a thread applies
+//               its neighbour's stored in-warp aggregate to the value entering its warp and re-walks
+//               its chunk with the cheap seeded recursion, emitting outputs.
+// Global loads of the leaf kernels are warp-cooperative cp.async copies into a double-buffered
+// shared-memory stage (rows padded to an odd number of 16-byte units -> conflict-free LDS.128):
+// each lane needs ITS OWN chunk's time step, i.e. a stride-T0 gather; fetching it with per-lane
+// loads costs 32 L1 wavefronts per instruction and made the first version L1-bound (profiles/r01a).
+// Aggregates live in SoA planes (component-major).  There is no spin-waiting between CTAs, so
+// every call is graph-capturable and cannot hang.  With enough independent problems (`batch`) the
+// plan degenerates to one sequence per lane: a single pass, no up-sweep at all.
 //
 // K2's down-sweep emits K3's leaf aggregates for free (same chunks), so one Newton step reads
 // fx, fu, Q, R, M, ru twice (the second time from L2 when the working set fits) and Kx, d once.
@@ -52,6 +59,14 @@ IPOC_DEV void soa_store(const T& t, double* __restrict__ base, size_t stride, si
     for (int c = 0; c < SZ; ++c) base[(size_t)c * stride + idx] = t.r[c];
 }
 template <class T>
+IPOC_DEV T shfl_down_all(const T& t, int delta) {
+    constexpr int SZ = sizeof(T) / sizeof(double);
+    T o;
+#pragma unroll
+    for (int c = 0; c < SZ; ++c) o.r[c] = __shfl_down_sync(0xffffffffu, t.r[c], delta);
+    return o;
+}
+template <class T>
 IPOC_DEV T shfl_up_all(const T& t, int delta) {
     constexpr int SZ = sizeof(T) / sizeof(double);
     T o;
@@ -88,23 +103,70 @@ IPOC_DEV void st_vec(double* __restrict__ p, const double* src) {
     }
 }
 
+// In-warp inclusive scan of one aggregate per lane, in SCAN order, through a per-warp shared
+// scratch `ws` of 2 x ESZ x 32 doubles (two component-major buffers, ping-pong): both operands of
+// every combine are read from shared memory and the result goes back to shared memory, so no
+// aggregate has to live in registers during the scan.  Returns the buffer holding the result.
+// reverse = true : scan order runs from lane 31 down to lane 0 (backward-in-time scans);
+//                  afterwards lane l holds the composition of lanes 31..l, lane 0 the warp total.
+// reverse = false: lane l holds the composition of lanes 0..l, lane 31 the warp total.
+template <class Op>
+constexpr size_t scan_scratch_bytes() { return 2 * sizeof(typename Op::Elem) * 32; }
+
+template <class Op>
+IPOC_DEV double* warp_scan_mem(double* ws, int lane, bool reverse) {
+    constexpr int ESZ = sizeof(typename Op::Elem) / sizeof(double);
+    int cur = 0;
+#pragma unroll 1
+    for (int delta = 1; delta < 32; delta <<= 1) {
+        const double* src = ws + cur * (ESZ * 32);
+        double* dst = ws + (cur ^ 1) * (ESZ * 32) + lane;
+        const int partner = reverse ? lane + delta : lane - delta;
+        if (partner >= 0 && partner < 32) {
+            Op::compose_mm(dst, 32, src + partner, 32, src + lane, 32);
+        } else {
+#pragma unroll
+            for (int c = 0; c < ESZ; ++c) dst[c * 32] = src[c * 32 + lane];
+        }
+        __syncwarp();
+        cur ^= 1;
+    }
+    return ws + cur * (ESZ * 32);
+}
+// Register-resident variant for the leaf kernels (many warps per SM, code stays hot): the combine
+// is inlined, both operands are read from one shared buffer, the result stays in registers.
+template <class Op>
+IPOC_DEV void warp_scan(typename Op::Elem& a, double* ws, int lane, bool reverse) {
+    constexpr int ESZ = sizeof(typename Op::Elem) / sizeof(double);
+    using View = typename Op::View;
+#pragma unroll 1
+    for (int delta = 1; delta < 32; delta <<= 1) {
+#pragma unroll
+        for (int c = 0; c < ESZ; ++c) ws[c * 32 + lane] = a.r[c];
+        __syncwarp();
+        const int partner = reverse ? lane + delta : lane - delta;
+        if (partner >= 0 && partner < 32) Op::compose_t(a, View{ws + partner, 32}, View{ws + lane, 32});
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ generic mid / top kernels
 template <class Op>
 __global__ void __launch_bounds__(kMidThreads)
 k_mid_up(const double* __restrict__ in, size_t istride, int n_in,
          double* __restrict__ out, size_t ostride, int n_out, int T, int batch) {
+    constexpr int ESZ = sizeof(typename Op::Elem) / sizeof(double);
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)batch * n_out) return;
     const int b = (int)(g / n_out), j2 = (int)(g % n_out);
     const int j0 = j2 * T, j1 = min(n_in, j0 + T);
     const size_t base = (size_t)b * n_in;
-    typename Op::Elem a, e;
-    soa_load(a, in, istride, base + j0);
-    for (int j = j0 + 1; j < j1; ++j) {
-        soa_load(e, in, istride, base + j);
-        Op::compose(a, a, e);
-    }
-    soa_store(a, out, ostride, (size_t)g);
+    double acc[ESZ];   // running aggregate (thread-local memory, read through a stride-1 view)
+#pragma unroll
+    for (int c = 0; c < ESZ; ++c) acc[c] = in[(size_t)c * istride + base + j0];
+    for (int j = j0 + 1; j < j1; ++j) Op::compose_mm(acc, 1, acc, 1, in + base + j, (int)istride);
+#pragma unroll
+    for (int c = 0; c < ESZ; ++c) out[(size_t)c * ostride + (size_t)g] = acc[c];
 }
 
 template <class Op>
@@ -118,81 +180,103 @@ k_mid_down(const double* __restrict__ agg, size_t astride, int n_in,
     const int j0 = j2 * T, j1 = min(n_in, j0 + T);
     const size_t base = (size_t)b * n_in;
     typename Op::Val v;
-    typename Op::Elem e;
     soa_load(v, vals_out, vostride, (size_t)g);
     for (int j = j0; j < j1; ++j) {
         soa_store(v, vals_in, vistride, base + j);
-        if (j + 1 < j1) {
-            soa_load(e, agg, astride, base + j);
-            Op::apply(v, e, v);
-        }
+        if (j + 1 < j1) Op::apply_mm(v, agg + base + j, (int)astride);
+    }
+}
+
+// Side job a top kernel can do for its sequence (saves a launch): fixed-order reduction of the
+// per-warp pred / feasibility partials of K2 -> pred = -1/2 sum d'Gd, feasible = AND (G > 0).
+struct PredJob {
+    const double* pred_part;
+    const int* feas_part;
+    int n;
+    double* pred;
+    int32_t* feasible;
+};
+IPOC_DEV void pred_reduce(const PredJob& pj, int b, int lane) {   // one full warp; fixed order
+    double acc = 0.0;
+    int f = 1;
+    for (int j = lane; j < pj.n; j += 32) {
+        acc += pj.pred_part[(size_t)b * pj.n + j];
+        f &= pj.feas_part[(size_t)b * pj.n + j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        f &= __shfl_xor_sync(0xffffffffu, f, o);
+    }
+    if (lane == 0) {
+        pj.pred[b] = -0.5 * acc;
+        pj.feasible[b] = f;
     }
 }
 
 // One CTA per sequence.  vals[j] = value ENTERING aggregate j (i.e. after aggregates 0..j-1 were
 // applied to the seed).  Optionally writes the composition of all n aggregates to `total`
 // (component-major with stride `batch`) and/or skips the value pass (reduce_only).
+// Dynamic shared memory: per warp 2 x ESZ x 32 doubles of scan scratch (see warp_scan_mem); the
+// buffer holding the warp's inclusive aggregates stays valid afterwards, so warp totals and
+// neighbours are read from there.
 template <class Op>
 __global__ void __launch_bounds__(kTopThreads)
 k_top(const double* __restrict__ agg, size_t astride, int n, int batch,
       const double* __restrict__ seed, double* __restrict__ vals, size_t vstride,
-      double* __restrict__ total, int reduce_only) {
-    using Elem = typename Op::Elem;
+      double* __restrict__ total, int reduce_only, PredJob pj) {
     using Val = typename Op::Val;
-    constexpr int ESZ = sizeof(Elem) / sizeof(double);
+    constexpr int ESZ = sizeof(typename Op::Elem) / sizeof(double);
     constexpr int VSZ = sizeof(Val) / sizeof(double);
     constexpr int MAXW = kTopThreads / 32;
-    __shared__ double s_w[MAXW][ESZ];
+    constexpr int WSZ = 2 * ESZ * 32;
+    extern __shared__ __align__(16) double s_scan[];   // [nw][2][ESZ][32]
     __shared__ double s_v[MAXW][VSZ];
+    __shared__ double s_tot[ESZ];
 
     const int b = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
     const int lane = t & 31, w = t >> 5, nw = nt >> 5;
     const int q = (n + nt - 1) / nt;
     const size_t base = (size_t)b * n;
     const int j0 = t * q, j1 = min(n, j0 + q);
+    double* ws = s_scan + (size_t)w * WSZ;
+    if (pj.pred != nullptr && w == nw - 1) pred_reduce(pj, b, lane);
 
-    Elem inc;
+    // thread-level fold of its q aggregates, accumulated in place in the scan scratch
     if (j0 < n) {
-        soa_load(inc, agg, astride, base + j0);
-        Elem e;
-        for (int j = j0 + 1; j < j1; ++j) {
-            soa_load(e, agg, astride, base + j);
-            Op::compose(inc, inc, e);
-        }
+#pragma unroll
+        for (int c = 0; c < ESZ; ++c) ws[c * 32 + lane] = agg[(size_t)c * astride + base + j0];
+        for (int j = j0 + 1; j < j1; ++j)
+            Op::compose_mm(ws + lane, 32, ws + lane, 32, agg + base + j, (int)astride);
     } else {
-        Op::identity(inc);
-    }
-    // warp-level inclusive scan (Kogge-Stone over shuffles)
-#pragma unroll 1
-    for (int delta = 1; delta < 32; delta <<= 1) {
-        Elem o = shfl_up_all(inc, delta);
-        if (lane >= delta) Op::compose(inc, o, inc);
-    }
-    if (lane == 31) {
+        typename Op::Elem id;
+        Op::identity(id);
 #pragma unroll
-        for (int c = 0; c < ESZ; ++c) s_w[w][c] = inc.r[c];
+        for (int c = 0; c < ESZ; ++c) ws[c * 32 + lane] = id.r[c];
     }
+    __syncwarp();
+    const double* inc = warp_scan_mem<Op>(ws, lane, false);   // this warp's inclusive aggregates
+    const int inc_off = (int)(inc - ws);                      // same buffer parity in every warp
     __syncthreads();
-    if (w == 0) {
-        Elem wi;
-        if (lane < nw) {
+    if (w == 0 && lane == 0) {
+        if (total != nullptr) {
+            // composition of all warp totals (time-sharded reduce phase)
 #pragma unroll
-            for (int c = 0; c < ESZ; ++c) wi.r[c] = s_w[lane][c];
-        } else {
-            Op::identity(wi);
-        }
-#pragma unroll 1
-        for (int delta = 1; delta < MAXW; delta <<= 1) {
-            Elem o = shfl_up_all(wi, delta);
-            if (lane >= delta) Op::compose(wi, o, wi);
-        }
-        if (total != nullptr && lane == nw - 1) soa_store(wi, total, (size_t)batch, (size_t)b);
-        if (!reduce_only && lane < nw) {
-            Val sd, o;
-            soa_load(sd, seed, (size_t)batch, (size_t)b);
-            Op::apply(o, wi, sd);
+            for (int c = 0; c < ESZ; ++c) s_tot[c] = s_scan[inc_off + c * 32 + 31];
+            for (int ww = 1; ww < nw; ++ww)
+                Op::compose_mm(s_tot, 1, s_tot, 1, s_scan + (size_t)ww * WSZ + inc_off + 31, 32);
 #pragma unroll
-            for (int c = 0; c < VSZ; ++c) s_v[lane][c] = o.r[c];
+            for (int c = 0; c < ESZ; ++c) total[(size_t)c * batch + b] = s_tot[c];
+        }
+        if (!reduce_only) {
+            // value entering every warp: a short serial chain of `apply` (about half a combine each)
+            Val v;
+            soa_load(v, seed, (size_t)batch, (size_t)b);
+            for (int ww = 1; ww < nw; ++ww) {
+                Op::apply_mm(v, s_scan + (size_t)(ww - 1) * WSZ + inc_off + 31, 32);
+#pragma unroll
+                for (int c = 0; c < VSZ; ++c) s_v[ww - 1][c] = v.r[c];
+            }
         }
     }
     if (reduce_only) return;
@@ -204,45 +288,155 @@ k_top(const double* __restrict__ agg, size_t astride, int n, int batch,
 #pragma unroll
         for (int c = 0; c < VSZ; ++c) v.r[c] = s_v[w - 1][c];
     }
-    {
-        Elem ex = shfl_up_all(inc, 1);
-        if (lane > 0) Op::apply(v, ex, v);
-    }
+    if (lane > 0) Op::apply_mm(v, inc + lane - 1, 32);   // exclusive prefix = previous lane's inclusive
     if (j0 < n) {
-        Elem e;
         for (int j = j0; j < j1; ++j) {
             soa_store(v, vals, vstride, base + j);
-            if (j + 1 < j1) {
-                soa_load(e, agg, astride, base + j);
-                Op::apply(v, e, v);
-            }
+            if (j + 1 < j1) Op::apply_mm(v, agg + base + j, (int)astride);
         }
     }
 }
 
-// Sequentially push a seed through `nprev` gathered segment aggregates (time-sharded mode):
-// seed_out = apply(carry[order[nprev-1]], ... apply(carry[order[0]], seed_in)).
+// Sequentially push a seed through gathered segment aggregates (time-sharded mode):
 // carries are rank-major AoS: carry[r * ESZ + c].  first = index of the first aggregate to
 // apply, step = +1/-1, count = how many.
 template <class Op>
 __global__ void k_chain_seed(const double* __restrict__ carries, int first, int step, int count,
                              const double* __restrict__ seed_in, double* __restrict__ seed_out) {
-    using Elem = typename Op::Elem;
     using Val = typename Op::Val;
-    constexpr int ESZ = sizeof(Elem) / sizeof(double);
+    constexpr int ESZ = sizeof(typename Op::Elem) / sizeof(double);
     constexpr int VSZ = sizeof(Val) / sizeof(double);
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Val v;
 #pragma unroll
     for (int c = 0; c < VSZ; ++c) v.r[c] = seed_in[c];
-    Elem e;
-    for (int i = 0, r = first; i < count; ++i, r += step) {
-#pragma unroll
-        for (int c = 0; c < ESZ; ++c) e.r[c] = carries[(size_t)r * ESZ + c];
-        Op::apply(v, e, v);
-    }
+    for (int i = 0, r = first; i < count; ++i, r += step) Op::apply_mm(v, carries + (size_t)r * ESZ, 1);
 #pragma unroll
     for (int c = 0; c < VSZ; ++c) seed_out[c] = v.r[c];
+}
+
+// ------------------------------------------------------------------ leaf geometry
+// mode A (per_lane = 0): sequence b is cut into n1 chunks of T0 steps; warp `wi` of the sequence
+//   owns chunks wi*32 .. wi*32+31 (warps never straddle sequences), nW = ceil(n1/32).
+// mode B (per_lane = 1): one whole sequence per lane (T0 = N), no scan at all.
+struct Geom {
+    int N, T0, n1, nW, batch, per_lane;
+    int pw_bytes;   // per-warp shared-memory pitch of the current launch (set by the launcher)
+};
+struct Lane {
+    int b, wi, len;        // sequence, warp-in-sequence, number of valid steps of this lane's chunk
+    long long t0;          // global step index (b*N + k0) of the chunk's first step
+    long long slot;        // per-thread slot in the SoA planes
+    int k0;
+};
+__host__ __device__ inline long long total_warps(const Geom& g) {
+    return g.per_lane ? ((long long)g.batch + 31) / 32 : (long long)g.batch * g.nW;
+}
+IPOC_DEV Lane lane_info(const Geom& g, long long wg, int lane) {
+    Lane L;
+    if (g.per_lane) {
+        const long long b = wg * 32 + lane;
+        L.b = (int)(b < g.batch ? b : g.batch - 1);
+        L.wi = 0;
+        L.k0 = 0;
+        L.len = b < g.batch ? g.N : 0;
+    } else {
+        L.b = (int)(wg / g.nW);
+        L.wi = (int)(wg % g.nW);
+        const long long c = (long long)L.wi * 32 + lane;
+        const long long k0 = c * g.T0;
+        L.k0 = (int)(k0 < g.N ? k0 : g.N);
+        const long long rem = (long long)g.N - k0;
+        L.len = (int)(rem <= 0 ? 0 : (rem < g.T0 ? rem : g.T0));
+    }
+    L.t0 = (long long)L.b * g.N + L.k0;
+    L.slot = wg * 32 + lane;
+    return L;
+}
+
+// ------------------------------------------------------------------ staged (cp.async) row loads
+__host__ __device__ constexpr int row_gran(int cnt) { return (cnt % 2 == 0) ? 16 : 8; }
+__host__ __device__ constexpr int row_cpr(int cnt) { return cnt * 8 / row_gran(cnt); }
+__host__ __device__ constexpr int row_pitch(int cnt) { return (row_cpr(cnt) % 2 == 1) ? cnt * 8 : cnt * 8 + row_gran(cnt); }
+__host__ __device__ constexpr int arr_bytes(int cnt) { return (32 * row_pitch(cnt) + 15) / 16 * 16; }
+constexpr int kTabBytes = 32 * 8 + 32 * 4;   // per-warp table: row step offsets + row lengths
+
+IPOC_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NKEEP>
+IPOC_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
+
+// Copy step (tab_t[r] + j) of every lane-row r of one input array into the stage: the warp
+// cooperates, `CPR` granules per row, consecutive lanes on consecutive granules of the same row.
+template <int CNT>
+IPOC_DEV void issue_rows(char* dst_arr, const double* __restrict__ g, const long long* tab_t, const int* tab_len,
+                         int j, int lane) {
+    constexpr int G = row_gran(CNT), CPR = row_cpr(CNT), PITCH = row_pitch(CNT);
+#pragma unroll
+    for (int i = 0; i < CPR; ++i) {
+        const int idx = lane + 32 * i;
+        const int r = idx / CPR, part = idx % CPR;
+        if (j < tab_len[r]) {
+            const char* src = reinterpret_cast<const char*>(g) + ((tab_t[r] + j) * CNT) * 8 + part * G;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(dst_arr + r * PITCH + part * G);
+            if constexpr (G == 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
+        }
+    }
+}
+template <int CNT>
+IPOC_DEV void read_row(double* dst, const char* src_arr, int lane) {
+    const char* p = src_arr + lane * row_pitch(CNT);
+    if constexpr (CNT % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < CNT / 2; ++i) {
+            const double2 v = *reinterpret_cast<const double2*>(p + 16 * i);
+            dst[2 * i] = v.x;
+            dst[2 * i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; ++i) dst[i] = *reinterpret_cast<const double*>(p + 8 * i);
+    }
+}
+
+// Per-warp shared memory: [table | stage 0 | stage 1]
+struct WarpSmem {
+    long long* tab_t;
+    int* tab_len;
+    char* stage0;
+};
+IPOC_DEV WarpSmem warp_smem(char* smem, int per_warp_bytes, int warp_in_block, const Lane& L, int lane) {
+    char* base = smem + (size_t)warp_in_block * per_warp_bytes;
+    WarpSmem w;
+    w.tab_t = reinterpret_cast<long long*>(base);
+    w.tab_len = reinterpret_cast<int*>(base + 32 * 8);
+    w.stage0 = base + kTabBytes;
+    w.tab_t[lane] = L.t0;
+    w.tab_len[lane] = L.len;
+    __syncwarp();
+    return w;
+}
+
+// Double-buffered walk over the T steps of a chunk (uniform trip count; lanes with shorter chunks
+// idle).  body(j, stage) runs for the lane's valid steps with its row available in `stage`.
+template <class Ld, class F>
+IPOC_DEV void staged_walk(const Ld& ld, const WarpSmem& w, int T, int len, int lane, bool reverse, F&& body) {
+    int cur = 0;
+    ld.issue(w.stage0, w.tab_t, w.tab_len, reverse ? T - 1 : 0, lane);
+    cp_async_commit();
+    for (int it = 0; it < T; ++it) {
+        const int j = reverse ? T - 1 - it : it;
+        if (it + 1 < T)
+            ld.issue(w.stage0 + (cur ^ 1) * Ld::STAGE_BYTES, w.tab_t, w.tab_len, reverse ? j - 1 : j + 1, lane);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        if (j < len) body(j, w.stage0 + cur * Ld::STAGE_BYTES);
+        __syncwarp();
+        cur ^= 1;
+    }
 }
 
 // ------------------------------------------------------------------ K2 loaders
@@ -253,16 +447,25 @@ __global__ void k_chain_seed(const double* __restrict__ carries, int first, int 
 template <int NX, int NU>
 struct NewtonLoader {
     const double *fx, *fu, *ru, *Q, *R, *M, *reg;
-    int N;
-    IPOC_DEV void load(StepLQ<NX, NU>& s, int b, int k) const {
-        const size_t t = (size_t)b * N + k;
+    static constexpr int O_FX = 0, O_FU = O_FX + arr_bytes(NX * NX), O_Q = O_FU + arr_bytes(NX * NU),
+                         O_R = O_Q + arr_bytes(NX * NX), O_M = O_R + arr_bytes(NU * NU),
+                         O_RU = O_M + arr_bytes(NX * NU), STAGE_BYTES = O_RU + arr_bytes(NU);
+    IPOC_DEV void issue(char* st, const long long* tt, const int* tl, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_FX, fx, tt, tl, j, lane);
+        issue_rows<NX * NU>(st + O_FU, fu, tt, tl, j, lane);
+        issue_rows<NX * NX>(st + O_Q, Q, tt, tl, j, lane);
+        issue_rows<NU * NU>(st + O_R, R, tt, tl, j, lane);
+        issue_rows<NX * NU>(st + O_M, M, tt, tl, j, lane);
+        issue_rows<NU>(st + O_RU, ru, tt, tl, j, lane);
+    }
+    IPOC_DEV void read(StepLQ<NX, NU>& s, const char* st, int lane, int b) const {
         double Qf[NX][NX], Rf[NU][NU], ruv[NU];
-        ld_vec<NX * NX>(&s.A[0][0], fx + t * NX * NX);
-        ld_vec<NX * NU>(&s.B[0][0], fu + t * NX * NU);
-        ld_vec<NX * NX>(&Qf[0][0], Q + t * NX * NX);
-        ld_vec<NU * NU>(&Rf[0][0], R + t * NU * NU);
-        ld_vec<NX * NU>(&s.M[0][0], M + t * NX * NU);
-        ld_vec<NU>(ruv, ru + t * NU);
+        read_row<NX * NX>(&s.A[0][0], st + O_FX, lane);
+        read_row<NX * NU>(&s.B[0][0], st + O_FU, lane);
+        read_row<NX * NX>(&Qf[0][0], st + O_Q, lane);
+        read_row<NU * NU>(&Rf[0][0], st + O_R, lane);
+        read_row<NX * NU>(&s.M[0][0], st + O_M, lane);
+        read_row<NU>(ruv, st + O_RU, lane);
         const double rg = __ldg(reg + b);
 #pragma unroll
         for (int a = 0; a < NU; ++a)
@@ -323,23 +526,34 @@ struct NewtonLoader {
     }
 };
 
-// LQT mode: effective terms given directly.
+// LQT mode: effective terms given directly (c may be NULL = 0).
 template <int NX, int NU>
 struct LqtLoader {
     const double *A, *B, *c, *X, *U, *M, *q, *p;
-    int N;
-    IPOC_DEV void load(StepLQ<NX, NU>& s, int b, int k) const {
-        const size_t t = (size_t)b * N + k;
+    static constexpr int O_A = 0, O_B = O_A + arr_bytes(NX * NX), O_C = O_B + arr_bytes(NX * NU),
+                         O_X = O_C + arr_bytes(NX), O_U = O_X + arr_bytes(NX * NX), O_M = O_U + arr_bytes(NU * NU),
+                         O_Q = O_M + arr_bytes(NX * NU), O_P = O_Q + arr_bytes(NX), STAGE_BYTES = O_P + arr_bytes(NU);
+    IPOC_DEV void issue(char* st, const long long* tt, const int* tl, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_A, A, tt, tl, j, lane);
+        issue_rows<NX * NU>(st + O_B, B, tt, tl, j, lane);
+        if (c != nullptr) issue_rows<NX>(st + O_C, c, tt, tl, j, lane);
+        issue_rows<NX * NX>(st + O_X, X, tt, tl, j, lane);
+        issue_rows<NU * NU>(st + O_U, U, tt, tl, j, lane);
+        issue_rows<NX * NU>(st + O_M, M, tt, tl, j, lane);
+        issue_rows<NX>(st + O_Q, q, tt, tl, j, lane);
+        issue_rows<NU>(st + O_P, p, tt, tl, j, lane);
+    }
+    IPOC_DEV void read(StepLQ<NX, NU>& s, const char* st, int lane, int) const {
         double Xf[NX][NX], Uf[NU][NU];
-        ld_vec<NX * NX>(&s.A[0][0], A + t * NX * NX);
-        ld_vec<NX * NU>(&s.B[0][0], B + t * NX * NU);
-        ld_vec<NX * NX>(&Xf[0][0], X + t * NX * NX);
-        ld_vec<NU * NU>(&Uf[0][0], U + t * NU * NU);
-        ld_vec<NX * NU>(&s.M[0][0], M + t * NX * NU);
-        ld_vec<NX>(s.q, q + t * NX);
-        ld_vec<NU>(s.p, p + t * NU);
+        read_row<NX * NX>(&s.A[0][0], st + O_A, lane);
+        read_row<NX * NU>(&s.B[0][0], st + O_B, lane);
+        read_row<NX * NX>(&Xf[0][0], st + O_X, lane);
+        read_row<NU * NU>(&Uf[0][0], st + O_U, lane);
+        read_row<NX * NU>(&s.M[0][0], st + O_M, lane);
+        read_row<NX>(s.q, st + O_Q, lane);
+        read_row<NU>(s.p, st + O_P, lane);
         if (c != nullptr) {
-            ld_vec<NX>(s.c, c + t * NX);
+            read_row<NX>(s.c, st + O_C, lane);
         } else {
 #pragma unroll
             for (int i = 0; i < NX; ++i) s.c[i] = 0.0;
@@ -355,13 +569,55 @@ struct LqtLoader {
     }
 };
 
+// closed-loop step data of K3: A, B, c (may be NULL), Kx, d
+template <int NX, int NU>
+struct FwdLoader {
+    const double *A, *B, *c, *Kx, *d;
+    static constexpr int O_A = 0, O_B = O_A + arr_bytes(NX * NX), O_C = O_B + arr_bytes(NX * NU),
+                         O_K = O_C + arr_bytes(NX), O_D = O_K + arr_bytes(NU * NX), STAGE_BYTES = O_D + arr_bytes(NU);
+    IPOC_DEV void issue(char* st, const long long* tt, const int* tl, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_A, A, tt, tl, j, lane);
+        issue_rows<NX * NU>(st + O_B, B, tt, tl, j, lane);
+        if (c != nullptr) issue_rows<NX>(st + O_C, c, tt, tl, j, lane);
+        issue_rows<NU * NX>(st + O_K, Kx, tt, tl, j, lane);
+        issue_rows<NU>(st + O_D, d, tt, tl, j, lane);
+    }
+};
+
+// one affine array pair: F (NX x NX), c (NX)
+template <int NX>
+struct AffLoader {
+    const double *F, *c;
+    static constexpr int O_F = 0, O_C = O_F + arr_bytes(NX * NX), STAGE_BYTES = O_C + arr_bytes(NX);
+    IPOC_DEV void issue(char* st, const long long* tt, const int* tl, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_F, F, tt, tl, j, lane);
+        issue_rows<NX>(st + O_C, c, tt, tl, j, lane);
+    }
+    IPOC_DEV void read(AffElem<NX>& e, const char* st, int lane, int transpose) const {
+        double Fm[NX][NX], cv[NX];
+        read_row<NX * NX>(&Fm[0][0], st + O_F, lane);
+        read_row<NX>(cv, st + O_C, lane);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) e.F(i, j) = transpose ? Fm[j][i] : Fm[i][j];
+            e.c(i) = cv[i];
+        }
+    }
+};
+
 // Terminal value function per problem -> SoA seed (stride = batch).
 // ST: full (nx,nx) matrix at ST + b*st_stride (symmetrised), vT at vT + b*nx (NULL = 0).
 template <int NX>
 __global__ void k_ric_seed(const double* __restrict__ ST, size_t st_stride,
-                           const double* __restrict__ vT, int batch, double* __restrict__ seed) {
+                           const double* __restrict__ vT, int batch, double* __restrict__ seed,
+                           double* __restrict__ zero_aff_seed) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
+    if (zero_aff_seed != nullptr) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) zero_aff_seed[(size_t)i * batch + b] = 0.0;
+    }
     RicVal<NX> v;
     const double* s = ST + (size_t)b * st_stride;
 #pragma unroll
@@ -374,52 +630,72 @@ __global__ void k_ric_seed(const double* __restrict__ ST, size_t st_stride,
 }
 
 // ------------------------------------------------------------------ K2 leaf kernels
-// Up-sweep: thread (b, c) folds steps [c*T0, min(N,(c+1)T0)) backwards in time into one
-// element; stored at scan index n1-1-c (the scan runs from the end of the horizon).
+// Up-sweep: each lane folds its chunk backwards in time into one element (starting from the
+// identity, so the first prepend reproduces the single-step element exactly), then the warp scans.
+//   incl  [slot]               : in-warp inclusive aggregate of every lane          (SoA, stride istride)
+//   agg1  [b*nW + (nW-1-wi)]   : warp totals in scan order (end of horizon first)   (SoA, stride a1stride)
 template <int NX, int NU, class Loader>
 __global__ void __launch_bounds__(kLeafThreads)
-k_ric_leaf_up(Loader ld, int N, int T0, int n1, int batch, double* __restrict__ agg, size_t astride) {
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)batch * n1) return;
-    const int b = (int)(g / n1), c = (int)(g % n1);
-    const int k0 = c * T0, k1 = min(N, k0 + T0);
-    StepLQ<NX, NU> s;
-    StepElem<NX, NU> e;
+k_ric_leaf_up(Loader ld, Geom g, double* __restrict__ incl, size_t istride, double* __restrict__ agg1,
+              size_t a1stride) {
+    extern __shared__ __align__(16) char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (wg >= total_warps(g)) return;
+    const Lane L = lane_info(g, wg, lane);
+    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
     RicElem<NX> a;
-    ld.load(s, b, k1 - 1);
-    make_step_elem(e, s);
-    step_to_elem(a, e);
-    for (int k = k1 - 2; k >= k0; --k) {
-        ld.load(s, b, k);
+    RicOp<NX>::identity(a);
+    staged_walk(ld, w, g.T0, L.len, lane, true, [&](int, const char* st) {
+        StepLQ<NX, NU> s;
+        StepElem<NX, NU> e;
+        ld.read(s, st, lane, L.b);
         make_step_elem(e, s);
         ric_prepend_step(a, e);
-    }
-    soa_store(a, agg, astride, (size_t)b * n1 + (n1 - 1 - c));
+    });
+    warp_scan<RicOp<NX>>(a, reinterpret_cast<double*>(w.stage0), lane, true);
+    soa_store(a, incl, istride, (size_t)L.slot);
+    if (lane == 0) soa_store(a, agg1, a1stride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
 }
 
-// Down-sweep: seeded Riccati recursion over the chunk, gains out, pred/feasibility partials,
-// and the chunk's forward (closed-loop) affine aggregate for K3.
+// Down-sweep: seeded Riccati recursion over the chunk, gains out, pred/feasibility partials, and
+// the in-warp scan of the chunk's forward (closed-loop) affine aggregates for K3.
+//   wvals [b*nW + (nW-1-wi)] : value function entering each warp (from the levels / the seed)
+//   mode B (per_lane): wvals = seed (stride batch), no neighbours, final pred/feasible written here.
 template <int NX, int NU, class Loader>
 __global__ void __launch_bounds__(kLeafThreads)
-k_ric_leaf_down(Loader ld, int N, int T0, int n1, int batch,
-                const double* __restrict__ vals, size_t vstride,
+k_ric_leaf_down(Loader ld, Geom g, const double* __restrict__ incl, size_t istride,
+                const double* __restrict__ wvals, size_t wvstride,
                 double* __restrict__ Kx, double* __restrict__ d,
                 double* __restrict__ S_out, double* __restrict__ v_out,
                 double* __restrict__ pred_part, int* __restrict__ feas_part,
-                double* __restrict__ fagg, size_t fstride) {
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)batch * n1) return;
-    const int b = (int)(g / n1), c = (int)(g % n1);
-    const int k0 = c * T0, k1 = min(N, k0 + T0);
+                double* __restrict__ pred, int32_t* __restrict__ feasible,
+                double* __restrict__ fincl, size_t fistride, double* __restrict__ fagg1, size_t fa1stride) {
+    extern __shared__ __align__(16) char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (wg >= total_warps(g)) return;
+    const Lane L = lane_info(g, wg, lane);
+    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
+    const int N = g.N;
     RicVal<NX> val;
-    soa_load(val, vals, vstride, (size_t)b * n1 + (n1 - 1 - c));
+    if (g.per_lane) {
+        soa_load(val, wvals, wvstride, (size_t)L.b);
+    } else {
+        soa_load(val, wvals, wvstride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
+        if (lane < 31) {   // exclusive prefix (scan order) = inclusive aggregate of the next lane
+            RicElem<NX> ex;
+            soa_load(ex, incl, istride, (size_t)L.slot + 1);
+            RicOp<NX>::apply(val, ex, val);
+        }
+    }
     AffElem<NX> fa;
     AffOp<NX>::identity(fa);
     double predsum = 0.0;
     bool feas = true;
     auto write_Sv = [&](int k) {
-        double* Sp = S_out + ((size_t)b * (N + 1) + k) * NX * NX;
-        double* vp = v_out + ((size_t)b * (N + 1) + k) * NX;
+        double* Sp = S_out + ((size_t)L.b * (N + 1) + k) * NX * NX;
+        double* vp = v_out + ((size_t)L.b * (N + 1) + k) * NX;
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
 #pragma unroll
@@ -427,228 +703,238 @@ k_ric_leaf_down(Loader ld, int N, int T0, int n1, int batch,
             vp[i] = val.v(i);
         }
     };
-    if (S_out != nullptr && k1 == N) write_Sv(N);
-    StepLQ<NX, NU> s;
-    StepGain<NX, NU> gn;
-    for (int k = k1 - 1; k >= k0; --k) {
-        ld.load(s, b, k);
+    if (S_out != nullptr && L.len > 0 && L.k0 + L.len == N) write_Sv(N);
+    staged_walk(ld, w, g.T0, L.len, lane, true, [&](int j, const char* st) {
+        StepLQ<NX, NU> s;
+        StepGain<NX, NU> gn;
+        ld.read(s, st, lane, L.b);
         ric_step_back(val, gn, s);
-        const size_t t = (size_t)b * N + k;
+        const size_t t = (size_t)(L.t0 + j);
         st_vec<NU * NX>(Kx + t * NU * NX, &gn.Kx[0][0]);
         st_vec<NU>(d + t * NU, gn.d);
         predsum += gn.dGd;
         feas = feas && gn.pd;
-        if (S_out != nullptr) write_Sv(k);
-        if (fagg != nullptr) {
+        if (S_out != nullptr) write_Sv(L.k0 + j);
+        if (fincl != nullptr || fagg1 != nullptr) {
             // fa <- fa o step_k :  P <- P Fcl,  q <- P ccl + q
-            AffElem<NX> st;
+            AffElem<NX> se;
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
 #pragma unroll
-                for (int j = 0; j < NX; ++j) st.F(i, j) = gn.Fcl[i][j];
-                st.c(i) = gn.ccl[i];
+                for (int jj = 0; jj < NX; ++jj) se.F(i, jj) = gn.Fcl[i][jj];
+                se.c(i) = gn.ccl[i];
             }
-            AffOp<NX>::compose(fa, st, fa);
+            AffOp<NX>::compose(fa, se, fa);
         }
-    }
-    pred_part[g] = predsum;
-    feas_part[g] = feas ? 1 : 0;
-    if (fagg != nullptr) soa_store(fa, fagg, fstride, (size_t)g);
-}
-
-// pred = -1/2 sum_k d'Gd, feasible = AND_k (G_k > 0); fixed-order tree per problem.
-static __global__ void __launch_bounds__(256)
-k_finalize_pred(const double* __restrict__ pred_part, const int* __restrict__ feas_part, int n1,
-                double* __restrict__ pred, int32_t* __restrict__ feasible, int accumulate) {
-    __shared__ double sp[256];
-    __shared__ int sf[256];
-    const int b = blockIdx.x, t = threadIdx.x;
-    double acc = 0.0;
-    int f = 1;
-    for (int j = t; j < n1; j += 256) {
-        acc += pred_part[(size_t)b * n1 + j];
-        f &= feas_part[(size_t)b * n1 + j];
-    }
-    sp[t] = acc;
-    sf[t] = f;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (t < o) {
-            sp[t] += sp[t + o];
-            sf[t] &= sf[t + o];
+    });
+    if (g.per_lane) {
+        if (L.len > 0) {
+            pred[L.b] = -0.5 * predsum;
+            feasible[L.b] = feas ? 1 : 0;
         }
-        __syncthreads();
+        return;
     }
-    if (t == 0) {
-        pred[b] = -0.5 * sp[0];
-        feasible[b] = sf[0];
+    // deterministic in-warp reduction of the pred / feasibility partials (xor butterfly)
+    int fi = feas ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        predsum += __shfl_xor_sync(0xffffffffu, predsum, o);
+        fi &= __shfl_xor_sync(0xffffffffu, fi, o);
+    }
+    if (lane == 0) {
+        pred_part[wg] = predsum;
+        feas_part[wg] = fi;
+    }
+    if (fincl != nullptr) {
+        warp_scan<AffOp<NX>>(fa, reinterpret_cast<double*>(w.stage0), lane, false);
+        soa_store(fa, fincl, fistride, (size_t)L.slot);
+        if (lane == 31) soa_store(fa, fagg1, fa1stride, (size_t)L.b * g.nW + L.wi);
     }
 }
 
-// ------------------------------------------------------------------ K3 leaf down
+// pred / feasible finalisation as a stand-alone launch (only when no K3 top scan follows that could
+// carry it as a side job).
+static __global__ void __launch_bounds__(32) k_finalize_pred(PredJob pj) { pred_reduce(pj, blockIdx.x, threadIdx.x); }
+
+// ------------------------------------------------------------------ K3 leaves
+template <int NX, int NU>
+IPOC_DEV void read_fwd_step(const FwdLoader<NX, NU>& ld, const char* st, int lane, double (&Am)[NX][NX],
+                            double (&Bm)[NX][NU], double (&Km)[NU][NX], double (&dv)[NU], double (&cv)[NX]) {
+    using FL = FwdLoader<NX, NU>;
+    read_row<NX * NX>(&Am[0][0], st + FL::O_A, lane);
+    read_row<NX * NU>(&Bm[0][0], st + FL::O_B, lane);
+    read_row<NU * NX>(&Km[0][0], st + FL::O_K, lane);
+    read_row<NU>(dv, st + FL::O_D, lane);
+    if (ld.c != nullptr) {
+        read_row<NX>(cv, st + FL::O_C, lane);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) cv[i] = 0.0;
+    }
+}
+
+//   xw [b*nW + wi] : state entering each warp;  fincl[slot] : in-warp inclusive forward aggregates
 template <int NX, int NU>
 __global__ void __launch_bounds__(kLeafThreads)
-k_fwd_leaf_down(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ cc,
-                const double* __restrict__ Kx, const double* __restrict__ d,
-                int N, int T0, int n1, int batch,
-                const double* __restrict__ xvals, size_t xstride,
+k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, size_t fistride,
+                const double* __restrict__ xw, size_t xwstride,
                 double* __restrict__ x_out, double* __restrict__ u_out) {
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)batch * n1) return;
-    const int b = (int)(g / n1), c = (int)(g % n1);
-    const int k0 = c * T0, k1 = min(N, k0 + T0);
+    extern __shared__ __align__(16) char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (wg >= total_warps(g)) return;
+    const Lane L = lane_info(g, wg, lane);
+    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
+    const int N = g.N;
     AffVal<NX> xv;
-    soa_load(xv, xvals, xstride, (size_t)g);
+    if (g.per_lane) {
+        soa_load(xv, xw, xwstride, (size_t)L.b);
+    } else {
+        soa_load(xv, xw, xwstride, (size_t)L.b * g.nW + L.wi);
+        if (lane > 0) {
+            AffElem<NX> ex;
+            soa_load(ex, fincl, fistride, (size_t)L.slot - 1);
+            AffOp<NX>::apply(xv, ex, xv);
+        }
+    }
     double x[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = xv.r[i];
-    for (int k = k0; k < k1; ++k) {
-        const size_t t = (size_t)b * N + k;
+    staged_walk(ld, w, g.T0, L.len, lane, false, [&](int j, const char* st) {
         double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU], cv[NX], u[NU], xn[NX];
-        ld_vec<NX * NX>(&Am[0][0], A + t * NX * NX);
-        ld_vec<NX * NU>(&Bm[0][0], B + t * NX * NU);
-        ld_vec<NU * NX>(&Km[0][0], Kx + t * NU * NX);
-        ld_vec<NU>(dv, d + t * NU);
-        if (cc != nullptr) {
-            ld_vec<NX>(cv, cc + t * NX);
-        } else {
-#pragma unroll
-            for (int i = 0; i < NX; ++i) cv[i] = 0.0;
-        }
+        read_fwd_step<NX, NU>(ld, st, lane, Am, Bm, Km, dv, cv);
 #pragma unroll
         for (int a = 0; a < NU; ++a) {
             double v = dv[a];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) v -= Km[a][j] * x[j];
+            for (int jj = 0; jj < NX; ++jj) v -= Km[a][jj] * x[jj];
             u[a] = v;
         }
-        st_vec<NX>(x_out + ((size_t)b * (N + 1) + k) * NX, x);
+        const size_t t = (size_t)(L.t0 + j);
+        st_vec<NX>(x_out + ((size_t)L.b * (N + 1) + L.k0 + j) * NX, x);
         st_vec<NU>(u_out + t * NU, u);
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
             double v = cv[i];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) v += Am[i][j] * x[j];
+            for (int jj = 0; jj < NX; ++jj) v += Am[i][jj] * x[jj];
 #pragma unroll
             for (int a = 0; a < NU; ++a) v += Bm[i][a] * u[a];
             xn[i] = v;
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = xn[i];
-    }
-    if (k1 == N) st_vec<NX>(x_out + ((size_t)b * (N + 1) + N) * NX, x);
+    });
+    if (L.len > 0 && L.k0 + L.len == N) st_vec<NX>(x_out + ((size_t)L.b * (N + 1) + N) * NX, x);
 }
 
 // K3 leaf up (only for the stand-alone par_fwd_pass API; the Newton step gets these aggregates
 // from K2's down-sweep).
 template <int NX, int NU>
 __global__ void __launch_bounds__(kLeafThreads)
-k_fwd_leaf_up(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ cc,
-              const double* __restrict__ Kx, const double* __restrict__ d,
-              int N, int T0, int n1, int batch, double* __restrict__ fagg, size_t fstride) {
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)batch * n1) return;
-    const int b = (int)(g / n1), c = (int)(g % n1);
-    const int k0 = c * T0, k1 = min(N, k0 + T0);
+k_fwd_leaf_up(FwdLoader<NX, NU> ld, Geom g, double* __restrict__ fincl, size_t fistride,
+              double* __restrict__ fagg1, size_t fa1stride) {
+    extern __shared__ __align__(16) char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (wg >= total_warps(g)) return;
+    const Lane L = lane_info(g, wg, lane);
+    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
     AffElem<NX> fa;
     AffOp<NX>::identity(fa);
-    for (int k = k0; k < k1; ++k) {
-        const size_t t = (size_t)b * N + k;
-        double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU];
-        AffElem<NX> st;
-        ld_vec<NX * NX>(&Am[0][0], A + t * NX * NX);
-        ld_vec<NX * NU>(&Bm[0][0], B + t * NX * NU);
-        ld_vec<NU * NX>(&Km[0][0], Kx + t * NU * NX);
-        ld_vec<NU>(dv, d + t * NU);
+    staged_walk(ld, w, g.T0, L.len, lane, false, [&](int, const char* st) {
+        double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU], cv[NX];
+        read_fwd_step<NX, NU>(ld, st, lane, Am, Bm, Km, dv, cv);
+        AffElem<NX> se;
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
 #pragma unroll
-            for (int j = 0; j < NX; ++j) {
-                double v = Am[i][j];
+            for (int jj = 0; jj < NX; ++jj) {
+                double v = Am[i][jj];
 #pragma unroll
-                for (int a = 0; a < NU; ++a) v -= Bm[i][a] * Km[a][j];
-                st.F(i, j) = v;
+                for (int a = 0; a < NU; ++a) v -= Bm[i][a] * Km[a][jj];
+                se.F(i, jj) = v;
             }
-            double v = (cc != nullptr) ? __ldg(cc + t * NX + i) : 0.0;
+            double v = cv[i];
 #pragma unroll
             for (int a = 0; a < NU; ++a) v += Bm[i][a] * dv[a];
-            st.c(i) = v;
+            se.c(i) = v;
         }
-        AffOp<NX>::compose(fa, fa, st);
-    }
-    soa_store(fa, fagg, fstride, (size_t)g);
+        AffOp<NX>::compose(fa, fa, se);
+    });
+    warp_scan<AffOp<NX>>(fa, reinterpret_cast<double*>(w.stage0), lane, false);
+    soa_store(fa, fincl, fistride, (size_t)L.slot);
+    if (lane == 31) soa_store(fa, fagg1, fa1stride, (size_t)L.b * g.nW + L.wi);
 }
 
 // ------------------------------------------------------------------ K1 (generic affine scan) leaves
 template <int NX>
-IPOC_DEV void load_affine_step(AffElem<NX>& st, const double* __restrict__ F, const double* __restrict__ c,
-                               size_t t, int transpose) {
-    double Fm[NX][NX], cv[NX];
-    ld_vec<NX * NX>(&Fm[0][0], F + t * NX * NX);
-    ld_vec<NX>(cv, c + t * NX);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-#pragma unroll
-        for (int j = 0; j < NX; ++j) st.F(i, j) = transpose ? Fm[j][i] : Fm[i][j];
-        st.c(i) = cv[i];
-    }
-}
-
-template <int NX>
 __global__ void __launch_bounds__(kLeafThreads)
-k_aff_leaf_up(const double* __restrict__ F, const double* __restrict__ c, int reverse, int transpose,
-              int N, int T0, int n1, int batch, double* __restrict__ agg, size_t astride) {
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)batch * n1) return;
-    const int b = (int)(g / n1), ch = (int)(g % n1);
-    const int k0 = ch * T0, k1 = min(N, k0 + T0);
-    AffElem<NX> a, st;
+k_aff_leaf_up(AffLoader<NX> ld, int reverse, int transpose, Geom g, double* __restrict__ incl, size_t istride,
+              double* __restrict__ agg1, size_t a1stride) {
+    extern __shared__ __align__(16) char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (wg >= total_warps(g)) return;
+    const Lane L = lane_info(g, wg, lane);
+    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
+    AffElem<NX> a;
+    AffOp<NX>::identity(a);
+    staged_walk(ld, w, g.T0, L.len, lane, reverse != 0, [&](int, const char* st) {
+        AffElem<NX> se;
+        ld.read(se, st, lane, transpose);
+        AffOp<NX>::compose(a, a, se);
+    });
+    warp_scan<AffOp<NX>>(a, reinterpret_cast<double*>(w.stage0), lane, reverse != 0);
+    soa_store(a, incl, istride, (size_t)L.slot);
     if (reverse) {
-        load_affine_step<NX>(a, F, c, (size_t)b * N + (k1 - 1), transpose);
-        for (int k = k1 - 2; k >= k0; --k) {
-            load_affine_step<NX>(st, F, c, (size_t)b * N + k, transpose);
-            AffOp<NX>::compose(a, a, st);
-        }
-        soa_store(a, agg, astride, (size_t)b * n1 + (n1 - 1 - ch));
+        if (lane == 0) soa_store(a, agg1, a1stride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
     } else {
-        load_affine_step<NX>(a, F, c, (size_t)b * N + k0, transpose);
-        for (int k = k0 + 1; k < k1; ++k) {
-            load_affine_step<NX>(st, F, c, (size_t)b * N + k, transpose);
-            AffOp<NX>::compose(a, a, st);
-        }
-        soa_store(a, agg, astride, (size_t)g);
+        if (lane == 31) soa_store(a, agg1, a1stride, (size_t)L.b * g.nW + L.wi);
     }
 }
 
 template <int NX>
 __global__ void __launch_bounds__(kLeafThreads)
-k_aff_leaf_down(const double* __restrict__ F, const double* __restrict__ c, int reverse, int transpose,
-                int N, int T0, int n1, int batch,
-                const double* __restrict__ vals, size_t vstride, double* __restrict__ out) {
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)batch * n1) return;
-    const int b = (int)(g / n1), ch = (int)(g % n1);
-    const int k0 = ch * T0, k1 = min(N, k0 + T0);
+k_aff_leaf_down(AffLoader<NX> ld, int reverse, int transpose, Geom g, const double* __restrict__ incl,
+                size_t istride, const double* __restrict__ wvals, size_t wvstride, double* __restrict__ out) {
+    extern __shared__ __align__(16) char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (wg >= total_warps(g)) return;
+    const Lane L = lane_info(g, wg, lane);
+    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
+    const int N = g.N;
     AffVal<NX> x;
-    AffElem<NX> st;
-    double* ob = out + (size_t)b * (N + 1) * NX;
-    if (reverse) {
-        soa_load(x, vals, vstride, (size_t)b * n1 + (n1 - 1 - ch));
-        if (k1 == N) st_vec<NX>(ob + (size_t)N * NX, x.r);
-        for (int k = k1 - 1; k >= k0; --k) {
-            load_affine_step<NX>(st, F, c, (size_t)b * N + k, transpose);
-            AffOp<NX>::apply(x, st, x);
-            st_vec<NX>(ob + (size_t)k * NX, x.r);
+    if (g.per_lane) {
+        soa_load(x, wvals, wvstride, (size_t)L.b);
+    } else if (reverse) {
+        soa_load(x, wvals, wvstride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
+        if (lane < 31) {
+            AffElem<NX> ex;
+            soa_load(ex, incl, istride, (size_t)L.slot + 1);
+            AffOp<NX>::apply(x, ex, x);
         }
     } else {
-        soa_load(x, vals, vstride, (size_t)g);
-        if (k0 == 0) st_vec<NX>(ob, x.r);
-        for (int k = k0; k < k1; ++k) {
-            load_affine_step<NX>(st, F, c, (size_t)b * N + k, transpose);
-            AffOp<NX>::apply(x, st, x);
-            st_vec<NX>(ob + (size_t)(k + 1) * NX, x.r);
+        soa_load(x, wvals, wvstride, (size_t)L.b * g.nW + L.wi);
+        if (lane > 0) {
+            AffElem<NX> ex;
+            soa_load(ex, incl, istride, (size_t)L.slot - 1);
+            AffOp<NX>::apply(x, ex, x);
         }
     }
+    double* ob = out + (size_t)L.b * (N + 1) * NX;
+    if (reverse) {
+        if (L.len > 0 && L.k0 + L.len == N) st_vec<NX>(ob + (size_t)N * NX, x.r);
+    } else {
+        if (L.len > 0 && L.k0 == 0) st_vec<NX>(ob, x.r);
+    }
+    staged_walk(ld, w, g.T0, L.len, lane, reverse != 0, [&](int j, const char* st) {
+        AffElem<NX> se;
+        ld.read(se, st, lane, transpose);
+        AffOp<NX>::apply(x, se, x);
+        st_vec<NX>(ob + (size_t)(L.k0 + j + (reverse ? 0 : 1)) * NX, x.r);
+    });
 }
 
 // AoS (batch, nx) -> SoA seed planes (stride batch); NULL source = zeros.
@@ -662,7 +948,7 @@ __global__ void k_aff_seed(const double* __restrict__ src, int batch, double* __
 
 // SoA planes (stride `stride`, index idx) -> AoS carry (time-sharded mode)
 static __global__ void k_soa_to_aos(const double* __restrict__ soa, size_t stride, size_t idx, int sz,
-                             double* __restrict__ aos) {
+                                    double* __restrict__ aos) {
     const int c = threadIdx.x;
     if (c < sz) aos[c] = soa[(size_t)c * stride + idx];
 }
@@ -670,34 +956,45 @@ static __global__ void k_soa_to_aos(const double* __restrict__ soa, size_t strid
 // =================================================================== host side
 constexpr int MAXLEV = 8;
 struct Plan {
-    int N, batch, T0, n1, nlev;
-    int n[MAXLEV];   // aggregates per sequence at level l (n[0] = n1)
-    int T[MAXLEV];   // fan-in from level l to l+1
+    Geom g;
+    int nlev;          // aggregate levels above the warps (0: the seed enters every warp directly)
+    int n[MAXLEV];     // aggregates per sequence at level l (n[0] = nW)
+    int T[MAXLEV];     // fan-in from level l to l+1
+    long long warps, slots;
 };
 
-static Plan make_plan(int N, int batch) {
+// force_scan: time-sharded mode always wants the segment total, hence at least one level.
+static Plan make_plan(int N, int batch, bool force_scan = false) {
     Plan p{};
-    p.N = N;
-    p.batch = batch;
-    const int top_max = g_tune.top_max > 0 ? g_tune.top_max : 512;
+    Geom& g = p.g;
+    g.N = N;
+    g.batch = batch;
+    const int top_max = g_tune.top_max > 0 ? g_tune.top_max : 2048;
     const int mid = g_tune.mid_fanin > 1 ? g_tune.mid_fanin : 8;
     int T0 = g_tune.leaf_chunk;
+    g.per_lane = 0;
     if (T0 <= 0) {
-        const long long total = (long long)N * batch;
-        if (batch >= kTargetThreads / 4) {
-            T0 = N;   // enough independent problems: one pass, no scan
+        if (!force_scan && (long long)batch * 2 >= kTargetThreads) {
+            T0 = N;   // enough independent problems: one sequence per lane, single pass, no scan
         } else {
-            long long t = (total + kTargetThreads - 1) / kTargetThreads;
+            long long want = (kTargetThreads + batch - 1) / batch;   // chunks per sequence to fill the chip
+            want = ((want + 31) / 32) * 32;                          // whole warps
+            if (want < 32) want = 32;
+            long long t = ((long long)N + want - 1) / want;
             T0 = (int)(t < 4 ? 4 : t);
         }
     }
     if (T0 > N) T0 = N;
     if (T0 < 1) T0 = 1;
-    p.T0 = T0;
-    p.n1 = (N + T0 - 1) / T0;
+    g.T0 = T0;
+    g.n1 = (N + T0 - 1) / T0;
+    if (g.n1 == 1 && !force_scan && batch >= 32) g.per_lane = 1;
+    g.nW = g.per_lane ? 1 : (g.n1 + 31) / 32;
+    p.warps = g.per_lane ? ((long long)batch + 31) / 32 : (long long)batch * g.nW;
+    p.slots = p.warps * 32;
     p.nlev = 0;
-    if (p.n1 > 1) {
-        p.n[0] = p.n1;
+    if (!g.per_lane && (g.nW > 1 || force_scan)) {
+        p.n[0] = g.nW;
         p.nlev = 1;
         while (p.n[p.nlev - 1] > top_max && p.nlev < MAXLEV) {
             p.T[p.nlev - 1] = mid;
@@ -722,19 +1019,25 @@ struct Bump {
 };
 
 struct ScanWs {   // workspace of one hierarchical scan
-    double* agg[MAXLEV];
-    double* val[MAXLEV];
+    double* incl;          // per-thread in-warp inclusive aggregates (SoA, stride = slots)
+    double* agg[MAXLEV];   // agg[0] = warp totals
+    double* val[MAXLEV];   // val[0] = value entering each warp
     double* seed;
     double* total;
 };
 
 static void carve_scan(Bump& bp, const Plan& p, int esz, int vsz, ScanWs& w) {
+    w.incl = bp.take<double>((size_t)esz * p.slots);
     for (int l = 0; l < p.nlev; ++l) {
-        w.agg[l] = bp.take<double>((size_t)esz * p.batch * p.n[l]);
-        w.val[l] = bp.take<double>((size_t)vsz * p.batch * p.n[l]);
+        w.agg[l] = bp.take<double>((size_t)esz * p.g.batch * p.n[l]);
+        w.val[l] = bp.take<double>((size_t)vsz * p.g.batch * p.n[l]);
     }
-    w.seed = bp.take<double>((size_t)vsz * p.batch);
-    w.total = bp.take<double>((size_t)esz * p.batch);
+    if (p.nlev == 0) {   // still need a place for the (unused) warp totals of the leaf-up kernels
+        w.agg[0] = bp.take<double>((size_t)esz * p.g.batch * p.g.nW);
+        w.val[0] = nullptr;
+    }
+    w.seed = bp.take<double>((size_t)vsz * p.g.batch);
+    w.total = bp.take<double>((size_t)esz * p.g.batch);
 }
 
 struct NewtonWs {
@@ -748,8 +1051,8 @@ template <int NX>
 static void carve_newton(Bump& bp, const Plan& p, NewtonWs& w) {
     carve_scan(bp, p, RicElem<NX>::ESZ, RicVal<NX>::VSZ, w.ric);
     carve_scan(bp, p, AffElem<NX>::ESZ, NX, w.aff);
-    w.pred_part = bp.take<double>((size_t)p.batch * p.n1);
-    w.feas_part = bp.take<int>((size_t)p.batch * p.n1);
+    w.pred_part = bp.take<double>((size_t)p.warps);
+    w.feas_part = bp.take<int>((size_t)p.warps);
     w.scratch = bp.take<double>(256);
 }
 
@@ -759,93 +1062,188 @@ static void carve_newton(Bump& bp, const Plan& p, NewtonWs& w) {
         prof_mark(name, st);                                       \
         if (cudaPeekAtLastError() != cudaSuccess) return IPOC_ECUDA; \
     } while (0)
-#define IPOC_LAUNCH_CHECK() IPOC_LAUNCH_CHECK_N("kernel", st)
 
 static inline unsigned grid_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
-static inline int top_threads(int n) {
-    int t = ((n + 31) / 32) * 32;
-    return t > kTopThreads ? kTopThreads : t;
+// Leaf launch shape: warps per CTA limited by the double-buffered stage (two CTAs per SM should fit).
+struct LeafLaunch {
+    int wpc, threads;
+    unsigned grid;
+    size_t smem;
+};
+static LeafLaunch leaf_launch(const Plan& p, int stage_bytes, size_t scratch_bytes = 0) {
+    // Warps of a leaf CTA never synchronise with each other, so the CTA size is free: take the
+    // smallest CTA that still reaches the largest number of resident warps per SM under the
+    // shared-memory limit (228 KB per SM, 1 KB reserved per CTA, at most 32 CTAs) — small CTAs
+    // balance the single wave better.
+    size_t body = 2 * (size_t)stage_bytes;   // the scan scratch reuses the stage area after the walk
+    if (body < scratch_bytes) body = scratch_bytes;
+    const size_t per_warp = (size_t)kTabBytes + body;
+    const size_t sm_bytes = 228 * 1024;
+    int best_wpc = 1, best_warps = 0;
+    for (int wpc = 1; wpc <= kLeafThreads / 32; wpc *= 2) {
+        const size_t cta = per_warp * wpc + 1024;
+        if (per_warp * wpc > 227 * 1024) break;
+        long long ctas = (long long)(sm_bytes / cta);
+        if (ctas > 32) ctas = 32;
+        const int warps = (int)(ctas * wpc);
+        if (warps > best_warps) {
+            best_warps = warps;
+            best_wpc = wpc;
+        }
+    }
+    LeafLaunch l;
+    l.wpc = best_wpc;
+    l.threads = best_wpc * 32;
+    l.grid = (unsigned)((p.warps + best_wpc - 1) / best_wpc);
+    l.smem = per_warp * best_wpc;
+    return l;
+}
+template <class K>
+static int set_smem_plain(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+            return IPOC_ECUDA;
+    return IPOC_OK;
+}
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+            return IPOC_ECUDA;
+    // ask for the largest shared-memory carve-out so that two CTAs (8 warps) fit per SM
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) !=
+        cudaSuccess)
+        return IPOC_ECUDA;
+    return IPOC_OK;
 }
 
-// up-sweep over the aggregate levels (level 0 already filled), top scan, down-sweep to level 0.
-// On return w.val[0] holds the value entering every leaf chunk.  If reduce_only, only the total
-// aggregate of each sequence is produced (w.total, SoA stride batch).
+// top-scan launch shape: up to kTopThreads threads, limited by the per-warp scan scratch
 template <class Op>
-static int run_levels(const Plan& p, const ScanWs& w, bool want_total, bool reduce_only, cudaStream_t st) {
-    const int L = p.nlev;
+static inline int top_threads(int n) {
+    constexpr size_t per_warp = 2 * sizeof(typename Op::Elem) * 32;
+    int maxw = (int)((200 * 1024) / per_warp);
+    if (maxw > kTopThreads / 32) maxw = kTopThreads / 32;
+    if (maxw < 1) maxw = 1;
+    int t = ((n + 31) / 32) * 32;
+    return t > maxw * 32 ? maxw * 32 : t;
+}
+template <class Op>
+static inline size_t top_smem(int threads) { return 2 * sizeof(typename Op::Elem) * 32 * (size_t)(threads / 32); }
+template <class Op>
+static int top_prepare(int threads) {
+    return set_smem_plain(k_top<Op>, top_smem<Op>(threads));
+}
+
+// up-sweep over the aggregate levels (level 0 = warp totals, already filled), top scan, down-sweep
+// to level 0.  On return w.val[0] holds the value entering every warp.  If reduce_only, only the
+// total aggregate of each sequence is produced (w.total, SoA stride batch).
+template <class Op>
+static int run_levels(const Plan& p, const ScanWs& w, bool want_total, bool reduce_only, cudaStream_t st,
+                      PredJob pj = PredJob{nullptr, nullptr, 0, nullptr, nullptr}) {
+    const int L = p.nlev, batch = p.g.batch;
     for (int l = 0; l + 1 < L; ++l) {
-        const long long cnt = (long long)p.batch * p.n[l + 1];
+        const long long cnt = (long long)batch * p.n[l + 1];
         k_mid_up<Op><<<grid_for(cnt, kMidThreads), kMidThreads, 0, st>>>(
-            w.agg[l], (size_t)p.batch * p.n[l], p.n[l], w.agg[l + 1], (size_t)p.batch * p.n[l + 1], p.n[l + 1],
-            p.T[l], p.batch);
+            w.agg[l], (size_t)batch * p.n[l], p.n[l], w.agg[l + 1], (size_t)batch * p.n[l + 1], p.n[l + 1],
+            p.T[l], batch);
         IPOC_LAUNCH_CHECK_N(Op::tag_mid_up, st);
     }
-    k_top<Op><<<p.batch, top_threads(p.n[L - 1]), 0, st>>>(
-        w.agg[L - 1], (size_t)p.batch * p.n[L - 1], p.n[L - 1], p.batch, w.seed, w.val[L - 1],
-        (size_t)p.batch * p.n[L - 1], (want_total || reduce_only) ? w.total : nullptr, reduce_only ? 1 : 0);
+    const int tt = top_threads<Op>(p.n[L - 1]);
+    if (int rc = top_prepare<Op>(tt)) return rc;
+    k_top<Op><<<batch, tt, top_smem<Op>(tt), st>>>(
+        w.agg[L - 1], (size_t)batch * p.n[L - 1], p.n[L - 1], batch, w.seed, w.val[L - 1],
+        (size_t)batch * p.n[L - 1], (want_total || reduce_only) ? w.total : nullptr, reduce_only ? 1 : 0, pj);
     IPOC_LAUNCH_CHECK_N(Op::tag_top, st);
     if (reduce_only) return IPOC_OK;
     for (int l = L - 2; l >= 0; --l) {
-        const long long cnt = (long long)p.batch * p.n[l + 1];
+        const long long cnt = (long long)batch * p.n[l + 1];
         k_mid_down<Op><<<grid_for(cnt, kMidThreads), kMidThreads, 0, st>>>(
-            w.agg[l], (size_t)p.batch * p.n[l], p.n[l], w.val[l], (size_t)p.batch * p.n[l], w.val[l + 1],
-            (size_t)p.batch * p.n[l + 1], p.n[l + 1], p.T[l], p.batch);
+            w.agg[l], (size_t)batch * p.n[l], p.n[l], w.val[l], (size_t)batch * p.n[l], w.val[l + 1],
+            (size_t)batch * p.n[l + 1], p.n[l + 1], p.T[l], batch);
         IPOC_LAUNCH_CHECK_N(Op::tag_mid_down, st);
     }
     return IPOC_OK;
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// values entering the warps: from the levels, or straight from the seed when there is one warp
+// per sequence (or one sequence per lane)
+static void leaf_values(const Plan& p, const ScanWs& w, const double*& vals, size_t& stride) {
+    if (p.nlev > 0) {
+        vals = w.val[0];
+        stride = (size_t)p.g.batch * p.g.nW;
+    } else {
+        vals = w.seed;
+        stride = (size_t)p.g.batch;
+    }
+}
 
 // ---- K2 (+K3 aggregates) for any loader ---------------------------------------------------
 template <int NX, int NU, class Loader>
-static int run_bwd(const Plan& p, const NewtonWs& w, const Loader& ld, double* Kx, double* d, double* S, double* v,
-                   double* pred, int32_t* feasible, bool want_fwd_agg, cudaStream_t st) {
-    using ROp = RicOp<NX>;
-    const long long chunks = (long long)p.batch * p.n1;
-    const double* leaf_vals;
-    size_t leaf_vstride;
-    if (p.nlev > 0) {
-        k_ric_leaf_up<NX, NU, Loader><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
-            ld, p.N, p.T0, p.n1, p.batch, w.ric.agg[0], (size_t)chunks);
-        IPOC_LAUNCH_CHECK_N("k_ric_leaf_up", st);
-        int rc = run_levels<ROp>(p, w.ric, false, false, st);
-        if (rc) return rc;
-        leaf_vals = w.ric.val[0];
-        leaf_vstride = (size_t)chunks;
-    } else {
-        leaf_vals = w.ric.seed;
-        leaf_vstride = (size_t)p.batch;
-    }
-    double* fagg = nullptr;
-    size_t fstride = 0;
-    if (want_fwd_agg && p.nlev > 0) {
-        fagg = w.aff.agg[0];
-        fstride = (size_t)chunks;
-    }
-    k_ric_leaf_down<NX, NU, Loader><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
-        ld, p.N, p.T0, p.n1, p.batch, leaf_vals, leaf_vstride, Kx, d, S, v, w.pred_part, w.feas_part, fagg, fstride);
-    IPOC_LAUNCH_CHECK_N("k_ric_leaf_down", st);
-    k_finalize_pred<<<p.batch, 256, 0, st>>>(w.pred_part, w.feas_part, p.n1, pred, feasible, 0);
-    IPOC_LAUNCH_CHECK_N("k_finalize_pred", st);
+static int run_bwd_up(const Plan& p, const NewtonWs& w, const Loader& ld, cudaStream_t st) {
+    const LeafLaunch ll = leaf_launch(p, Loader::STAGE_BYTES, scan_scratch_bytes<RicOp<NX>>());
+    Geom g = p.g;
+    g.pw_bytes = (int)(ll.smem / ll.wpc);
+    auto kern = k_ric_leaf_up<NX, NU, Loader>;
+    if (int rc = set_smem(kern, ll.smem)) return rc;
+    kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.ric.incl, (size_t)p.slots, w.ric.agg[0],
+                                              (size_t)p.g.batch * p.g.nW);
+    IPOC_LAUNCH_CHECK_N("k_ric_leaf_up", st);
     return IPOC_OK;
 }
 
-// ---- K3 given leaf aggregates in w.aff.agg[0] (if nlev > 0) and seed in w.aff.seed ---------
+template <int NX, int NU, class Loader>
+static int run_bwd_down(const Plan& p, const NewtonWs& w, const Loader& ld, double* Kx, double* d, double* S,
+                        double* v, double* pred, int32_t* feasible, bool want_fwd_agg, cudaStream_t st,
+                        bool defer_pred = false) {
+    const double* vals;
+    size_t vstride;
+    leaf_values(p, w.ric, vals, vstride);
+    const LeafLaunch ll = leaf_launch(p, Loader::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>());
+    Geom g = p.g;
+    g.pw_bytes = (int)(ll.smem / ll.wpc);
+    auto kern = k_ric_leaf_down<NX, NU, Loader>;
+    if (int rc = set_smem(kern, ll.smem)) return rc;
+    const bool fwd = want_fwd_agg && !p.g.per_lane;
+    kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.ric.incl, (size_t)p.slots, vals, vstride, Kx, d, S, v,
+                                              w.pred_part, w.feas_part, pred, feasible, fwd ? w.aff.incl : nullptr,
+                                              (size_t)p.slots, fwd ? w.aff.agg[0] : nullptr,
+                                              (size_t)p.g.batch * p.g.nW);
+    IPOC_LAUNCH_CHECK_N("k_ric_leaf_down", st);
+    if (!p.g.per_lane && !defer_pred) {
+        k_finalize_pred<<<p.g.batch, 32, 0, st>>>(PredJob{w.pred_part, w.feas_part, p.g.nW, pred, feasible});
+        IPOC_LAUNCH_CHECK_N("k_finalize_pred", st);
+    }
+    return IPOC_OK;
+}
+
+template <int NX, int NU, class Loader>
+static int run_bwd(const Plan& p, const NewtonWs& w, const Loader& ld, double* Kx, double* d, double* S, double* v,
+                   double* pred, int32_t* feasible, bool want_fwd_agg, cudaStream_t st, bool defer_pred = false) {
+    if (!p.g.per_lane) {
+        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st)) return rc;
+        if (p.nlev > 0)
+            if (int rc = run_levels<RicOp<NX>>(p, w.ric, false, false, st)) return rc;
+    }
+    return run_bwd_down<NX, NU>(p, w, ld, Kx, d, S, v, pred, feasible, want_fwd_agg, st, defer_pred);
+}
+
+// ---- K3 given in-warp forward aggregates in w.aff.incl / w.aff.agg[0] and the seed in w.aff.seed
 template <int NX, int NU>
 static int run_fwd_down(const Plan& p, const NewtonWs& w, const double* A, const double* B, const double* c,
-                        const double* Kx, const double* d, double* x, double* u, cudaStream_t st) {
-    const long long chunks = (long long)p.batch * p.n1;
-    const double* leaf_vals = w.aff.seed;
-    size_t leaf_vstride = (size_t)p.batch;
-    if (p.nlev > 0) {
-        int rc = run_levels<AffOp<NX>>(p, w.aff, false, false, st);
-        if (rc) return rc;
-        leaf_vals = w.aff.val[0];
-        leaf_vstride = (size_t)chunks;
-    }
-    k_fwd_leaf_down<NX, NU><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
-        A, B, c, Kx, d, p.N, p.T0, p.n1, p.batch, leaf_vals, leaf_vstride, x, u);
+                        const double* Kx, const double* d, double* x, double* u, bool levels, cudaStream_t st,
+                        PredJob pj = PredJob{nullptr, nullptr, 0, nullptr, nullptr}) {
+    if (levels && p.nlev > 0)
+        if (int rc = run_levels<AffOp<NX>>(p, w.aff, false, false, st, pj)) return rc;
+    const double* vals;
+    size_t vstride;
+    leaf_values(p, w.aff, vals, vstride);
+    FwdLoader<NX, NU> ld{A, B, c, Kx, d};
+    const LeafLaunch ll = leaf_launch(p, FwdLoader<NX, NU>::STAGE_BYTES, 0);
+    Geom g = p.g;
+    g.pw_bytes = (int)(ll.smem / ll.wpc);
+    auto kern = k_fwd_leaf_down<NX, NU>;
+    if (int rc = set_smem(kern, ll.smem)) return rc;
+    kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.aff.incl, (size_t)p.slots, vals, vstride, x, u);
     IPOC_LAUNCH_CHECK_N("k_fwd_leaf_down", st);
     return IPOC_OK;
 }
@@ -859,15 +1257,18 @@ static int newton_step_impl(int N, int batch, const double* fx, const double* fu
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
-    // terminal value function: XT = Q[0], HT = I, rT = 0 (ref noc/par_interior_point_newton.py:73-75)
-    k_ric_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(Q, (size_t)N * NX * NX, nullptr, batch, w.ric.seed);
+    // terminal value function: XT = Q[0], HT = I, rT = 0 (ref noc/par_interior_point_newton.py:73-75);
+    // zero initial deviation dx_0 = 0 (:122) — both seeds in one launch
+    k_ric_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(Q, (size_t)N * NX * NX, nullptr, batch, w.ric.seed,
+                                                        w.aff.seed);
     IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
-    k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(nullptr, batch, w.aff.seed);   // dx_0 = 0 (:122)
-    IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
-    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg, N};
-    int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st);
-    if (rc) return rc;
-    return run_fwd_down<NX, NU>(p, w, fx, fu, nullptr, Kx, d, dx, du, st);
+    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg};
+    // the pred / feasibility partials are folded by K3's top scan when there is one
+    const bool defer = p.nlev > 0;
+    if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer)) return rc;
+    PredJob pj{nullptr, nullptr, 0, nullptr, nullptr};
+    if (defer) pj = PredJob{w.pred_part, w.feas_part, p.g.nW, pred, feasible};
+    return run_fwd_down<NX, NU>(p, w, fx, fu, nullptr, Kx, d, dx, du, true, st, pj);
 }
 
 template <int NX, int NU>
@@ -880,10 +1281,25 @@ static int lqt_bwd_impl(int N, int batch, const double* A, const double* B, cons
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
-    k_ric_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(ST, (size_t)NX * NX, vT, batch, w.ric.seed);
+    k_ric_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(ST, (size_t)NX * NX, vT, batch, w.ric.seed, nullptr);
     IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
-    LqtLoader<NX, NU> ld{A, B, c, X, U, M, q, pp, N};
+    LqtLoader<NX, NU> ld{A, B, c, X, U, M, q, pp};
     return run_bwd<NX, NU>(p, w, ld, Kx, d, S, v, pred, feasible, false, st);
+}
+
+template <int NX, int NU>
+static int run_fwd_up(const Plan& p, const NewtonWs& w, const double* A, const double* B, const double* c,
+                      const double* Kx, const double* d, cudaStream_t st) {
+    FwdLoader<NX, NU> ld{A, B, c, Kx, d};
+    const LeafLaunch ll = leaf_launch(p, FwdLoader<NX, NU>::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>());
+    Geom g = p.g;
+    g.pw_bytes = (int)(ll.smem / ll.wpc);
+    auto kern = k_fwd_leaf_up<NX, NU>;
+    if (int rc = set_smem(kern, ll.smem)) return rc;
+    kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.aff.incl, (size_t)p.slots, w.aff.agg[0],
+                                              (size_t)p.g.batch * p.g.nW);
+    IPOC_LAUNCH_CHECK_N("k_fwd_leaf_up", st);
+    return IPOC_OK;
 }
 
 template <int NX, int NU>
@@ -897,13 +1313,41 @@ static int lqt_fwd_impl(int N, int batch, const double* A, const double* B, cons
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(x0, batch, w.aff.seed);
     IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
-    if (p.nlev > 0) {
-        const long long chunks = (long long)batch * p.n1;
-        k_fwd_leaf_up<NX, NU><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
-            A, B, c, Kx, d, N, p.T0, p.n1, batch, w.aff.agg[0], (size_t)chunks);
-        IPOC_LAUNCH_CHECK_N("k_fwd_leaf_up", st);
-    }
-    return run_fwd_down<NX, NU>(p, w, A, B, c, Kx, d, x, u, st);
+    if (!p.g.per_lane)
+        if (int rc = run_fwd_up<NX, NU>(p, w, A, B, c, Kx, d, st)) return rc;
+    return run_fwd_down<NX, NU>(p, w, A, B, c, Kx, d, x, u, true, st);
+}
+
+template <int NX>
+static int aff_up(const Plan& p, const ScanWs& w, const double* F, const double* c, int reverse, int transpose,
+                  cudaStream_t st) {
+    AffLoader<NX> ld{F, c};
+    const LeafLaunch ll = leaf_launch(p, AffLoader<NX>::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>());
+    Geom g = p.g;
+    g.pw_bytes = (int)(ll.smem / ll.wpc);
+    auto kern = k_aff_leaf_up<NX>;
+    if (int rc = set_smem(kern, ll.smem)) return rc;
+    kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, reverse, transpose, g, w.incl, (size_t)p.slots, w.agg[0],
+                                              (size_t)p.g.batch * p.g.nW);
+    IPOC_LAUNCH_CHECK_N("k_aff_leaf_up", st);
+    return IPOC_OK;
+}
+template <int NX>
+static int aff_down(const Plan& p, const ScanWs& w, const double* F, const double* c, int reverse, int transpose,
+                    double* out, cudaStream_t st) {
+    const double* vals;
+    size_t vstride;
+    leaf_values(p, w, vals, vstride);
+    AffLoader<NX> ld{F, c};
+    const LeafLaunch ll = leaf_launch(p, AffLoader<NX>::STAGE_BYTES, 0);
+    Geom g = p.g;
+    g.pw_bytes = (int)(ll.smem / ll.wpc);
+    auto kern = k_aff_leaf_down<NX>;
+    if (int rc = set_smem(kern, ll.smem)) return rc;
+    kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, reverse, transpose, g, w.incl, (size_t)p.slots, vals, vstride,
+                                              out);
+    IPOC_LAUNCH_CHECK_N("k_aff_leaf_down", st);
+    return IPOC_OK;
 }
 
 template <int NX>
@@ -914,55 +1358,56 @@ static int affine_scan_impl(int reverse, int transpose, int N, int batch, const 
     ScanWs w;
     carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
-    k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(seed, batch, w.seed);
-    IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
-    const long long chunks = (long long)batch * p.n1;
-    const double* leaf_vals = w.seed;
-    size_t leaf_vstride = (size_t)batch;
-    if (p.nlev > 0) {
-        k_aff_leaf_up<NX><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
-            F, c, reverse, transpose, N, p.T0, p.n1, batch, w.agg[0], (size_t)chunks);
-        IPOC_LAUNCH_CHECK_N("k_aff_leaf_up", st);
-        int rc = run_levels<AffOp<NX>>(p, w, false, false, st);
-        if (rc) return rc;
-        leaf_vals = w.val[0];
-        leaf_vstride = (size_t)chunks;
+    if (batch == 1 && seed != nullptr) {
+        w.seed = const_cast<double*>(seed);   // one problem: the SoA seed plane IS the caller's vector
+    } else {
+        k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(seed, batch, w.seed);
+        IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
     }
-    k_aff_leaf_down<NX><<<grid_for(chunks, kLeafThreads), kLeafThreads, 0, st>>>(
-        F, c, reverse, transpose, N, p.T0, p.n1, batch, leaf_vals, leaf_vstride, out);
-    IPOC_LAUNCH_CHECK_N("k_aff_leaf_down", st);
-    return IPOC_OK;
+    if (!p.g.per_lane) {
+        if (int rc = aff_up<NX>(p, w, F, c, reverse, transpose, st)) return rc;
+        if (p.nlev > 0)
+            if (int rc = run_levels<AffOp<NX>>(p, w, false, false, st)) return rc;
+    }
+    return aff_down<NX>(p, w, F, c, reverse, transpose, out, st);
 }
 
 // ---- time-sharded split-phase implementations ----------------------------------------------
-// A segment always uses at least one aggregate level here (forced chunking) so that the
-// segment total falls out of the top scan.
-static Plan make_plan_sharded(int N) {
-    Plan p = make_plan(N, 1);
-    if (p.nlev == 0) {   // single chunk: make it a one-aggregate level so k_top produces the total
-        p.n[0] = 1;
-        p.nlev = 1;
-    }
-    return p;
-}
-
+// The reduce phase leaves the in-warp aggregates and the level arrays in the workspace; the apply
+// phase (same workspace, same plan) only runs the seeded way down.
 template <int NX, int NU>
 static int newton_bwd_reduce_impl(int N, const double* fx, const double* fu, const double* ru, const double* Q,
                                   const double* R, const double* M, const double* reg, double* carry_out, void* ws,
                                   size_t ws_bytes, cudaStream_t st) {
-    const Plan p = make_plan_sharded(N);
+    const Plan p = make_plan(N, 1, true);
     Bump bp{(char*)ws, 0, ws_bytes, false};
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
-    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg, N};
-    k_ric_leaf_up<NX, NU, NewtonLoader<NX, NU>><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(
-        ld, N, p.T0, p.n1, 1, w.ric.agg[0], (size_t)p.n1);
-    IPOC_LAUNCH_CHECK_N("k_ric_leaf_up", st);
-    int rc = run_levels<RicOp<NX>>(p, w.ric, true, true, st);
-    if (rc) return rc;
+    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg};
+    if (int rc = run_bwd_up<NX, NU>(p, w, ld, st)) return rc;
+    if (int rc = run_levels<RicOp<NX>>(p, w.ric, true, true, st)) return rc;
     k_soa_to_aos<<<1, 256, 0, st>>>(w.ric.total, 1, 0, RicElem<NX>::ESZ, carry_out);
     IPOC_LAUNCH_CHECK_N("k_soa_to_aos", st);
+    return IPOC_OK;
+}
+
+// levels on the way down only (aggregates already in the workspace)
+template <class Op>
+static int run_levels_down(const Plan& p, const ScanWs& w, cudaStream_t st) {
+    const int L = p.nlev;
+    const int tt = top_threads<Op>(p.n[L - 1]);
+    if (int rc = top_prepare<Op>(tt)) return rc;
+    k_top<Op><<<1, tt, top_smem<Op>(tt), st>>>(w.agg[L - 1], (size_t)p.n[L - 1], p.n[L - 1], 1, w.seed,
+                                               w.val[L - 1], (size_t)p.n[L - 1], nullptr, 0,
+                                               PredJob{nullptr, nullptr, 0, nullptr, nullptr});
+    IPOC_LAUNCH_CHECK_N(Op::tag_top, st);
+    for (int l = L - 2; l >= 0; --l) {
+        k_mid_down<Op><<<grid_for(p.n[l + 1], kMidThreads), kMidThreads, 0, st>>>(
+            w.agg[l], (size_t)p.n[l], p.n[l], w.val[l], (size_t)p.n[l], w.val[l + 1], (size_t)p.n[l + 1], p.n[l + 1],
+            p.T[l], 1);
+        IPOC_LAUNCH_CHECK_N(Op::tag_mid_down, st);
+    }
     return IPOC_OK;
 }
 
@@ -972,42 +1417,21 @@ static int newton_bwd_apply_impl(int N, int rank, int nranks, const double* fx, 
                                  const double* carries, const double* ST, double* Kx, double* d, double* pred,
                                  int32_t* feasible, double* fwd_carry_out, void* ws, size_t ws_bytes,
                                  cudaStream_t st) {
-    const Plan p = make_plan_sharded(N);
+    const Plan p = make_plan(N, 1, true);
     Bump bp{(char*)ws, 0, ws_bytes, false};
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
-    // terminal seed of the whole horizon, then pushed back through the later ranks' aggregates
+    // terminal seed of the whole horizon, pushed back through the later ranks' aggregates
     double* seed0 = w.scratch;   // RicVal packed
-    k_ric_seed<NX><<<1, 32, 0, st>>>(ST, (size_t)NX * NX, nullptr, 1, seed0);
+    k_ric_seed<NX><<<1, 32, 0, st>>>(ST, (size_t)NX * NX, nullptr, 1, seed0, nullptr);
     IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
     k_chain_seed<RicOp<NX>><<<1, 32, 0, st>>>(carries, nranks - 1, -1, nranks - 1 - rank, seed0, w.ric.seed);
     IPOC_LAUNCH_CHECK_N("k_chain_seed_ric", st);
-    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg, N};
-    // the leaf aggregates of this segment were computed in the reduce phase with the same plan
-    // and are still in the workspace (same carve order) — the caller must pass the same ws.
-    using ROp = RicOp<NX>;
-    {
-        // recompute values from existing aggregates: top (not reduce-only) + mid downs
-        const int L = p.nlev;
-        k_top<ROp><<<1, top_threads(p.n[L - 1]), 0, st>>>(w.ric.agg[L - 1], (size_t)p.n[L - 1], p.n[L - 1], 1,
-                                                         w.ric.seed, w.ric.val[L - 1], (size_t)p.n[L - 1], nullptr, 0);
-        IPOC_LAUNCH_CHECK_N("k_top_ric", st);
-        for (int l = L - 2; l >= 0; --l) {
-            k_mid_down<ROp><<<grid_for(p.n[l + 1], kMidThreads), kMidThreads, 0, st>>>(
-                w.ric.agg[l], (size_t)p.n[l], p.n[l], w.ric.val[l], (size_t)p.n[l], w.ric.val[l + 1],
-                (size_t)p.n[l + 1], p.n[l + 1], p.T[l], 1);
-            IPOC_LAUNCH_CHECK_N("k_mid_down_ric", st);
-        }
-    }
-    k_ric_leaf_down<NX, NU, NewtonLoader<NX, NU>><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(
-        ld, N, p.T0, p.n1, 1, w.ric.val[0], (size_t)p.n1, Kx, d, nullptr, nullptr, w.pred_part, w.feas_part,
-        w.aff.agg[0], (size_t)p.n1);
-    IPOC_LAUNCH_CHECK_N("k_ric_leaf_down", st);
-    k_finalize_pred<<<1, 256, 0, st>>>(w.pred_part, w.feas_part, p.n1, pred, feasible, 0);
-    IPOC_LAUNCH_CHECK_N("k_finalize_pred", st);
-    int rc = run_levels<AffOp<NX>>(p, w.aff, true, true, st);
-    if (rc) return rc;
+    if (int rc = run_levels_down<RicOp<NX>>(p, w.ric, st)) return rc;
+    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg};
+    if (int rc = run_bwd_down<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st)) return rc;
+    if (int rc = run_levels<AffOp<NX>>(p, w.aff, true, true, st)) return rc;
     k_soa_to_aos<<<1, 256, 0, st>>>(w.aff.total, 1, 0, AffElem<NX>::ESZ, fwd_carry_out);
     IPOC_LAUNCH_CHECK_N("k_soa_to_aos", st);
     return IPOC_OK;
@@ -1017,7 +1441,7 @@ template <int NX, int NU>
 static int newton_fwd_apply_impl(int N, int rank, int nranks, const double* fx, const double* fu, const double* Kx,
                                  const double* d, const double* fwd_carries, double* dx, double* du, void* ws,
                                  size_t ws_bytes, cudaStream_t st) {
-    const Plan p = make_plan_sharded(N);
+    const Plan p = make_plan(N, 1, true);
     Bump bp{(char*)ws, 0, ws_bytes, false};
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
@@ -1027,36 +1451,20 @@ static int newton_fwd_apply_impl(int N, int rank, int nranks, const double* fx, 
     IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
     k_chain_seed<AffOp<NX>><<<1, 32, 0, st>>>(fwd_carries, 0, +1, rank, seed0, w.aff.seed);
     IPOC_LAUNCH_CHECK_N("k_chain_seed_aff", st);
-    using AOp = AffOp<NX>;
-    const int L = p.nlev;
-    k_top<AOp><<<1, top_threads(p.n[L - 1]), 0, st>>>(w.aff.agg[L - 1], (size_t)p.n[L - 1], p.n[L - 1], 1, w.aff.seed,
-                                                     w.aff.val[L - 1], (size_t)p.n[L - 1], nullptr, 0);
-    IPOC_LAUNCH_CHECK_N("k_top_aff", st);
-    for (int l = L - 2; l >= 0; --l) {
-        k_mid_down<AOp><<<grid_for(p.n[l + 1], kMidThreads), kMidThreads, 0, st>>>(
-            w.aff.agg[l], (size_t)p.n[l], p.n[l], w.aff.val[l], (size_t)p.n[l], w.aff.val[l + 1], (size_t)p.n[l + 1],
-            p.n[l + 1], p.T[l], 1);
-        IPOC_LAUNCH_CHECK_N("k_mid_down_aff", st);
-    }
-    k_fwd_leaf_down<NX, NU><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(
-        fx, fu, nullptr, Kx, d, N, p.T0, p.n1, 1, w.aff.val[0], (size_t)p.n1, dx, du);
-    IPOC_LAUNCH_CHECK_N("k_fwd_leaf_down", st);
-    return IPOC_OK;
+    if (int rc = run_levels_down<AffOp<NX>>(p, w.aff, st)) return rc;
+    return run_fwd_down<NX, NU>(p, w, fx, fu, nullptr, Kx, d, dx, du, false, st);
 }
 
 template <int NX>
 static int affine_reduce_impl(int reverse, int transpose, int N, const double* F, const double* c, double* carry_out,
                               void* ws, size_t ws_bytes, cudaStream_t st) {
-    const Plan p = make_plan_sharded(N);
+    const Plan p = make_plan(N, 1, true);
     Bump bp{(char*)ws, 0, ws_bytes, false};
     ScanWs w;
     carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
-    k_aff_leaf_up<NX><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(F, c, reverse, transpose, N, p.T0, p.n1,
-                                                                            1, w.agg[0], (size_t)p.n1);
-    IPOC_LAUNCH_CHECK_N("k_aff_leaf_up", st);
-    int rc = run_levels<AffOp<NX>>(p, w, true, true, st);
-    if (rc) return rc;
+    if (int rc = aff_up<NX>(p, w, F, c, reverse, transpose, st)) return rc;
+    if (int rc = run_levels<AffOp<NX>>(p, w, true, true, st)) return rc;
     k_soa_to_aos<<<1, 256, 0, st>>>(w.total, 1, 0, AffElem<NX>::ESZ, carry_out);
     IPOC_LAUNCH_CHECK_N("k_soa_to_aos", st);
     return IPOC_OK;
@@ -1066,7 +1474,7 @@ template <int NX>
 static int affine_apply_impl(int reverse, int transpose, int N, int rank, int nranks, const double* F,
                              const double* c, const double* carries, const double* seed, double* out, void* ws,
                              size_t ws_bytes, cudaStream_t st) {
-    const Plan p = make_plan_sharded(N);
+    const Plan p = make_plan(N, 1, true);
     Bump bp{(char*)ws, 0, ws_bytes, false};
     ScanWs w;
     carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
@@ -1077,25 +1485,13 @@ static int affine_apply_impl(int reverse, int transpose, int N, int rank, int nr
     else
         k_chain_seed<AOp><<<1, 32, 0, st>>>(carries, 0, +1, rank, seed, w.seed);
     IPOC_LAUNCH_CHECK_N("k_chain_seed_aff", st);
-    const int L = p.nlev;
-    k_top<AOp><<<1, top_threads(p.n[L - 1]), 0, st>>>(w.agg[L - 1], (size_t)p.n[L - 1], p.n[L - 1], 1, w.seed,
-                                                     w.val[L - 1], (size_t)p.n[L - 1], nullptr, 0);
-    IPOC_LAUNCH_CHECK_N("k_top_aff", st);
-    for (int l = L - 2; l >= 0; --l) {
-        k_mid_down<AOp><<<grid_for(p.n[l + 1], kMidThreads), kMidThreads, 0, st>>>(
-            w.agg[l], (size_t)p.n[l], p.n[l], w.val[l], (size_t)p.n[l], w.val[l + 1], (size_t)p.n[l + 1], p.n[l + 1],
-            p.T[l], 1);
-        IPOC_LAUNCH_CHECK_N("k_mid_down_aff", st);
-    }
-    k_aff_leaf_down<NX><<<grid_for(p.n1, kLeafThreads), kLeafThreads, 0, st>>>(F, c, reverse, transpose, N, p.T0,
-                                                                              p.n1, 1, w.val[0], (size_t)p.n1, out);
-    IPOC_LAUNCH_CHECK_N("k_aff_leaf_down", st);
-    return IPOC_OK;
+    if (int rc = run_levels_down<AOp>(p, w, st)) return rc;
+    return aff_down<NX>(p, w, F, c, reverse, transpose, out, st);
 }
 
 template <int NX>
 static size_t ws_bytes_impl(int kind, int N, int batch, bool sharded) {
-    const Plan p = sharded ? make_plan_sharded(N) : make_plan(N, batch);
+    const Plan p = make_plan(N, sharded ? 1 : batch, sharded);
     Bump bp{nullptr, 0, 0, true};
     if (kind == IPOC_WS_AFFINE_SCAN) {
         ScanWs w;
@@ -1106,6 +1502,5 @@ static size_t ws_bytes_impl(int kind, int N, int batch, bool sharded) {
     }
     return bp.off + 256;
 }
-
 
 }  // namespace ipoc

@@ -125,6 +125,17 @@ struct AffVal {
     double r[VSZ];
 };
 
+// Strided read-only views of elements kept in (shared) memory: component c lives at p[c * s].
+// The scan kernels keep both operands of a combine in shared memory so that only the result and
+// the temporaries occupy registers (two register-resident operands + result would exceed 255).
+template <int NX>
+struct AffView {
+    const double* p;
+    int s;
+    IPOC_DEV double F(int i, int j) const { return p[(i * NX + j) * s]; }
+    IPOC_DEV double c(int i) const { return p[(NX * NX + i) * s]; }
+};
+
 template <int NX>
 struct AffOp {
     using Elem = AffElem<NX>;
@@ -140,8 +151,10 @@ struct AffOp {
             e.c(i) = 0.0;
         }
     }
+    using View = AffView<NX>;
     // out = second o first
-    IPOC_DEV static void compose(Elem& out, const Elem& first, const Elem& second) {
+    template <class E2, class E1>
+    IPOC_DEV static void compose_t(Elem& out, const E2& first, const E1& second) {
         Elem t;
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
@@ -159,7 +172,11 @@ struct AffOp {
         }
         out = t;
     }
-    IPOC_DEV static void apply(Val& out, const Elem& e, const Val& x) {
+    IPOC_DEV static void compose(Elem& out, const Elem& first, const Elem& second) {
+        compose_t<Elem, Elem>(out, first, second);
+    }
+    template <class E>
+    IPOC_DEV static void apply_t(Val& out, const E& e, const Val& x) {
         Val t;
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
@@ -170,6 +187,15 @@ struct AffOp {
         }
         out = t;
     }
+    IPOC_DEV static void apply(Val& out, const Elem& e, const Val& x) { apply_t<Elem>(out, e, x); }
+    // memory-to-memory forms used by the generic scan kernels (strided operands, see RicOp)
+    IPOC_DEV static void compose_mm(double* dst, int ds, const double* first, int fs, const double* second, int ss) {
+        Elem o;
+        compose_t(o, View{first, fs}, View{second, ss});
+#pragma unroll
+        for (int c = 0; c < Elem::ESZ; ++c) dst[c * ds] = o.r[c];
+    }
+    IPOC_DEV static void apply_mm(Val& v, const double* e, int es) { apply_t(v, View{e, es}, v); }
 };
 
 // ================================================================ Riccati operator (K2)
@@ -192,6 +218,18 @@ struct RicElem {
     IPOC_DEV double eta(int i) const { return r[OE + i]; }
     IPOC_DEV double& J(int i, int j) { return r[OJ + Sym<NX>::at(i, j)]; }
     IPOC_DEV double J(int i, int j) const { return r[OJ + Sym<NX>::at(i, j)]; }
+};
+
+template <int NX>
+struct RicView {
+    using E = RicElem<NX>;
+    const double* p;
+    int s;
+    IPOC_DEV double A(int i, int j) const { return p[(E::OA + i * NX + j) * s]; }
+    IPOC_DEV double b(int i) const { return p[(E::OB + i) * s]; }
+    IPOC_DEV double C(int i, int j) const { return p[(E::OC + Sym<NX>::at(i, j)) * s]; }
+    IPOC_DEV double eta(int i) const { return p[(E::OE + i) * s]; }
+    IPOC_DEV double J(int i, int j) const { return p[(E::OJ + Sym<NX>::at(i, j)) * s]; }
 };
 
 // Value function V(x) = 1/2 x' S x - v' x
@@ -223,103 +261,111 @@ struct RicOp {
 
     // The scan runs backwards in time: `first` is the LATER segment (j -> k, already holding the
     // value information of the end of the horizon), `second` the EARLIER one (i -> j).
-    // out = combine(e1 = second, e2 = first):
-    //   W = I + C1 J2
+    // out = combine(e1 = second, e2 = first), with W = I + C1 J2:
     //   A = A2 W^-1 A1            b = A2 W^-1 (b1 + C1 eta2) + b2      C = A2 W^-1 C1 A2' + C2
     //   eta = A1' W^-T (eta2 - J2 b1) + eta1                            J = A1' W^-T J2 A1 + J1
-    IPOC_DEV static void compose(Elem& out, const Elem& first, const Elem& second) {
-        const Elem& e1 = second;
-        const Elem& e2 = first;
+    // Only ONE factorisation is needed: by the push-through identity W^-T J2 = J2 W^-1, so with
+    // XA = W^-1 A1 and xb = W^-1 b1 (two of the right-hand sides of the first solve)
+    //   J = A1' (J2 XA) + J1,      eta = XA' eta2 - A1' (J2 xb) + eta1.
+    using View = RicView<NX>;
+    template <class E2, class E1>
+    IPOC_DEV static void compose_t(Elem& out, const E2& first, const E1& second) {
+        const E1& e1 = second;
+        const E2& e2 = first;
         Elem o;
-        {
-            double W[NX][NX];
-            double X[NX][2 * NX + 1];
+        double W[NX][NX];
+        // right-hand sides: [A1 (NX) | b1 | C1 eta2 | C1 A2' (NX)]
+        double X[NX][2 * NX + 2];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
+        for (int i = 0; i < NX; ++i) {
 #pragma unroll
-                for (int j = 0; j < NX; ++j) {
-                    double w = (i == j) ? 1.0 : 0.0;
-                    double ca = 0.0;
+            for (int j = 0; j < NX; ++j) {
+                double w = (i == j) ? 1.0 : 0.0;
+                double ca = 0.0;
 #pragma unroll
-                    for (int k = 0; k < NX; ++k) {
-                        w += e1.C(i, k) * e2.J(k, j);
-                        ca += e1.C(i, k) * e2.A(j, k);   // (C1 A2')_{ij}
-                    }
-                    W[i][j] = w;
-                    X[i][j] = e1.A(i, j);
-                    X[i][NX + 1 + j] = ca;
+                for (int k = 0; k < NX; ++k) {
+                    w += e1.C(i, k) * e2.J(k, j);
+                    ca += e1.C(i, k) * e2.A(j, k);   // (C1 A2')_{ij}
                 }
-                double s = e1.b(i);
-#pragma unroll
-                for (int k = 0; k < NX; ++k) s += e1.C(i, k) * e2.eta(k);
-                X[i][NX] = s;
+                W[i][j] = w;
+                X[i][j] = e1.A(i, j);
+                X[i][NX + 2 + j] = ca;
             }
-            lu_solve<NX, 2 * NX + 1>(W, X);
+            double s = 0.0;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
-#pragma unroll
-                for (int j = 0; j < NX; ++j) {
-                    double a = 0.0;
-#pragma unroll
-                    for (int k = 0; k < NX; ++k) a += e2.A(i, k) * X[k][j];
-                    o.A(i, j) = a;
-                    if (j >= i) {
-                        double c = e2.C(i, j);
-#pragma unroll
-                        for (int k = 0; k < NX; ++k) c += e2.A(i, k) * X[k][NX + 1 + j];
-                        o.C(i, j) = c;
-                    }
-                }
-                double s = e2.b(i);
-#pragma unroll
-                for (int k = 0; k < NX; ++k) s += e2.A(i, k) * X[k][NX];
-                o.b(i) = s;
-            }
+            for (int k = 0; k < NX; ++k) s += e1.C(i, k) * e2.eta(k);
+            X[i][NX] = e1.b(i);
+            X[i][NX + 1] = s;
         }
-        {
-            double W[NX][NX];
-            double Y[NX][NX + 1];
+        lu_solve<NX, 2 * NX + 2>(W, X);
+        double JX[NX][NX + 1];   // J2 [XA | xb]
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
+        for (int i = 0; i < NX; ++i) {
 #pragma unroll
-                for (int j = 0; j < NX; ++j) {
-                    double w = (i == j) ? 1.0 : 0.0;
-                    double ja = 0.0;
+            for (int j = 0; j < NX; ++j) {
+                double a = 0.0, jx = 0.0;
 #pragma unroll
-                    for (int k = 0; k < NX; ++k) {
-                        w += e2.J(i, k) * e1.C(k, j);
-                        ja += e2.J(i, k) * e1.A(k, j);
-                    }
-                    W[i][j] = w;
-                    Y[i][1 + j] = ja;
+                for (int k = 0; k < NX; ++k) {
+                    a += e2.A(i, k) * X[k][j];
+                    jx += e2.J(i, k) * X[k][j];
                 }
-                double s = e2.eta(i);
+                o.A(i, j) = a;
+                JX[i][j] = jx;
+                if (j >= i) {
+                    double c = e2.C(i, j);
 #pragma unroll
-                for (int k = 0; k < NX; ++k) s -= e2.J(i, k) * e1.b(k);
-                Y[i][0] = s;
+                    for (int k = 0; k < NX; ++k) c += e2.A(i, k) * X[k][NX + 2 + j];
+                    o.C(i, j) = c;
+                }
             }
-            lu_solve<NX, NX + 1>(W, Y);
+            double s = e2.b(i), jb = 0.0;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                double s = e1.eta(i);
+            for (int k = 0; k < NX; ++k) {
+                s += e2.A(i, k) * (X[k][NX] + X[k][NX + 1]);
+                jb += e2.J(i, k) * X[k][NX];
+            }
+            o.b(i) = s;
+            JX[i][NX] = jb;
+        }
 #pragma unroll
-                for (int k = 0; k < NX; ++k) s += e1.A(k, i) * Y[k][0];
-                o.eta(i) = s;
+        for (int i = 0; i < NX; ++i) {
+            double s = e1.eta(i);
 #pragma unroll
-                for (int j = i; j < NX; ++j) {
-                    double c = e1.J(i, j);
+            for (int k = 0; k < NX; ++k) s += X[k][i] * e2.eta(k) - e1.A(k, i) * JX[k][NX];
+            o.eta(i) = s;
 #pragma unroll
-                    for (int k = 0; k < NX; ++k) c += e1.A(k, i) * Y[k][1 + j];
-                    o.J(i, j) = c;
-                }
+            for (int j = i; j < NX; ++j) {
+                double c = e1.J(i, j);
+#pragma unroll
+                for (int k = 0; k < NX; ++k) c += e1.A(k, i) * JX[k][j];
+                o.J(i, j) = c;
             }
         }
         out = o;
     }
+    IPOC_DEV static void compose(Elem& out, const Elem& first, const Elem& second) {
+        compose_t<Elem, Elem>(out, first, second);
+    }
 
     // Push a value function (S, v) at the end of segment e back to its start:
     //   S' = A' (I + S C)^-1 S A + J,   v' = A' (I + S C)^-1 (v - S b) + eta
-    IPOC_DEV static void apply(Val& out, const Elem& e, const Val& in) {
+    IPOC_DEV static void apply(Val& out, const Elem& e, const Val& in) { apply_t<Elem>(out, e, in); }
+    // Memory-to-memory forms, deliberately NOT inlined: the scan kernels of the latency regime run
+    // each combine only a handful of times with one or two warps per SM, where instruction fetch of
+    // the ~2k-instruction unrolled body dominates (profiles/r01b: "no_instructions" stalls, 10
+    // cycles per instruction); one shared copy per kernel keeps the fetched code small.
+    // Operands are strided views (component c at p[c * stride]) in shared, local or global memory;
+    // dst may alias an operand (the result is formed in registers first).
+    static __device__ __noinline__ void compose_mm(double* dst, int ds, const double* first, int fs,
+                                                   const double* second, int ss) {
+        Elem o;
+        compose_t(o, View{first, fs}, View{second, ss});
+#pragma unroll
+        for (int c = 0; c < Elem::ESZ; ++c) dst[c * ds] = o.r[c];
+    }
+    static __device__ __noinline__ void apply_mm(Val& v, const double* e, int es) { apply_t(v, View{e, es}, v); }
+    template <class E>
+    IPOC_DEV static void apply_t(Val& out, const E& e, const Val& in) {
         double W[NX][NX];
         double Y[NX][NX + 1];
 #pragma unroll
