@@ -255,7 +255,9 @@ def run_ours(args):
     h2d = sum(t.numel() * 8 for t in host.values()) + 8
     d2h = dx_h.numel() * 8 + du_h.numel() * 8 + 8 + 4
     torch.cuda.synchronize(dev)
-    dx_check = float((dx_h.to(dev) - npass.dx[0]).abs().max())   # same step as the resident path (rp=1 at first pass only)
+    from ipoc_b200 import noc
+    dx_res = noc.newton_step(w["fx"], w["fu"], w["ru"], w["Q"], w["R"], w["M"], reg_h.to(dev))[0]
+    dx_check = float((dx_h.to(dev) - dx_res).abs().max())   # host-buffer path == resident path on the same inputs
 
     # ---- max over ranks, aggregate
     def allmax(x):

@@ -61,6 +61,12 @@ size_t ipoc_workspace_bytes(int kind, int N, int nx, int nu, int batch);
  * mid-level fan-in, maximum number of aggregates handled by the single-CTA top scan. */
 void ipoc_set_tuning(int leaf_chunk, int mid_fanin, int top_max);
 
+/* Newton-step entry points only: 0 (default) = use the closed form of `noc_to_lqt`'s references
+ * (q = 0, p = ru: what ref noc/par_interior_point_newton.py:62-66 evaluates to in exact arithmetic);
+ * 1 = follow those lines operation by operation (X^-1 M by pivoted LU, s, r, then fold back).
+ * The two differ by rounding of order eps*cond(Q); both are tested against the oracle. */
+void ipoc_set_literal_lqt(int on);
+
 /* ---- K2 + K3: one Newton step ----------------------------------------------------------
  * Replaces `par_Newton` (ref noc/par_interior_point_newton.py:107-124) from the regularisation
  * add onwards: R + reg*I (:118), `noc_to_lqt` (:50-84, r/s by two small solves per step,

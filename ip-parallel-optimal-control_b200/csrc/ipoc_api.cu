@@ -14,6 +14,7 @@ struct Tuning {
 };
 unsigned long long g_launches = 0;
 Tuning g_tune = {0, 0, 0};
+int g_literal_lqt = 0;
 
 // ---- per-launch profiler: one CUDA event after every kernel launch, on the launching stream ----
 constexpr int kMaxProf = 256;
@@ -66,7 +67,7 @@ k_reduce_partial(const double* __restrict__ ru, const double* __restrict__ cu, c
     __shared__ double s_max[kRedThreads];
     __shared__ double s_sq[kRedThreads];
     __shared__ int s_ok[kRedThreads];
-    const int b = blockIdx.y, j = blockIdx.x, t = threadIdx.x;
+    const int b = blockIdx.x / nblk, j = blockIdx.x % nblk, t = threadIdx.x;   // 1-D grid: batch may exceed 65535
     double mx = 0.0, sq = 0.0;
     int ok = 1;
     auto slice = [&](long long total, long long& lo, long long& hi) {
@@ -223,6 +224,8 @@ void ipoc_set_tuning(int leaf_chunk, int mid_fanin, int top_max) {
 
 unsigned long long ipoc_launch_count(void) { return g_launches; }
 
+void ipoc_set_literal_lqt(int on) { g_literal_lqt = on ? 1 : 0; }
+
 int ipoc_carry_doubles(int kind, int nx) {
     if (nx < 1 || nx > 8) return 0;
     const int sy = nx * (nx + 1) / 2;
@@ -303,7 +306,7 @@ int ipoc_reductions_f64(int N, int nu, int nc, int batch, const double* ru, cons
     if (ws_bytes < (size_t)batch * nblk * 3 * sizeof(double)) return IPOC_EWORKSPACE;
     cudaStream_t st_ = (cudaStream_t)stream;
     double* partials = (double*)ws;
-    k_reduce_partial<<<dim3(nblk, batch), kRedThreads, 0, st_>>>(ru, cu, cons, N, nu, nc, nblk, partials);
+    k_reduce_partial<<<(unsigned)((long long)nblk * batch), kRedThreads, 0, st_>>>(ru, cu, cons, N, nu, nc, nblk, partials);
     IPOC_API_LAUNCH_CHECK(st_);
     k_reduce_final<<<batch, kRedThreads, 0, st_>>>(partials, nblk, ru != nullptr, cu != nullptr, cons != nullptr,
                                                    hu_norm, cu_norm, traj_feasible, rp, reg);

@@ -38,12 +38,17 @@ struct Tuning {
 // shared, defined in ipoc_api.cu
 extern unsigned long long g_launches;
 extern Tuning g_tune;
+extern int g_literal_lqt;   // 0: q = 0, p = ru (default); 1: literal noc_to_lqt arithmetic
 void prof_mark(const char* name, cudaStream_t st);   // no-op unless profiling is armed
 
 constexpr int kLeafThreads = 128;
+#ifndef IPOC_RIC_MINB
+#define IPOC_RIC_MINB 1
+#endif
 constexpr int kMidThreads = 128;
 constexpr int kTopThreads = 256;
-constexpr int kTargetThreads = 148 * 256;
+constexpr int kTargetThreads = 148 * 256;       // K2/K3: 8 warps per SM (register-limited)
+constexpr int kAffTargetThreads = 148 * 256;    // K1: light kernels are bytes-in-flight limited
 
 // ------------------------------------------------------------------ SoA helpers
 template <class T>
@@ -359,25 +364,37 @@ __host__ __device__ constexpr int row_gran(int cnt) { return (cnt % 2 == 0) ? 16
 __host__ __device__ constexpr int row_cpr(int cnt) { return cnt * 8 / row_gran(cnt); }
 __host__ __device__ constexpr int row_pitch(int cnt) { return (row_cpr(cnt) % 2 == 1) ? cnt * 8 : cnt * 8 + row_gran(cnt); }
 __host__ __device__ constexpr int arr_bytes(int cnt) { return (32 * row_pitch(cnt) + 15) / 16 * 16; }
-constexpr int kTabBytes = 32 * 8 + 32 * 4;   // per-warp table: row step offsets + row lengths
+constexpr int kTabBytes = 0;   // (rows are addressed arithmetically, see RowMap)
 
 IPOC_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int NKEEP>
 IPOC_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
 
-// Copy step (tab_t[r] + j) of every lane-row r of one input array into the stage: the warp
-// cooperates, `CPR` granules per row, consecutive lanes on consecutive granules of the same row.
+// Rows of a warp are affine in the lane index: row r starts at global step tb + r*S and has
+// clamp(rem - r*S, 0, T0) valid steps (mode A: S = T0, consecutive chunks of one sequence;
+// mode B: S = N, consecutive sequences).  No per-row table is needed.
+struct RowMap {
+    long long tb;    // global step index of row 0
+    long long rem;   // steps left from row 0's start to the end of what this warp may touch
+    int S, T0;
+    IPOC_DEV int len(int r) const {
+        const long long v = rem - (long long)r * S;
+        return (int)(v <= 0 ? 0 : (v < T0 ? v : T0));
+    }
+};
+
+// Copy step j of every lane-row r of one input array into the stage: the warp cooperates, `CPR`
+// granules per row, consecutive lanes on consecutive granules of the same row.
 template <int CNT>
-IPOC_DEV void issue_rows(char* dst_arr, const double* __restrict__ g, const long long* tab_t, const int* tab_len,
-                         int j, int lane) {
+IPOC_DEV void issue_rows(unsigned dst_arr, const double* __restrict__ g, const RowMap& m, int j, int lane) {
     constexpr int G = row_gran(CNT), CPR = row_cpr(CNT), PITCH = row_pitch(CNT);
 #pragma unroll
     for (int i = 0; i < CPR; ++i) {
         const int idx = lane + 32 * i;
         const int r = idx / CPR, part = idx % CPR;
-        if (j < tab_len[r]) {
-            const char* src = reinterpret_cast<const char*>(g) + ((tab_t[r] + j) * CNT) * 8 + part * G;
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(dst_arr + r * PITCH + part * G);
+        if ((long long)j < m.rem - (long long)r * m.S) {   // j < T0 always holds
+            const char* src = reinterpret_cast<const char*>(g) + ((m.tb + (long long)r * m.S + j) * CNT) * 8 + part * G;
+            const unsigned dst = dst_arr + r * PITCH + part * G;
             if constexpr (G == 16)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
             else
@@ -401,62 +418,76 @@ IPOC_DEV void read_row(double* dst, const char* src_arr, int lane) {
     }
 }
 
-// Per-warp shared memory: [table | stage 0 | stage 1]
+// Per-warp shared memory: [stage 0 | stage 1] (+ scan scratch overlaid after the walk)
 struct WarpSmem {
-    long long* tab_t;
-    int* tab_len;
+    RowMap map;
     char* stage0;
+    unsigned stage0_s;   // the same address in the shared window (computed once, not per copy)
 };
-IPOC_DEV WarpSmem warp_smem(char* smem, int per_warp_bytes, int warp_in_block, const Lane& L, int lane) {
-    char* base = smem + (size_t)warp_in_block * per_warp_bytes;
+IPOC_DEV WarpSmem warp_smem(char* smem, const Geom& g, int warp_in_block, long long wg) {
     WarpSmem w;
-    w.tab_t = reinterpret_cast<long long*>(base);
-    w.tab_len = reinterpret_cast<int*>(base + 32 * 8);
-    w.stage0 = base + kTabBytes;
-    w.tab_t[lane] = L.t0;
-    w.tab_len[lane] = L.len;
-    __syncwarp();
+    w.stage0 = smem + (size_t)warp_in_block * g.pw_bytes;
+    w.stage0_s = (unsigned)__cvta_generic_to_shared(w.stage0);
+    if (g.per_lane) {
+        w.map.tb = wg * 32 * (long long)g.N;
+        w.map.rem = ((long long)g.batch - wg * 32) * g.N;
+        w.map.S = g.N;
+        w.map.T0 = g.N;
+    } else {
+        const long long b = wg / g.nW, wi = wg % g.nW;
+        w.map.tb = b * g.N + wi * 32 * g.T0;
+        w.map.rem = (long long)g.N - wi * 32 * g.T0;
+        w.map.S = g.T0;
+        w.map.T0 = g.T0;
+    }
     return w;
 }
 
-// Double-buffered walk over the T steps of a chunk (uniform trip count; lanes with shorter chunks
-// idle).  body(j, stage) runs for the lane's valid steps with its row available in `stage`.
-template <class Ld, class F>
-IPOC_DEV void staged_walk(const Ld& ld, const WarpSmem& w, int T, int len, int lane, bool reverse, F&& body) {
-    int cur = 0;
-    ld.issue(w.stage0, w.tab_t, w.tab_len, reverse ? T - 1 : 0, lane);
+// Walk over the T steps of a chunk (uniform trip count; lanes with shorter chunks idle) with ONE
+// shared stage per warp: fetch(stage) copies the lane's row into registers, after which the stage
+// is free again, so the copies of the NEXT step are issued before compute(j) runs and have the
+// whole compute time to land.  (A second stage would buy no extra overlap and halve the number of
+// resident warps the shared memory allows.)
+template <class Ld, class F1, class F2>
+IPOC_DEV void staged_walk(const Ld& ld, const WarpSmem& w, int T, int len, int lane, bool reverse, F1&& fetch,
+                          F2&& compute) {
+    ld.issue(w.stage0_s, w.map, reverse ? T - 1 : 0, lane);
     cp_async_commit();
     for (int it = 0; it < T; ++it) {
         const int j = reverse ? T - 1 - it : it;
-        if (it + 1 < T)
-            ld.issue(w.stage0 + (cur ^ 1) * Ld::STAGE_BYTES, w.tab_t, w.tab_len, reverse ? j - 1 : j + 1, lane);
+        cp_async_wait<0>();
+        __syncwarp();
+        if (j < len) fetch(w.stage0);
+        __syncwarp();
+        if (it + 1 < T) ld.issue(w.stage0_s, w.map, reverse ? j - 1 : j + 1, lane);
         cp_async_commit();
-        cp_async_wait<1>();
-        __syncwarp();
-        if (j < len) body(j, w.stage0 + cur * Ld::STAGE_BYTES);
-        __syncwarp();
-        cur ^= 1;
+        if (j < len) compute(j);
     }
 }
 
 // ------------------------------------------------------------------ K2 loaders
-// Newton mode: builds the LQT terms of `noc_to_lqt` (ref noc/par_interior_point_newton.py:50-84)
-// on the fly: U = R + reg I (:118); X^-1 M (:63); s = -(U - M'X^-1M)^-1 ru (:64); r = -X^-1 M s
-// (:65); then the tracking references are folded back into linear cost terms
-// q = -(X r + M s), p = -(U s + M' r)   (H = Z = I, c = 0, :72-80).
-template <int NX, int NU>
+// Newton mode: the LQT terms of `noc_to_lqt` (ref noc/par_interior_point_newton.py:50-84) on the fly.
+// LITERAL = true follows the reference operation by operation: U = R + reg I (:118); X^-1 M (:63);
+//   s = -(U - M'X^-1M)^-1 ru (:64); r = -X^-1 M s (:65); then the tracking references are folded
+//   back into linear cost terms q = -(X r + M s), p = -(U s + M' r)   (H = Z = I, c = 0, :72-80).
+// LITERAL = false (default) uses what those lines evaluate to in exact arithmetic, q = 0 and
+//   p = ru (the identities -X r - M s = 0, -U s - M'r = ru of :62-66), skipping the nx x nx solve
+//   per step; it differs from the literal path by rounding of order eps * cond(Q) only and does
+//   not break down for singular Q.  Both are tested against the oracle; ipoc_set_literal_lqt(1)
+//   selects the literal one at run time.
+template <int NX, int NU, bool LITERAL = false>
 struct NewtonLoader {
     const double *fx, *fu, *ru, *Q, *R, *M, *reg;
     static constexpr int O_FX = 0, O_FU = O_FX + arr_bytes(NX * NX), O_Q = O_FU + arr_bytes(NX * NU),
                          O_R = O_Q + arr_bytes(NX * NX), O_M = O_R + arr_bytes(NU * NU),
                          O_RU = O_M + arr_bytes(NX * NU), STAGE_BYTES = O_RU + arr_bytes(NU);
-    IPOC_DEV void issue(char* st, const long long* tt, const int* tl, int j, int lane) const {
-        issue_rows<NX * NX>(st + O_FX, fx, tt, tl, j, lane);
-        issue_rows<NX * NU>(st + O_FU, fu, tt, tl, j, lane);
-        issue_rows<NX * NX>(st + O_Q, Q, tt, tl, j, lane);
-        issue_rows<NU * NU>(st + O_R, R, tt, tl, j, lane);
-        issue_rows<NX * NU>(st + O_M, M, tt, tl, j, lane);
-        issue_rows<NU>(st + O_RU, ru, tt, tl, j, lane);
+    IPOC_DEV void issue(unsigned st, const RowMap& m, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_FX, fx, m, j, lane);
+        issue_rows<NX * NU>(st + O_FU, fu, m, j, lane);
+        issue_rows<NX * NX>(st + O_Q, Q, m, j, lane);
+        issue_rows<NU * NU>(st + O_R, R, m, j, lane);
+        issue_rows<NX * NU>(st + O_M, M, m, j, lane);
+        issue_rows<NU>(st + O_RU, ru, m, j, lane);
     }
     IPOC_DEV void read(StepLQ<NX, NU>& s, const char* st, int lane, int b) const {
         double Qf[NX][NX], Rf[NU][NU], ruv[NU];
@@ -471,6 +502,18 @@ struct NewtonLoader {
         for (int a = 0; a < NU; ++a)
 #pragma unroll
             for (int c = 0; c < NU; ++c) s.U[a][c] = Rf[a][c] + ((a == c) ? rg : 0.0);
+        if constexpr (!LITERAL) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                s.q[i] = 0.0;
+                s.c[i] = 0.0;
+#pragma unroll
+                for (int j = i; j < NX; ++j) s.X[Sym<NX>::at(i, j)] = 0.5 * (Qf[i][j] + Qf[j][i]);
+            }
+#pragma unroll
+            for (int a = 0; a < NU; ++a) s.p[a] = ruv[a];
+            return;
+        }
         // X^-1 M
         double W[NX][NX], XiM[NX][NU];
 #pragma unroll
@@ -533,15 +576,15 @@ struct LqtLoader {
     static constexpr int O_A = 0, O_B = O_A + arr_bytes(NX * NX), O_C = O_B + arr_bytes(NX * NU),
                          O_X = O_C + arr_bytes(NX), O_U = O_X + arr_bytes(NX * NX), O_M = O_U + arr_bytes(NU * NU),
                          O_Q = O_M + arr_bytes(NX * NU), O_P = O_Q + arr_bytes(NX), STAGE_BYTES = O_P + arr_bytes(NU);
-    IPOC_DEV void issue(char* st, const long long* tt, const int* tl, int j, int lane) const {
-        issue_rows<NX * NX>(st + O_A, A, tt, tl, j, lane);
-        issue_rows<NX * NU>(st + O_B, B, tt, tl, j, lane);
-        if (c != nullptr) issue_rows<NX>(st + O_C, c, tt, tl, j, lane);
-        issue_rows<NX * NX>(st + O_X, X, tt, tl, j, lane);
-        issue_rows<NU * NU>(st + O_U, U, tt, tl, j, lane);
-        issue_rows<NX * NU>(st + O_M, M, tt, tl, j, lane);
-        issue_rows<NX>(st + O_Q, q, tt, tl, j, lane);
-        issue_rows<NU>(st + O_P, p, tt, tl, j, lane);
+    IPOC_DEV void issue(unsigned st, const RowMap& m, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_A, A, m, j, lane);
+        issue_rows<NX * NU>(st + O_B, B, m, j, lane);
+        if (c != nullptr) issue_rows<NX>(st + O_C, c, m, j, lane);
+        issue_rows<NX * NX>(st + O_X, X, m, j, lane);
+        issue_rows<NU * NU>(st + O_U, U, m, j, lane);
+        issue_rows<NX * NU>(st + O_M, M, m, j, lane);
+        issue_rows<NX>(st + O_Q, q, m, j, lane);
+        issue_rows<NU>(st + O_P, p, m, j, lane);
     }
     IPOC_DEV void read(StepLQ<NX, NU>& s, const char* st, int lane, int) const {
         double Xf[NX][NX], Uf[NU][NU];
@@ -575,12 +618,12 @@ struct FwdLoader {
     const double *A, *B, *c, *Kx, *d;
     static constexpr int O_A = 0, O_B = O_A + arr_bytes(NX * NX), O_C = O_B + arr_bytes(NX * NU),
                          O_K = O_C + arr_bytes(NX), O_D = O_K + arr_bytes(NU * NX), STAGE_BYTES = O_D + arr_bytes(NU);
-    IPOC_DEV void issue(char* st, const long long* tt, const int* tl, int j, int lane) const {
-        issue_rows<NX * NX>(st + O_A, A, tt, tl, j, lane);
-        issue_rows<NX * NU>(st + O_B, B, tt, tl, j, lane);
-        if (c != nullptr) issue_rows<NX>(st + O_C, c, tt, tl, j, lane);
-        issue_rows<NU * NX>(st + O_K, Kx, tt, tl, j, lane);
-        issue_rows<NU>(st + O_D, d, tt, tl, j, lane);
+    IPOC_DEV void issue(unsigned st, const RowMap& m, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_A, A, m, j, lane);
+        issue_rows<NX * NU>(st + O_B, B, m, j, lane);
+        if (c != nullptr) issue_rows<NX>(st + O_C, c, m, j, lane);
+        issue_rows<NU * NX>(st + O_K, Kx, m, j, lane);
+        issue_rows<NU>(st + O_D, d, m, j, lane);
     }
 };
 
@@ -589,9 +632,9 @@ template <int NX>
 struct AffLoader {
     const double *F, *c;
     static constexpr int O_F = 0, O_C = O_F + arr_bytes(NX * NX), STAGE_BYTES = O_C + arr_bytes(NX);
-    IPOC_DEV void issue(char* st, const long long* tt, const int* tl, int j, int lane) const {
-        issue_rows<NX * NX>(st + O_F, F, tt, tl, j, lane);
-        issue_rows<NX>(st + O_C, c, tt, tl, j, lane);
+    IPOC_DEV void issue(unsigned st, const RowMap& m, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_F, F, m, j, lane);
+        issue_rows<NX>(st + O_C, c, m, j, lane);
     }
     IPOC_DEV void read(AffElem<NX>& e, const char* st, int lane, int transpose) const {
         double Fm[NX][NX], cv[NX];
@@ -635,7 +678,7 @@ __global__ void k_ric_seed(const double* __restrict__ ST, size_t st_stride,
 //   incl  [slot]               : in-warp inclusive aggregate of every lane          (SoA, stride istride)
 //   agg1  [b*nW + (nW-1-wi)]   : warp totals in scan order (end of horizon first)   (SoA, stride a1stride)
 template <int NX, int NU, class Loader>
-__global__ void __launch_bounds__(kLeafThreads)
+__global__ void __launch_bounds__(kLeafThreads, IPOC_RIC_MINB)
 k_ric_leaf_up(Loader ld, Geom g, double* __restrict__ incl, size_t istride, double* __restrict__ agg1,
               size_t a1stride) {
     extern __shared__ __align__(16) char smem[];
@@ -643,16 +686,16 @@ k_ric_leaf_up(Loader ld, Geom g, double* __restrict__ incl, size_t istride, doub
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     if (wg >= total_warps(g)) return;
     const Lane L = lane_info(g, wg, lane);
-    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
+    const WarpSmem w = warp_smem(smem, g, wib, wg);
     RicElem<NX> a;
     RicOp<NX>::identity(a);
-    staged_walk(ld, w, g.T0, L.len, lane, true, [&](int, const char* st) {
-        StepLQ<NX, NU> s;
-        StepElem<NX, NU> e;
-        ld.read(s, st, lane, L.b);
-        make_step_elem(e, s);
-        ric_prepend_step(a, e);
-    });
+    StepLQ<NX, NU> s;
+    staged_walk(ld, w, g.T0, L.len, lane, true, [&](const char* st) { ld.read(s, st, lane, L.b); },
+                [&](int) {
+                    StepElem<NX, NU> e;
+                    make_step_elem(e, s);
+                    ric_prepend_step(a, e);
+                });
     warp_scan<RicOp<NX>>(a, reinterpret_cast<double*>(w.stage0), lane, true);
     soa_store(a, incl, istride, (size_t)L.slot);
     if (lane == 0) soa_store(a, agg1, a1stride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
@@ -663,7 +706,7 @@ k_ric_leaf_up(Loader ld, Geom g, double* __restrict__ incl, size_t istride, doub
 //   wvals [b*nW + (nW-1-wi)] : value function entering each warp (from the levels / the seed)
 //   mode B (per_lane): wvals = seed (stride batch), no neighbours, final pred/feasible written here.
 template <int NX, int NU, class Loader>
-__global__ void __launch_bounds__(kLeafThreads)
+__global__ void __launch_bounds__(kLeafThreads, IPOC_RIC_MINB)
 k_ric_leaf_down(Loader ld, Geom g, const double* __restrict__ incl, size_t istride,
                 const double* __restrict__ wvals, size_t wvstride,
                 double* __restrict__ Kx, double* __restrict__ d,
@@ -676,7 +719,7 @@ k_ric_leaf_down(Loader ld, Geom g, const double* __restrict__ incl, size_t istri
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     if (wg >= total_warps(g)) return;
     const Lane L = lane_info(g, wg, lane);
-    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
+    const WarpSmem w = warp_smem(smem, g, wib, wg);
     const int N = g.N;
     RicVal<NX> val;
     if (g.per_lane) {
@@ -704,10 +747,9 @@ k_ric_leaf_down(Loader ld, Geom g, const double* __restrict__ incl, size_t istri
         }
     };
     if (S_out != nullptr && L.len > 0 && L.k0 + L.len == N) write_Sv(N);
-    staged_walk(ld, w, g.T0, L.len, lane, true, [&](int j, const char* st) {
-        StepLQ<NX, NU> s;
+    StepLQ<NX, NU> s;
+    staged_walk(ld, w, g.T0, L.len, lane, true, [&](const char* st) { ld.read(s, st, lane, L.b); }, [&](int j) {
         StepGain<NX, NU> gn;
-        ld.read(s, st, lane, L.b);
         ric_step_back(val, gn, s);
         const size_t t = (size_t)(L.t0 + j);
         st_vec<NU * NX>(Kx + t * NU * NX, &gn.Kx[0][0]);
@@ -784,7 +826,7 @@ k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, 
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     if (wg >= total_warps(g)) return;
     const Lane L = lane_info(g, wg, lane);
-    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
+    const WarpSmem w = warp_smem(smem, g, wib, wg);
     const int N = g.N;
     AffVal<NX> xv;
     if (g.per_lane) {
@@ -800,9 +842,10 @@ k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, 
     double x[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = xv.r[i];
-    staged_walk(ld, w, g.T0, L.len, lane, false, [&](int j, const char* st) {
-        double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU], cv[NX], u[NU], xn[NX];
-        read_fwd_step<NX, NU>(ld, st, lane, Am, Bm, Km, dv, cv);
+    double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU], cv[NX];
+    staged_walk(ld, w, g.T0, L.len, lane, false,
+                [&](const char* st) { read_fwd_step<NX, NU>(ld, st, lane, Am, Bm, Km, dv, cv); }, [&](int j) {
+        double u[NU], xn[NX];
 #pragma unroll
         for (int a = 0; a < NU; ++a) {
             double v = dv[a];
@@ -839,12 +882,12 @@ k_fwd_leaf_up(FwdLoader<NX, NU> ld, Geom g, double* __restrict__ fincl, size_t f
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     if (wg >= total_warps(g)) return;
     const Lane L = lane_info(g, wg, lane);
-    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
+    const WarpSmem w = warp_smem(smem, g, wib, wg);
     AffElem<NX> fa;
     AffOp<NX>::identity(fa);
-    staged_walk(ld, w, g.T0, L.len, lane, false, [&](int, const char* st) {
-        double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU], cv[NX];
-        read_fwd_step<NX, NU>(ld, st, lane, Am, Bm, Km, dv, cv);
+    double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU], cv[NX];
+    staged_walk(ld, w, g.T0, L.len, lane, false,
+                [&](const char* st) { read_fwd_step<NX, NU>(ld, st, lane, Am, Bm, Km, dv, cv); }, [&](int) {
         AffElem<NX> se;
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
@@ -877,14 +920,12 @@ k_aff_leaf_up(AffLoader<NX> ld, int reverse, int transpose, Geom g, double* __re
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     if (wg >= total_warps(g)) return;
     const Lane L = lane_info(g, wg, lane);
-    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
+    const WarpSmem w = warp_smem(smem, g, wib, wg);
     AffElem<NX> a;
     AffOp<NX>::identity(a);
-    staged_walk(ld, w, g.T0, L.len, lane, reverse != 0, [&](int, const char* st) {
-        AffElem<NX> se;
-        ld.read(se, st, lane, transpose);
-        AffOp<NX>::compose(a, a, se);
-    });
+    AffElem<NX> se;
+    staged_walk(ld, w, g.T0, L.len, lane, reverse != 0, [&](const char* st) { ld.read(se, st, lane, transpose); },
+                [&](int) { AffOp<NX>::compose(a, a, se); });
     warp_scan<AffOp<NX>>(a, reinterpret_cast<double*>(w.stage0), lane, reverse != 0);
     soa_store(a, incl, istride, (size_t)L.slot);
     if (reverse) {
@@ -903,7 +944,7 @@ k_aff_leaf_down(AffLoader<NX> ld, int reverse, int transpose, Geom g, const doub
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     if (wg >= total_warps(g)) return;
     const Lane L = lane_info(g, wg, lane);
-    const WarpSmem w = warp_smem(smem, g.pw_bytes, wib, L, lane);
+    const WarpSmem w = warp_smem(smem, g, wib, wg);
     const int N = g.N;
     AffVal<NX> x;
     if (g.per_lane) {
@@ -929,12 +970,12 @@ k_aff_leaf_down(AffLoader<NX> ld, int reverse, int transpose, Geom g, const doub
     } else {
         if (L.len > 0 && L.k0 == 0) st_vec<NX>(ob, x.r);
     }
-    staged_walk(ld, w, g.T0, L.len, lane, reverse != 0, [&](int j, const char* st) {
-        AffElem<NX> se;
-        ld.read(se, st, lane, transpose);
-        AffOp<NX>::apply(x, se, x);
-        st_vec<NX>(ob + (size_t)(L.k0 + j + (reverse ? 0 : 1)) * NX, x.r);
-    });
+    AffElem<NX> se;
+    staged_walk(ld, w, g.T0, L.len, lane, reverse != 0, [&](const char* st) { ld.read(se, st, lane, transpose); },
+                [&](int j) {
+                    AffOp<NX>::apply(x, se, x);
+                    st_vec<NX>(ob + (size_t)(L.k0 + j + (reverse ? 0 : 1)) * NX, x.r);
+                });
 }
 
 // AoS (batch, nx) -> SoA seed planes (stride batch); NULL source = zeros.
@@ -964,7 +1005,7 @@ struct Plan {
 };
 
 // force_scan: time-sharded mode always wants the segment total, hence at least one level.
-static Plan make_plan(int N, int batch, bool force_scan = false) {
+static Plan make_plan(int N, int batch, bool force_scan = false, int target_threads = kTargetThreads) {
     Plan p{};
     Geom& g = p.g;
     g.N = N;
@@ -974,10 +1015,10 @@ static Plan make_plan(int N, int batch, bool force_scan = false) {
     int T0 = g_tune.leaf_chunk;
     g.per_lane = 0;
     if (T0 <= 0) {
-        if (!force_scan && (long long)batch * 2 >= kTargetThreads) {
+        if (!force_scan && (long long)batch * 2 >= target_threads) {
             T0 = N;   // enough independent problems: one sequence per lane, single pass, no scan
         } else {
-            long long want = (kTargetThreads + batch - 1) / batch;   // chunks per sequence to fill the chip
+            long long want = (target_threads + batch - 1) / batch;   // chunks per sequence to fill the chip
             want = ((want + 31) / 32) * 32;                          // whole warps
             if (want < 32) want = 32;
             long long t = ((long long)N + want - 1) / want;
@@ -1075,7 +1116,7 @@ static LeafLaunch leaf_launch(const Plan& p, int stage_bytes, size_t scratch_byt
     // smallest CTA that still reaches the largest number of resident warps per SM under the
     // shared-memory limit (228 KB per SM, 1 KB reserved per CTA, at most 32 CTAs) — small CTAs
     // balance the single wave better.
-    size_t body = 2 * (size_t)stage_bytes;   // the scan scratch reuses the stage area after the walk
+    size_t body = (size_t)stage_bytes;   // one stage; the scan scratch reuses the area after the walk
     if (body < scratch_bytes) body = scratch_bytes;
     const size_t per_warp = (size_t)kTabBytes + body;
     const size_t sm_bytes = 228 * 1024;
@@ -1262,10 +1303,15 @@ static int newton_step_impl(int N, int batch, const double* fx, const double* fu
     k_ric_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(Q, (size_t)N * NX * NX, nullptr, batch, w.ric.seed,
                                                         w.aff.seed);
     IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
-    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg};
     // the pred / feasibility partials are folded by K3's top scan when there is one
     const bool defer = p.nlev > 0;
-    if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer)) return rc;
+    if (g_literal_lqt) {
+        NewtonLoader<NX, NU, true> ld{fx, fu, ru, Q, R, M, reg};
+        if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer)) return rc;
+    } else {
+        NewtonLoader<NX, NU, false> ld{fx, fu, ru, Q, R, M, reg};
+        if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer)) return rc;
+    }
     PredJob pj{nullptr, nullptr, 0, nullptr, nullptr};
     if (defer) pj = PredJob{w.pred_part, w.feas_part, p.g.nW, pred, feasible};
     return run_fwd_down<NX, NU>(p, w, fx, fu, nullptr, Kx, d, dx, du, true, st, pj);
@@ -1353,7 +1399,7 @@ static int aff_down(const Plan& p, const ScanWs& w, const double* F, const doubl
 template <int NX>
 static int affine_scan_impl(int reverse, int transpose, int N, int batch, const double* F, const double* c,
                             const double* seed, double* out, void* ws, size_t ws_bytes, cudaStream_t st) {
-    const Plan p = make_plan(N, batch);
+    const Plan p = make_plan(N, batch, false, kAffTargetThreads);
     Bump bp{(char*)ws, 0, ws_bytes, false};
     ScanWs w;
     carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
@@ -1384,8 +1430,13 @@ static int newton_bwd_reduce_impl(int N, const double* fx, const double* fu, con
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
-    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg};
-    if (int rc = run_bwd_up<NX, NU>(p, w, ld, st)) return rc;
+    if (g_literal_lqt) {
+        NewtonLoader<NX, NU, true> ld{fx, fu, ru, Q, R, M, reg};
+        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st)) return rc;
+    } else {
+        NewtonLoader<NX, NU, false> ld{fx, fu, ru, Q, R, M, reg};
+        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st)) return rc;
+    }
     if (int rc = run_levels<RicOp<NX>>(p, w.ric, true, true, st)) return rc;
     k_soa_to_aos<<<1, 256, 0, st>>>(w.ric.total, 1, 0, RicElem<NX>::ESZ, carry_out);
     IPOC_LAUNCH_CHECK_N("k_soa_to_aos", st);
@@ -1429,8 +1480,13 @@ static int newton_bwd_apply_impl(int N, int rank, int nranks, const double* fx, 
     k_chain_seed<RicOp<NX>><<<1, 32, 0, st>>>(carries, nranks - 1, -1, nranks - 1 - rank, seed0, w.ric.seed);
     IPOC_LAUNCH_CHECK_N("k_chain_seed_ric", st);
     if (int rc = run_levels_down<RicOp<NX>>(p, w.ric, st)) return rc;
-    NewtonLoader<NX, NU> ld{fx, fu, ru, Q, R, M, reg};
-    if (int rc = run_bwd_down<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st)) return rc;
+    if (g_literal_lqt) {
+        NewtonLoader<NX, NU, true> ld{fx, fu, ru, Q, R, M, reg};
+        if (int rc = run_bwd_down<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st)) return rc;
+    } else {
+        NewtonLoader<NX, NU, false> ld{fx, fu, ru, Q, R, M, reg};
+        if (int rc = run_bwd_down<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st)) return rc;
+    }
     if (int rc = run_levels<AffOp<NX>>(p, w.aff, true, true, st)) return rc;
     k_soa_to_aos<<<1, 256, 0, st>>>(w.aff.total, 1, 0, AffElem<NX>::ESZ, fwd_carry_out);
     IPOC_LAUNCH_CHECK_N("k_soa_to_aos", st);
@@ -1491,7 +1547,8 @@ static int affine_apply_impl(int reverse, int transpose, int N, int rank, int nr
 
 template <int NX>
 static size_t ws_bytes_impl(int kind, int N, int batch, bool sharded) {
-    const Plan p = make_plan(N, sharded ? 1 : batch, sharded);
+    const Plan p = make_plan(N, sharded ? 1 : batch, sharded,
+                             (kind == IPOC_WS_AFFINE_SCAN && !sharded) ? kAffTargetThreads : kTargetThreads);
     Bump bp{nullptr, 0, 0, true};
     if (kind == IPOC_WS_AFFINE_SCAN) {
         ScanWs w;

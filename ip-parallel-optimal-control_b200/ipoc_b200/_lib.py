@@ -18,6 +18,7 @@ _SIGS = {
     "ipoc_supported": (_I, [_I, _I]),
     "ipoc_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "ipoc_set_tuning": (None, [_I, _I, _I]),
+    "ipoc_set_literal_lqt": (None, [_I]),
     "ipoc_launch_count": (ctypes.c_ulonglong, []),
     "ipoc_carry_doubles": (_I, [_I, _I]),
     "ipoc_newton_step_f64": (_I, [_I] * 4 + [_P] * 13 + [_P, _SZ, _P]),

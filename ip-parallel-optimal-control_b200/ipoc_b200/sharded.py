@@ -90,9 +90,10 @@ def dist_all_gather(group=None):
 
     def gather(t):
         P = dist.get_world_size(group)
-        out = torch.empty((P,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
-        return out
+        flat = t.contiguous().reshape(-1)
+        out = torch.empty(P * flat.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, flat, group=group)
+        return out.view((P,) + tuple(t.shape))
 
     return gather
 

@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Multi-GPU check of the time-sharded Newton step with real NCCL (run on the GPU box):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/dist_time_sharded.py [N] [nx]
+
+Every rank builds the same synthetic LQ data, takes its contiguous time segment, runs
+reduce -> all-gather -> seeded scan with torch.distributed (NCCL), and compares its slice with the
+single-device scan of the whole horizon computed locally.  Prints one OK line per rank + timings."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "ip-parallel-optimal-control_b200"), os.path.join(ROOT, "tests")]
+import numpy as np
+import torch
+import torch.distributed as dist
+from helpers import random_lq
+from ipoc_b200 import noc, sharded
+
+
+def main():
+    N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100003
+    nx = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rng = np.random.default_rng(5)
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, 1, dt=min(0.5, 10.0 / N))
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    full = [T(a) for a in (fx, fu, ru, Q, R, M)]
+    reg = torch.tensor([0.25], dtype=torch.float64, device=dev)
+    dx1, du1, Kx1, d1, pred1, feas1 = noc.newton_step(*full, reg)
+    lo, hi = sharded.segment_bounds(N, world)[rank]
+    seg = sharded.SegmentNewton(*(t[lo:hi] for t in full), rank, world)
+    gather = sharded.dist_all_gather()
+    ST = full[3][0].contiguous()
+    dx, du, pred, feas = sharded.newton_step_time_sharded(seg, reg, ST, gather)
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+    errs = (rel(dx, dx1[lo:hi + 1]), rel(du, du1[lo:hi]), rel(seg.Kx, Kx1[lo:hi]), rel(seg.d, d1[lo:hi]),
+            abs(float(pred) - float(pred1)) / abs(float(pred1)))
+    ok = max(errs) < 1e-10 and feas == bool(feas1[0])
+    # timing (max over ranks)
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+    ms_sharded = timed(lambda: sharded.newton_step_time_sharded(seg, reg, ST, gather))
+    ms_single = timed(lambda: noc.newton_step(*full, reg))
+    print(f"[rank {rank}/{world}] N={N} nx={nx} segment=[{lo},{hi}) max rel err {max(errs):.2e} "
+          f"{'OK' if ok else 'FAIL'}  time-sharded {ms_sharded:.3f} ms vs single-GPU {ms_single:.3f} ms", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,8 +30,10 @@ def N_(t):
 def _reset_tuning():
     from ipoc_b200 import _lib
     _lib.lib().ipoc_set_tuning(0, 0, 0)
+    _lib.lib().ipoc_set_literal_lqt(0)
     yield
     _lib.lib().ipoc_set_tuning(0, 0, 0)
+    _lib.lib().ipoc_set_literal_lqt(0)
 
 
 def oracle_newton(fx, fu, ru, Q, R, M, reg):
@@ -81,12 +83,15 @@ def test_newton_step_all_hierarchy_shapes(tuning, nx, nu, N):
     assert abs(float(pred) - predo) <= 1e-10 * abs(predo) and bool(feas[0]) == bool(feaso)
 
 
+@pytest.mark.parametrize("literal", [0, 1])
 @pytest.mark.parametrize("name", STEP_FIXTURES)
-def test_newton_step_vs_reference_fixtures(golden, name):
+def test_newton_step_vs_reference_fixtures(golden, name, literal):
     """Real pendulum / cartpole linearisations; expected values computed by the reference's own
-    sequential Newton step (ref noc/seq_interior_point_newton.py:42-90) run from its source."""
-    from ipoc_b200 import noc
+    sequential Newton step (ref noc/seq_interior_point_newton.py:42-90) run from its source.
+    Both `noc_to_lqt` variants of the kernel (closed form / literal) are held to the same bound."""
+    from ipoc_b200 import noc, _lib
     from ipoc_b200.optimal_control_problem import Derivatives
+    _lib.lib().ipoc_set_literal_lqt(literal)
     g = golden(name)
     d = Derivatives(*(T(g["d_" + f]) for f in Derivatives._fields))
     dx, du, pred, feas, ru = noc.par_Newton(T(g["states"]), d, float(g["reg_param"]), T(g["ref_ru"]), T(g["ref_Q"]),
@@ -179,7 +184,7 @@ def test_mpc_example_par_equals_seq():
     assert relerr(xs_par, np.array(xs_seq)) < 1e-10 and relerr(us_par, np.array(us_seq)) < 1e-10
 
 
-@pytest.mark.parametrize("nx,nu,N,B", [(2, 1, 100, 7), (4, 1, 64, 33), (2, 1, 1000, 40000)])
+@pytest.mark.parametrize("nx,nu,N,B", [(2, 1, 100, 7), (4, 1, 64, 33), (4, 1, 1000, 300), (2, 1, 1000, 40000)])
 def test_batched_equals_unbatched(nx, nu, N, B):
     """Independent OCPs stacked on a batch axis give each problem the result of solving it alone."""
     from ipoc_b200 import noc
@@ -272,6 +277,19 @@ def test_accept_update_matches_reference_rule():
         exp_s.append(int(ok))
     assert N_(succ).tolist() == exp_s
     assert np.allclose(N_(rp), exp_rp, rtol=1e-15) and np.allclose(N_(ri), exp_ri, rtol=0)
+
+
+@pytest.mark.parametrize("literal", [0, 1])
+@pytest.mark.parametrize("nx,nu,N", [(4, 1, 300), (2, 2, 77)])
+def test_literal_and_closed_form_lqt_agree(nx, nu, N, literal):
+    from ipoc_b200 import noc, _lib
+    rng = np.random.default_rng(N)
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu, coupling=1.0)
+    dxo, duo, Kxo, do, predo, feaso = oracle_newton(fx, fu, ru, Q, R, M, 0.2)
+    _lib.lib().ipoc_set_literal_lqt(literal)
+    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), T([0.2]))
+    assert relerr(N_(dx), dxo) < 1e-11 and relerr(N_(du), duo) < 1e-11
+    assert abs(float(pred) - predo) <= 1e-11 * abs(predo) and bool(feas[0]) == bool(feaso)
 
 
 @pytest.mark.parametrize("name", ["solve_pendulum_N20", "solve_linear_N40", "solve_cartpole_N40",
