@@ -271,6 +271,47 @@ def run_ours(args):
     value = world / (ms_step_all * 1e-3)
     e2e_value = world / (ms_e2e_all * 1e-3)
 
+    # ---- time-sharded mode (BASELINE config 4): one long horizon cut into `world` contiguous segments,
+    #      K2+K3 with two NCCL all-gathers of the segment carries per step; synthetic LQ data, same seed
+    #      on every rank.  Strong scaling; reported next to the single-GPU time of the same horizon.
+    time_sharded = []
+    if not args.no_sweep:
+        from ipoc_b200 import sharded, noc as _noc
+        for Ns in (1_000_000, 10_000_000):
+            try:
+                lo, hi = sharded.segment_bounds(Ns, world)[rank]
+                # every rank generates only what it needs: its own segment (seeded by segment) + Q[0]
+                fx_, fu_, ru_, Q_, R_, M_ = workloads.synthetic_lq(hi - lo, NX, NU, dev, seed=100 + rank)
+                ST = workloads.synthetic_lq(4, NX, NU, dev, seed=100)[3][0].contiguous()
+                regs = torch.tensor([0.25], dtype=torch.float64, device=dev)
+                if world > 1:
+                    seg = sharded.SegmentNewton(fx_, fu_, ru_, Q_, R_, M_, rank, world)
+                    gather = sharded.dist_all_gather()
+                    fn = lambda: sharded.newton_step_time_sharded(seg, regs, ST, gather)
+                else:
+                    fn = lambda: _noc.newton_step(fx_, fu_, ru_, Q_, R_, M_, regs)
+                for _ in range(3):
+                    fn()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 10
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                barrier()
+                ms_ts = allmax(e0.elapsed_time(e1) / reps)
+                ab_ = alg_bytes(Ns)
+                time_sharded.append({"N": Ns, "n_gpus": world, "ms_per_newton_step_K2K3": ms_ts,
+                                     "hbm_frac_of_aggregate_peak": (ab_["K2"] + ab_["K3"]) / (ms_ts * 1e-3) / 1e9
+                                     / (hbm_peak * world),
+                                     "collectives_per_step": 0 if world == 1 else 2,
+                                     "launch": "plain stream launches (no graph), max over ranks"})
+                del fx_, fu_, ru_, Q_, R_, M_
+                torch.cuda.empty_cache()
+            except Exception as e:
+                time_sharded.append({"N": Ns, "error": repr(e)[:200]})
+
     # ---- horizon sweep (single GPU): Newton-step time and HBM fraction at N = 1e5, 1e6
     sweep = []
     if rank == 0 and not args.no_sweep:
@@ -338,6 +379,7 @@ def run_ours(args):
             "phases_ms_per_step": {k: round(v, 5) for k, v in phases.items()},
             "ms_per_step_plain_launch": ms_plain, "ms_per_step_l2_warm": ms_warm,
             "sweep": sweep,
+            "time_sharded": time_sharded,
         }
         if cpu:
             line["cpu_baseline"] = cpu

@@ -78,3 +78,21 @@ def newton_inputs(problem, N, device, seed=1, bp=0.1, x0_noise=0.0, chunk=200000
     cost = ocp.total_cost(x, u, bp)
     return dict(ocp=ocp, d=d, fx=d.fx, fu=d.fu, cx=d.cx, cu=d.cu, lamT=lamT, lam=lam, ru=ru, Q=Q, R=R, M=M, x=x, u=u,
                 cons=cons, cost=cost, x0=x0, u0=u0, Ts=Ts)
+
+
+def synthetic_lq(N, nx, nu, device, seed=0, dt=None):
+    """Well-conditioned random time-varying LQ data (fx, fu, ru, Q, R, M) generated on the device —
+    for timing at horizons where the torch.func set-up would dominate (time-sharded sweeps)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    o = dict(dtype=torch.float64, device=device, generator=g)
+    dt = dt if dt is not None else min(0.5, 10.0 / N)
+    eye = lambda n: torch.eye(n, dtype=torch.float64, device=device)
+    fx = eye(nx) + dt * torch.randn(N, nx, nx, **o)
+    fu = dt * torch.randn(N, nx, nu, **o) + 0.5 * dt
+    Lq = 0.3 * torch.randn(N, nx, nx, **o)
+    Q = Lq @ Lq.transpose(1, 2) + eye(nx) * (0.5 + torch.rand(N, 1, 1, **o))
+    Lr = 0.3 * torch.randn(N, nu, nu, **o)
+    R = Lr @ Lr.transpose(1, 2) + eye(nu) * (0.5 + torch.rand(N, 1, 1, **o))
+    M = 0.06 * torch.randn(N, nx, nu, **o)
+    ru = torch.randn(N, nu, **o)
+    return fx.contiguous(), fu.contiguous(), ru.contiguous(), Q.contiguous(), R.contiguous(), M.contiguous()
