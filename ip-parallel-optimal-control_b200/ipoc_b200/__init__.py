@@ -6,7 +6,8 @@ Reference-facing names (same signatures as the reference, torch CUDA tensors for
     from ipoc_b200.paroc import LQT, par_bwd_pass, par_fwd_pass
 """
 from .optimal_control_problem import OCP, Derivatives, LinearizedOCP  # noqa: F401
-from .paroc import LQT, par_bwd_pass, par_fwd_pass  # noqa: F401
+from .paroc import LQT, par_bwd_pass, par_fwd_pass, seq_bwd_pass, seq_fwd_pass  # noqa: F401
+from .batched import par_interior_point_optimal_control_batched, newton_oc_batched  # noqa: F401
 from .noc import (compute_derivatives, compute_lqr_params, check_traj_feasibility, noc_to_lqt,  # noqa: F401
                   par_costates, par_Newton, newton_oc, par_interior_point_optimal_control,
                   newton_step, affine_scan, reductions, accept_update)

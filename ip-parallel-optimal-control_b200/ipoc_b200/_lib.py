@@ -121,3 +121,15 @@ def workspace(kind, N, nx, nu, batch, device):
 def require_supported(nx, nu):
     if not lib().ipoc_supported(nx, nu):
         raise IpocError(f"unsupported (nx={nx}, nu={nu}): no kernel instantiated and there is no CPU fallback")
+
+
+_tuning = (0, 0, 0)
+
+
+def set_tuning(leaf_chunk=0, mid_fanin=0, top_max=0):
+    """Scan-plan knobs of the library (0 = default); remembered so callers can restore them."""
+    global _tuning
+    prev = _tuning
+    lib().ipoc_set_tuning(int(leaf_chunk), int(mid_fanin), int(top_max))
+    _tuning = (int(leaf_chunk), int(mid_fanin), int(top_max))
+    return prev

@@ -1,0 +1,120 @@
+"""Batched independent OCPs (BASELINE config 5: MPC over many initial states).
+
+No reference counterpart as a script — the reference solves one OCP at a time — but the natural JAX
+spelling would be `jax.vmap(par_interior_point_optimal_control, in_axes=(None, 0, 0))`, under which
+every `lax.while_loop` runs until ALL members are done while finished members are frozen by
+`select`: per-member iterates and iteration counts equal those of solving each problem alone
+(SURVEY.md Appendix B).  This module reproduces exactly that: every OCP keeps its own regularisation
+`rp`, `r_inc`, attempt counter, Newton counter and done-masks; the kernels run on the whole batch
+(`batch` axis of the C ABI), the accept/update kernel only touches the active members.
+
+Multi-GPU: split the batch with `sharded.shard_batch(batch, rank, world)` and call this on the local
+slice — no data-path collective.
+"""
+import torch
+from torch.func import vmap, grad, hessian, jacrev
+from . import _lib as L
+from .optimal_control_problem import OCP, Derivatives
+from .noc import reductions, newton_step, accept_update, affine_scan
+
+
+def rollout_batched(dynamics, controls, initial_states):
+    """(B,N,nu),(B,nx) -> (B,N+1,nx): serial in time, vectorised over the batch (ref noc/utils.py:57-63)."""
+    step = vmap(dynamics)
+    x = initial_states
+    xs = [x]
+    with torch.no_grad():
+        for k in range(controls.shape[1]):
+            x = step(x, controls[:, k])
+            xs.append(x)
+    return torch.stack(xs, dim=1).contiguous()
+
+
+def compute_derivatives_batched(ocp: OCP, states, controls, bp) -> Derivatives:
+    """ref noc/par_interior_point_newton.py:13-28, vmapped over (batch, time)."""
+    def body(x, u):
+        cx_k, cu_k = grad(ocp.stage_cost, (0, 1))(x, u, bp)
+        cxx_k = hessian(ocp.stage_cost, 0)(x, u, bp)
+        cuu_k = hessian(ocp.stage_cost, 1)(x, u, bp)
+        cxu_k = jacrev(jacrev(ocp.stage_cost, 0), 1)(x, u, bp)
+        fx_k, fu_k = jacrev(ocp.dynamics, (0, 1))(x, u)
+        fxx_k = jacrev(jacrev(ocp.dynamics, 0), 0)(x, u)
+        fuu_k = jacrev(jacrev(ocp.dynamics, 1), 1)(x, u)
+        fxu_k = jacrev(jacrev(ocp.dynamics, 0), 1)(x, u)
+        return cx_k, cu_k, cxx_k, cuu_k, cxu_k, fx_k, fu_k, fxx_k, fuu_k, fxu_k
+
+    B, N = controls.shape[0], controls.shape[1]
+    flat = vmap(body)(states[:, :-1].reshape(B * N, -1), controls.reshape(B * N, -1))
+    return Derivatives(*(t.reshape((B, N) + tuple(t.shape[1:])).contiguous() for t in flat))
+
+
+def compute_lqr_params_batched(lam, d: Derivatives):
+    """ref noc/par_interior_point_newton.py:31-42 with a leading batch axis."""
+    l = lam[:, 1:]
+    ru = d.cu + torch.einsum("btou,bto->btu", d.fu, l)
+    Q = d.cxx + torch.einsum("bto,btoij->btij", l, d.fxx)
+    R = d.cuu + torch.einsum("bto,btoij->btij", l, d.fuu)
+    M = d.cxu + torch.einsum("bto,btoij->btij", l, d.fxu)
+    return ru.contiguous(), Q.contiguous(), R.contiguous(), M.contiguous()
+
+
+def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
+    """Per-member semantics of ref noc/par_interior_point_newton.py:127-225 for a batch.
+    -> (x (B,N+1,nx), u (B,N,nu), iterations (B,) int64)"""
+    dev = controls.device
+    u = L.dev_f64(controls)
+    x = rollout_batched(ocp.dynamics, u, initial_states.to(dev))                   # :133
+    B = u.shape[0]
+    o = dict(dtype=torch.float64, device=dev)
+    rp = torch.ones(B, **o)                                                        # :134
+    r_inc = torch.full((B,), 2.0, **o)                                             # :135
+    iters = torch.zeros(B, dtype=torch.int64, device=dev)
+    hu_norm = torch.ones(B, **o)
+    total_cost = vmap(ocp.total_cost, in_dims=(0, 0, None))
+    cons_fn = vmap(vmap(ocp.constraints))
+    lamT_fn = vmap(grad(ocp.final_cost))
+    active = torch.ones(B, dtype=torch.bool, device=dev)                           # members still in the Newton loop
+    while bool(active.any()):                                                      # :199-202 (per member)
+        cost = total_cost(x, u, barrier_param)                                     # :142
+        d = compute_derivatives_batched(ocp, x, u, barrier_param)                  # :145
+        lam = affine_scan(d.fx, d.cx, lamT_fn(x[:, -1]), reverse=True, transpose=True)   # :147
+        ru, Q, R, M = compute_lqr_params_batched(lam, d)                           # :149
+        hu, cu_norm, _ = reductions(ru=ru, cu=d.cu)                                # :158, :116
+        inner = torch.zeros(B, dtype=torch.int64, device=dev)
+        act_in = active.clone()                                                    # members still in the attempt loop
+        tx, tu = x.clone(), u.clone()
+        while bool(act_in.any()):                                                  # :177-182 (per member)
+            dx, du, _, _, pred, bwd_feas = newton_step(d.fx, d.fu, ru, Q, R, M, rp * cu_norm)   # :153
+            cx_try, cu_try = x + dx, u + du                                        # :156-157
+            cons = cons_fn(cx_try[:, :-1], cu_try)
+            _, _, traj_feas = reductions(cons=cons.reshape(B, cons.shape[1], -1))  # :160
+            new_cost = total_cost(cx_try, cu_try, barrier_param)                   # :161
+            succ, _ = accept_update(cost, new_cost.contiguous(), traj_feas, pred, bwd_feas, rp, r_inc,
+                                    active=act_in.to(torch.int32))                 # :159-173, active members only
+            m = act_in.view(B, 1, 1)
+            tx = torch.where(m, cx_try, tx)                                        # :175 (kept regardless of success)
+            tu = torch.where(m, cu_try, tu)
+            inner = inner + act_in.to(torch.int64)                                 # :174
+            act_in = act_in & ~((succ != 0) | (inner > 500))
+        m = active.view(B, 1, 1)
+        x = torch.where(m, tx, x)                                                  # :184
+        u = torch.where(m, tu, u)
+        hu_norm = torch.where(active, hu, hu_norm)
+        iters = iters + active.to(torch.int64)                                     # :194
+        active = active & ~((hu_norm < 1e-4) | (iters > 1000))
+    return x, u, iters
+
+
+def par_interior_point_optimal_control_batched(ocp: OCP, controls, initial_states):
+    """Batched `par_interior_point_optimal_control` (ref :228-254): controls (B,N,nu), initial_states (B,nx)
+    -> (opt_u (B,N,nu), N_iterations (B,) int64)."""
+    if not controls.is_cuda:
+        raise L.IpocError("the batched solver needs CUDA tensors; there is no CPU fallback")
+    u = controls
+    total = torch.zeros(controls.shape[0], dtype=torch.int64, device=controls.device)
+    bp = 0.1                                                                       # :233
+    while bp > 1e-4:                                                               # :243-245
+        _, u, its = newton_oc_batched(ocp, u, initial_states, bp)                  # :237
+        bp = bp / 5                                                                # :238
+        total = total + its                                                        # :239
+    return u, total

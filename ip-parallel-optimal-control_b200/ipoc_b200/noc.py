@@ -171,13 +171,20 @@ def par_Newton(nominal_states, d: Derivatives, reg_param, ru, Q, R, M):
 
 # ------------------------------------------------------------------ driver loops
 def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, barrier_param: float, trace=None,
-              stage: int = 0):
+              stage: int = 0, use_graphs: bool = True):
     """ref noc/par_interior_point_newton.py:127-225 -> (opt_x, opt_u, iterations).
     The scalar accept/reject state (rp, r_inc, success) lives on the device; the host reads one
-    small record per attempt to steer the Python loop."""
+    small record per attempt to steer the Python loop.  With use_graphs (default) the two loop bodies
+    are CUDA graphs captured once per problem (ipoc_b200/graphed.py); the eager path below is the same
+    sequence of statements."""
     dev = controls.device
     u = L.dev_f64(controls)
     x = rollout(ocp.dynamics, u, initial_state.to(dev))                 # :133
+    if use_graphs:
+        from . import graphed
+        g = graphed.get(ocp, u.shape[0], x.shape[1], u.shape[1], dev, x, u, barrier_param)
+        if g:
+            return _newton_oc_graphed(g, x, u, barrier_param, trace, stage)
     o = dict(dtype=torch.float64, device=dev)
     rp = torch.ones(1, **o)                                              # :134
     r_inc = torch.full((1,), 2.0, **o)                                   # :135
@@ -212,14 +219,40 @@ def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, bar
     return x, u, iteration
 
 
-def par_interior_point_optimal_control(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, trace=None):
+def _newton_oc_graphed(g, x, u, barrier_param, trace, stage):
+    """Same loop as above with the two bodies replayed from CUDA graphs."""
+    g.x.copy_(x)
+    g.u.copy_(u)
+    g.bp.fill_(float(barrier_param))
+    g.rp.fill_(1.0)                                                      # :134
+    g.r_inc.fill_(2.0)                                                   # :135
+    iteration, Hu_norm = 0, 1.0
+    while not (Hu_norm < 1e-4 or iteration > 1000):                      # :199-202
+        g.iteration()                                                    # :142-149
+        success, inner = False, 0
+        while not (success or inner > 500):                              # :177-182
+            rp_before = float(g.rp) if trace is not None else None
+            success, Hu_norm, new_cost, pred, gain = g.attempt()         # :153-173
+            inner += 1                                                   # :174
+            if trace is not None:
+                trace.append(dict(stage=stage, iteration=iteration, attempt=inner, cost=float(g.cost),
+                                  new_cost=new_cost, pred=pred, gain_ratio=gain, success=success,
+                                  rp=rp_before, Hu_norm=Hu_norm))
+        g.x.copy_(g.tx)                                                  # :184 (taken even if never successful)
+        g.u.copy_(g.tu)
+        iteration += 1                                                   # :194
+    return g.x.clone(), g.u.clone(), iteration
+
+
+def par_interior_point_optimal_control(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, trace=None,
+                                       use_graphs: bool = True):
     """ref noc/par_interior_point_newton.py:228-254 -> (opt_u, N_iterations)."""
     if not controls.is_cuda:
         raise L.IpocError("par_interior_point_optimal_control needs CUDA tensors; there is no CPU fallback")
     u = controls
     bp, total, stage = 0.1, 0, 0                                         # :233
     while bp > 1e-4:                                                     # :243-245
-        _, u, its = newton_oc(ocp, u, initial_state, bp, trace, stage)   # :237
+        _, u, its = newton_oc(ocp, u, initial_state, bp, trace, stage, use_graphs)   # :237
         bp = bp / 5                                                      # :238
         total += its                                                     # :239
         stage += 1

@@ -14,12 +14,29 @@ from .optimal_control_problem import OCP
 from .utils import wrap_angle, euler, discretize_dynamics
 
 
+_const_cache = {}
+
+
+def _const(kind, vals, like):
+    """Constant vectors / diagonal matrices, created once per (device, dtype): building them with
+    torch.tensor(...) inside the cost would issue a host-to-device copy per call (and cannot be
+    captured in a CUDA graph)."""
+    key = (kind, tuple(vals), like.dtype, like.device)
+    t = _const_cache.get(key)
+    if t is None:
+        t = torch.tensor(vals, dtype=like.dtype, device=like.device)
+        if kind == "diag":
+            t = torch.diag(t)
+        _const_cache[key] = t
+    return t
+
+
 def _diag(vals, like):
-    return torch.diag(torch.tensor(vals, dtype=like.dtype, device=like.device))
+    return _const("diag", vals, like)
 
 
 def _vec(vals, like):
-    return torch.tensor(vals, dtype=like.dtype, device=like.device)
+    return _const("vec", vals, like)
 
 
 # ------------------------------------------------------------------ pendulum (nx=2, nu=1, nc=2)
@@ -101,9 +118,8 @@ def cartpole_x0(dtype=torch.float64, device="cpu"):
 
 # ------------------------------------------------------------------ double integrator
 def _double_integrator_ode(state, control):
-    A = torch.tensor([[0.0, 1.0], [0.0, 0.0]], dtype=state.dtype, device=state.device)
-    B = torch.tensor([[0.0], [1.0]], dtype=state.dtype, device=state.device)
-    return A @ state + B @ control
+    # xdot = [[0,1],[0,0]] x + [[0],[1]] u   (ref examples/linear_demo_cuda.py:19-22)
+    return torch.hstack((state[1:2], control[0:1]))
 
 
 def make_linear_demo(step: float = 0.1, control_bound=None) -> OCP:

@@ -310,6 +310,47 @@ def test_full_solve_matches_reference(golden, name):
     u, its = noc.par_interior_point_optimal_control(ocp, T(g["u0"]), T(g["x0"]))
     assert its == int(g["refp_iterations"])
     assert relerr(N_(u), g["refp_opt_u"]) < 1e-9
+    if N <= 100:   # the eager (graph-free) driver is the same sequence of statements
+        u2, its2 = noc.par_interior_point_optimal_control(ocp, T(g["u0"]), T(g["x0"]), use_graphs=False)
+        assert its2 == its and relerr(N_(u2), N_(u)) < 1e-12
+
+
+def test_seq_twins_equal_par():
+    """`seq_bwd_pass` / `seq_fwd_pass` (serial comparators of the MPC example) vs the parallel scans."""
+    from ipoc_b200.paroc import LQT, par_bwd_pass, par_fwd_pass, seq_bwd_pass, seq_fwd_pass
+    rng = np.random.default_rng(8)
+    N, nx, nu = 333, 4, 1
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu)
+    lq = noc_np.noc_to_lqt(ru, Q, R, M, fx, fu)._replace(c=0.01 * rng.standard_normal((N, nx)))
+    lqt = LQT(*(T(a) for a in lq))
+    Kx, d, S, v, _, _ = par_bwd_pass(lqt)
+    Kx2, d2, S2, v2 = seq_bwd_pass(lqt)
+    x0 = T(rng.standard_normal(nx))
+    u, x = par_fwd_pass(lqt, x0, Kx, d)
+    u2, x2 = seq_fwd_pass(lqt, x0, Kx2, d2)
+    for a, b in ((Kx, Kx2), (d, d2), (S, S2), (v, v2), (u, u2), (x, x2)):
+        assert relerr(N_(a), N_(b)) < 1e-10
+    Kxo, do, So, vo = paroc_np.seq_bwd_pass(lq)
+    assert relerr(N_(Kx2), Kxo) < 1e-10 and relerr(N_(S2), So) < 1e-10
+
+
+@pytest.mark.parametrize("problem,N,B", [("pendulum", 30, 6), ("cartpole", 24, 5)])
+def test_batched_solver_equals_per_problem_solves(problem, N, B):
+    """Config 5 semantics: every member of a batched solve gets the iterate and the Newton iteration
+    count of solving it alone (vmap-of-while_loop semantics)."""
+    from ipoc_b200 import noc, problems, batched
+    rng = np.random.default_rng(3)
+    if problem == "pendulum":
+        ocp, x0 = problems.make_pendulum(1.0 / N), problems.pendulum_x0().numpy()
+    else:
+        ocp, x0 = problems.make_cartpole(1.0 / N), problems.cartpole_x0().numpy()
+    x0s = x0[None] + 0.1 * rng.standard_normal((B, x0.shape[0]))
+    u0s = 0.1 * rng.standard_normal((B, N, 1))
+    ub, itb = batched.par_interior_point_optimal_control_batched(ocp, T(u0s), T(x0s))
+    for b in range(B):
+        u1, it1 = noc.par_interior_point_optimal_control(ocp, T(u0s[b]), T(x0s[b]))
+        assert int(itb[b]) == it1
+        assert relerr(N_(ub[b]), N_(u1)) < 1e-8
 
 
 def test_cpu_tensors_are_rejected():
