@@ -343,6 +343,47 @@ def run_ours(args):
             except Exception as e:   # the sweep must never take the headline line down
                 sweep.append({"N": Ns, "error": repr(e)[:200]})
 
+    # ---- full solves through the reference-facing API (BASELINE metric "IP-Newton solve ms vs horizon N"):
+    #      reference protocol (ref examples/cartpole_runtime.py:119-146): 1 warm-up (graph capture ~ jit), then
+    #      timed calls; rollout + derivatives (host framework) + all five barrier stages included.
+    solves, batched_solves = [], None
+    if rank == 0 and world == 1 and not args.no_solve:
+        from ipoc_b200 import noc as _noc2, problems as _pb, batched as _bt
+        for Ns in (1000, 10_000):
+            try:
+                ocp_ = _pb.make_cartpole(1.0 / Ns)
+                x0_ = _pb.cartpole_x0(device=dev)
+                u0_ = torch.as_tensor(0.1 * np.random.default_rng(1).standard_normal((Ns, 1)), device=dev)
+                _noc2.par_interior_point_optimal_control(ocp_, u0_, x0_)
+                torch.cuda.synchronize(dev)
+                ts_ = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    tr_ = []
+                    u_, it_ = _noc2.par_interior_point_optimal_control(ocp_, u0_, x0_)
+                    torch.cuda.synchronize(dev)
+                    ts_.append(time.perf_counter() - t0)
+                solves.append({"problem": "cartpole", "N": Ns, "solve_ms_mean": float(np.mean(ts_)) * 1e3,
+                               "solve_ms_median": float(np.median(ts_)) * 1e3, "newton_iterations": int(it_),
+                               "max_abs_u": float(u_.abs().max())})
+            except Exception as e:
+                solves.append({"N": Ns, "error": repr(e)[:200]})
+        try:   # BASELINE config 5 (reduced batch so that the default run stays short): batched solves/s
+            Bb, Nb = 512, 1000
+            ocp_ = _pb.make_pendulum(1.0 / Nb)
+            rng_ = np.random.default_rng(1)
+            x0s_ = _pb.pendulum_x0(device=dev)[None] + torch.as_tensor(0.1 * rng_.standard_normal((Bb, 2)), device=dev)
+            u0s_ = torch.as_tensor(0.1 * rng_.standard_normal((Bb, Nb, 1)), device=dev)
+            t0 = time.perf_counter()
+            ub_, itb_ = _bt.par_interior_point_optimal_control_batched(ocp_, u0s_, x0s_)
+            torch.cuda.synchronize(dev)
+            dtb = time.perf_counter() - t0
+            batched_solves = {"problem": "pendulum", "N": Nb, "batch": Bb, "solves_per_s": Bb / dtb,
+                              "seconds": dtb, "iterations_mean": float(itb_.double().mean()),
+                              "note": "eager host-framework autodiff dominates; no warm-up excluded"}
+        except Exception as e:
+            batched_solves = {"error": repr(e)[:200]}
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload with the oracle port
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -380,6 +421,8 @@ def run_ours(args):
             "ms_per_step_plain_launch": ms_plain, "ms_per_step_l2_warm": ms_warm,
             "sweep": sweep,
             "time_sharded": time_sharded,
+            "solves": solves,
+            "batched_solves": batched_solves,
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -410,6 +453,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-solve", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

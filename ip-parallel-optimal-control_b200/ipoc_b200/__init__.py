@@ -11,7 +11,7 @@ from .batched import par_interior_point_optimal_control_batched, newton_oc_batch
 from .noc import (compute_derivatives, compute_lqr_params, check_traj_feasibility, noc_to_lqt,  # noqa: F401
                   par_costates, par_Newton, newton_oc, par_interior_point_optimal_control,
                   newton_step, affine_scan, reductions, accept_update)
-from .utils import wrap_angle, euler, discretize_dynamics, rollout, runge_kutta  # noqa: F401
+from .utils import wrap_angle, euler, discretize_dynamics, rollout, rollout_parallel, runge_kutta  # noqa: F401
 from . import problems  # noqa: F401
 
 __version__ = "0.1.0"

@@ -15,7 +15,7 @@ from torch.func import vmap, grad, hessian, jacrev
 from . import _lib as L
 from .optimal_control_problem import OCP, Derivatives
 from .paroc import LQT, par_bwd_pass, par_fwd_pass  # noqa: F401  (re-exported, as the reference imports them)
-from .utils import rollout
+from .utils import rollout, rollout_parallel
 
 
 # ------------------------------------------------------------------ A1: derivatives (host framework)
@@ -171,7 +171,7 @@ def par_Newton(nominal_states, d: Derivatives, reg_param, ru, Q, R, M):
 
 # ------------------------------------------------------------------ driver loops
 def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, barrier_param: float, trace=None,
-              stage: int = 0, use_graphs: bool = True):
+              stage: int = 0, use_graphs: bool = True, parallel_rollout_from: int = 2000):
     """ref noc/par_interior_point_newton.py:127-225 -> (opt_x, opt_u, iterations).
     The scalar accept/reject state (rp, r_inc, success) lives on the device; the host reads one
     small record per attempt to steer the Python loop.  With use_graphs (default) the two loop bodies
@@ -179,7 +179,12 @@ def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, bar
     sequence of statements."""
     dev = controls.device
     u = L.dev_f64(controls)
-    x = rollout(ocp.dynamics, u, initial_state.to(dev))                 # :133
+    if u.shape[0] >= parallel_rollout_from:
+        # same states as the serial rollout (its fixed point), computed with the forward scan kernel;
+        # the serial Python loop would dominate the solve time at long horizons
+        x, _ = rollout_parallel(ocp.dynamics, u, initial_state.to(dev))
+    else:
+        x = rollout(ocp.dynamics, u, initial_state.to(dev))             # :133
     if use_graphs:
         from . import graphed
         g = graphed.get(ocp, u.shape[0], x.shape[1], u.shape[1], dev, x, u, barrier_param)

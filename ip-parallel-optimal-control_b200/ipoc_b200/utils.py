@@ -47,3 +47,41 @@ def rollout(dynamics, controls, initial_state):
             x = dynamics(x, us[k])
             xs.append(x)
     return torch.stack(xs).to(dev)
+
+
+def rollout_parallel(dynamics, controls, initial_state, x_guess=None, tol=1e-14, max_iter=200):
+    """Parallel-in-time nonlinear rollout (SURVEY.md §8f "next" #2; no reference counterpart — the
+    reference's `rollout` is a serial `lax.scan`, ref noc/utils.py:57-63).
+
+    Newton iteration on the rollout equations x_{k+1} = f(x_k, u_k): linearise along the current guess,
+    F_k = df/dx(x_k, u_k), c_k = f(x_k, u_k) - F_k x_k, and solve the resulting affine recursion for all
+    k at once with the forward affine scan kernel (ipoc_affine_scan_f64).  Every iteration fixes at
+    least one more leading state exactly, convergence is quadratic in practice (a handful of
+    iterations for the example plants), and the fixed point IS the serial rollout (same f evaluated at
+    the same states, up to rounding).  Returns (states (N+1,nx), iterations); falls back to the serial
+    rollout if it has not converged after max_iter iterations."""
+    from torch.func import vmap, jacrev
+    from .noc import affine_scan
+    dev = controls.device
+    N = controls.shape[0]
+    x0 = initial_state.to(dev)
+    X = x_guess if x_guess is not None else x0.unsqueeze(0).expand(N + 1, -1).contiguous()
+    X = X.clone()
+    X[0] = x0
+    f = vmap(dynamics)
+    fx = vmap(jacrev(dynamics, 0))
+    with torch.no_grad():
+        for it in range(1, max_iter + 1):
+            fv = f(X[:-1], controls)
+            F = fx(X[:-1], controls).contiguous()
+            c = (fv - (F @ X[:-1].unsqueeze(-1)).squeeze(-1)).contiguous()
+            Xn = affine_scan(F, c, x0, reverse=False, transpose=False)
+            err = float((Xn - X).abs().max())
+            scale = 1.0 + float(Xn.abs().max())
+            X = Xn
+            if not (err == err):   # NaN: diverged
+                break
+            if err <= tol * scale:
+                X = torch.cat((x0.unsqueeze(0), f(X[:-1], controls)))   # states are exactly f of their predecessor
+                return X.contiguous(), it
+    return rollout(dynamics, controls, initial_state), -1

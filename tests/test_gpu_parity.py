@@ -353,6 +353,20 @@ def test_batched_solver_equals_per_problem_solves(problem, N, B):
         assert relerr(N_(ub[b]), N_(u1)) < 1e-8
 
 
+@pytest.mark.parametrize("problem,N", [("cartpole", 3000), ("pendulum", 2500)])
+def test_parallel_rollout_equals_serial(problem, N):
+    """Newton-on-the-rollout with the forward affine scan reproduces the serial rollout."""
+    from ipoc_b200 import problems, utils
+    rng = np.random.default_rng(N)
+    ocp = problems.make_cartpole(1.0 / N) if problem == "cartpole" else problems.make_pendulum(1.0 / N)
+    x0 = (problems.cartpole_x0 if problem == "cartpole" else problems.pendulum_x0)(device=DEV)
+    u = T(2.0 * rng.standard_normal((N, 1)))
+    xs = utils.rollout(ocp.dynamics, u, x0)
+    xp, its = utils.rollout_parallel(ocp.dynamics, u, x0)
+    assert 0 < its < 50
+    assert relerr(N_(xp), N_(xs)) < 1e-11
+
+
 def test_cpu_tensors_are_rejected():
     from ipoc_b200 import noc, _lib
     rng = np.random.default_rng(0)
