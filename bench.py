@@ -51,7 +51,7 @@ PHASE_OF = {
     "k_ric_seed": "K2", "k_ric_leaf_up": "K2", "k_mid_up_ric": "K2", "k_top_ric": "K2", "k_mid_down_ric": "K2",
     "k_ric_leaf_down": "K2", "k_finalize_pred": "K2",
     "k_fwd_leaf_down": "K3", "k_fwd_leaf_up": "K3",
-    "k_reduce_partial": "K4", "k_reduce_final": "K4", "ipoc_reductions_f64": "K4", "ipoc_accept_update_f64": "K4",
+    "k_reduce_partial": "K4", "k_reduce_final": "K4", "k_reduce_single": "K4", "ipoc_reductions_f64": "K4", "ipoc_accept_update_f64": "K4",
 }
 
 

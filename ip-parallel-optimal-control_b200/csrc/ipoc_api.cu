@@ -150,7 +150,54 @@ k_reduce_final(const double* __restrict__ partials, int nblk, int has_ru, int ha
     }
 }
 
+// one CTA per problem, slice = everything, finalisation in the same launch (N*width <= 4096)
+static __global__ void __launch_bounds__(kRedThreads)
+k_reduce_single(const double* __restrict__ ru, const double* __restrict__ cu, const double* __restrict__ cons,
+                int N, int nu, int nc, double* __restrict__ hu_norm, double* __restrict__ cu_norm,
+                int32_t* __restrict__ traj_feasible, const double* __restrict__ rp, double* __restrict__ reg) {
+    __shared__ double s_max[kRedThreads];
+    __shared__ double s_sq[kRedThreads];
+    __shared__ int s_ok[kRedThreads];
+    const int b = blockIdx.x, t = threadIdx.x;
+    double mx = 0.0, sq = 0.0;
+    int ok = 1;
+    if (ru != nullptr) {
+        const double* p = ru + (size_t)b * N * nu;
+        for (int i = t; i < N * nu; i += kRedThreads) mx = nan_max(mx, fabs(p[i]));
+    }
+    if (cu != nullptr) {
+        const double* p = cu + (size_t)b * N * nu;
+        for (int i = t; i < N * nu; i += kRedThreads) sq += p[i] * p[i];
+    }
+    if (cons != nullptr) {
+        const double* p = cons + (size_t)b * N * nc;
+        for (int i = t; i < N * nc; i += kRedThreads) ok &= (p[i] <= 0.0) ? 1 : 0;
+    }
+    s_max[t] = mx;
+    s_sq[t] = sq;
+    s_ok[t] = ok;
+    __syncthreads();
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+        if (t < o) {
+            s_max[t] = nan_max(s_max[t], s_max[t + o]);
+            s_sq[t] += s_sq[t + o];
+            s_ok[t] &= s_ok[t + o];
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        if (ru != nullptr) hu_norm[b] = s_max[0];
+        if (cu != nullptr) {
+            const double nrm = sqrt(s_sq[0]);
+            cu_norm[b] = nrm;
+            if (rp != nullptr && reg != nullptr) reg[b] = rp[b] * nrm;   // ref :117
+        }
+        if (cons != nullptr) traj_feasible[b] = s_ok[0];
+    }
+}
+
 static int reduce_blocks(int N, int width, int batch) {
+    if ((long long)N * width <= 4096) return 1;
     long long per_problem = ((long long)N * width + 8191) / 8192;   // >= 8192 entries per block
     long long cap = (148LL * 8 + batch - 1) / batch;                // fill the chip, not more
     long long n = per_problem < cap ? per_problem : cap;
@@ -306,6 +353,12 @@ int ipoc_reductions_f64(int N, int nu, int nc, int batch, const double* ru, cons
     if (ws_bytes < (size_t)batch * nblk * 3 * sizeof(double)) return IPOC_EWORKSPACE;
     cudaStream_t st_ = (cudaStream_t)stream;
     double* partials = (double*)ws;
+    if (nblk == 1) {   // small problem: one launch does slice reduction and finalisation
+        k_reduce_single<<<batch, kRedThreads, 0, st_>>>(ru, cu, cons, N, nu, nc, hu_norm, cu_norm, traj_feasible, rp,
+                                                       reg);
+        IPOC_API_LAUNCH_CHECK(st_);
+        return IPOC_OK;
+    }
     k_reduce_partial<<<(unsigned)((long long)nblk * batch), kRedThreads, 0, st_>>>(ru, cu, cons, N, nu, nc, nblk, partials);
     IPOC_API_LAUNCH_CHECK(st_);
     k_reduce_final<<<batch, kRedThreads, 0, st_>>>(partials, nblk, ru != nullptr, cu != nullptr, cons != nullptr,

@@ -370,30 +370,28 @@ IPOC_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "m
 template <int NKEEP>
 IPOC_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
 
-// Rows of a warp are affine in the lane index: row r starts at global step tb + r*S and has
-// clamp(rem - r*S, 0, T0) valid steps (mode A: S = T0, consecutive chunks of one sequence;
-// mode B: S = N, consecutive sequences).  No per-row table is needed.
+// Rows of a warp are affine in the lane index: row r starts at global step tb + r*S (mode A: S = T0,
+// consecutive chunks of one sequence; mode B: S = N, consecutive sequences).  No per-row table.
 struct RowMap {
     long long tb;    // global step index of row 0
-    long long rem;   // steps left from row 0's start to the end of what this warp may touch
+    int remc;        // min(steps left from row 0's start, 32*S): row r, step j is valid iff r*S + j < remc
     int S, T0;
-    IPOC_DEV int len(int r) const {
-        const long long v = rem - (long long)r * S;
-        return (int)(v <= 0 ? 0 : (v < T0 ? v : T0));
-    }
 };
 
 // Copy step j of every lane-row r of one input array into the stage: the warp cooperates, `CPR`
-// granules per row, consecutive lanes on consecutive granules of the same row.
+// granules per row, consecutive lanes on consecutive granules of the same row.  32-bit index
+// arithmetic relative to the warp's first row, one wide multiply-add per copy.
 template <int CNT>
 IPOC_DEV void issue_rows(unsigned dst_arr, const double* __restrict__ g, const RowMap& m, int j, int lane) {
     constexpr int G = row_gran(CNT), CPR = row_cpr(CNT), PITCH = row_pitch(CNT);
+    const char* gbase = reinterpret_cast<const char*>(g + m.tb * CNT);
 #pragma unroll
     for (int i = 0; i < CPR; ++i) {
         const int idx = lane + 32 * i;
         const int r = idx / CPR, part = idx % CPR;
-        if ((long long)j < m.rem - (long long)r * m.S) {   // j < T0 always holds
-            const char* src = reinterpret_cast<const char*>(g) + ((m.tb + (long long)r * m.S + j) * CNT) * 8 + part * G;
+        const int k = r * m.S + j;
+        if (k < m.remc) {
+            const char* src = gbase + (long long)k * (CNT * 8) + part * G;
             const unsigned dst = dst_arr + r * PITCH + part * G;
             if constexpr (G == 16)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
@@ -428,18 +426,21 @@ IPOC_DEV WarpSmem warp_smem(char* smem, const Geom& g, int warp_in_block, long l
     WarpSmem w;
     w.stage0 = smem + (size_t)warp_in_block * g.pw_bytes;
     w.stage0_s = (unsigned)__cvta_generic_to_shared(w.stage0);
+    long long rem;
     if (g.per_lane) {
         w.map.tb = wg * 32 * (long long)g.N;
-        w.map.rem = ((long long)g.batch - wg * 32) * g.N;
+        rem = ((long long)g.batch - wg * 32) * g.N;
         w.map.S = g.N;
         w.map.T0 = g.N;
     } else {
         const long long b = wg / g.nW, wi = wg % g.nW;
         w.map.tb = b * g.N + wi * 32 * g.T0;
-        w.map.rem = (long long)g.N - wi * 32 * g.T0;
+        rem = (long long)g.N - wi * 32 * g.T0;
         w.map.S = g.T0;
         w.map.T0 = g.T0;
     }
+    const long long cap = 32LL * w.map.S;
+    w.map.remc = (int)(rem < cap ? rem : cap);
     return w;
 }
 
