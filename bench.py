@@ -384,6 +384,26 @@ def run_ours(args):
         except Exception as e:
             batched_solves = {"error": repr(e)[:200]}
 
+    # ---- B3 proxy: the same Newton step as a log-depth tree scan of batched torch ops on this
+    #      GPU — structurally what XLA:GPU emits for lax.associative_scan; NOT the reference (JAX is absent).
+    proxy = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            import torch_treescan as _tt
+            regp = float(npass.cu_norm[0])
+            fnp = lambda: _tt.par_newton(w["fx"], w["fu"], w["ru"], w["Q"], w["R"], w["M"], regp)
+            dxp = fnp()[0]
+            dxr = _noc2_step(w, regp, dev)
+            ms_p = float(np.mean(_time_local(torch, fnp, flush, 5, 3, dev)))
+            ms_ours = float(np.mean(_time_local(torch, lambda: _noc2_step(w, regp, dev), flush, 20, 3, dev)))
+            proxy = {"kind": "torch batched odd/even tree scan + torch.linalg.solve on B200, eager (structural proxy "
+                             "for XLA:GPU; NOT the reference)", "ms_per_newton_step_K2K3": ms_p,
+                     "ours_ms_per_newton_step_K2K3_eager_api": ms_ours,
+                     "max_rel_dx_diff_vs_ours": float((dxp - dxr).abs().max() / dxr.abs().max())}
+        except Exception as e:
+            proxy = {"error": repr(e)[:200]}
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload with the oracle port
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -421,6 +441,7 @@ def run_ours(args):
             "ms_per_step_plain_launch": ms_plain, "ms_per_step_l2_warm": ms_warm,
             "sweep": sweep,
             "time_sharded": time_sharded,
+            "xla_proxy": proxy,
             "solves": solves,
             "batched_solves": batched_solves,
         }
@@ -429,6 +450,13 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _noc2_step(w, reg, dev):
+    import torch
+    from ipoc_b200 import noc
+    return noc.newton_step(w["fx"], w["fu"], w["ru"], w["Q"], w["R"], w["M"],
+                           torch.tensor([reg], dtype=torch.float64, device=dev))[0]
 
 
 def _time_local(torch, fn, flush, steps, warmup, dev):
