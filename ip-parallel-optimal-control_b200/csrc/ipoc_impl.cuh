@@ -490,7 +490,10 @@ struct NewtonLoader {
         issue_rows<NX * NU>(st + O_M, M, m, j, lane);
         issue_rows<NU>(st + O_RU, ru, m, j, lane);
     }
-    IPOC_DEV void read(StepLQ<NX, NU>& s, const char* st, int lane, int b) const {
+    // per-lane constant fetched ONCE before the walk (a global load inside the step loop would expose
+    // its full latency every step: 16 % of the stall samples in profiles/r01)
+    IPOC_DEV double aux(int b) const { return __ldg(reg + b); }
+    IPOC_DEV void read(StepLQ<NX, NU>& s, const char* st, int lane, double rg) const {
         double Qf[NX][NX], Rf[NU][NU], ruv[NU];
         read_row<NX * NX>(&s.A[0][0], st + O_FX, lane);
         read_row<NX * NU>(&s.B[0][0], st + O_FU, lane);
@@ -498,7 +501,6 @@ struct NewtonLoader {
         read_row<NU * NU>(&Rf[0][0], st + O_R, lane);
         read_row<NX * NU>(&s.M[0][0], st + O_M, lane);
         read_row<NU>(ruv, st + O_RU, lane);
-        const double rg = __ldg(reg + b);
 #pragma unroll
         for (int a = 0; a < NU; ++a)
 #pragma unroll
@@ -513,8 +515,7 @@ struct NewtonLoader {
             }
 #pragma unroll
             for (int a = 0; a < NU; ++a) s.p[a] = ruv[a];
-            return;
-        }
+        } else {
         // X^-1 M
         double W[NX][NX], XiM[NX][NU];
 #pragma unroll
@@ -567,6 +568,7 @@ struct NewtonLoader {
             for (int i = 0; i < NX; ++i) v += s.M[i][a] * rr[i];     // + M' r
             s.p[a] = -v;
         }
+        }
     }
 };
 
@@ -587,7 +589,8 @@ struct LqtLoader {
         issue_rows<NX>(st + O_Q, q, m, j, lane);
         issue_rows<NU>(st + O_P, p, m, j, lane);
     }
-    IPOC_DEV void read(StepLQ<NX, NU>& s, const char* st, int lane, int) const {
+    IPOC_DEV double aux(int) const { return 0.0; }
+    IPOC_DEV void read(StepLQ<NX, NU>& s, const char* st, int lane, double) const {
         double Xf[NX][NX], Uf[NU][NU];
         read_row<NX * NX>(&s.A[0][0], st + O_A, lane);
         read_row<NX * NU>(&s.B[0][0], st + O_B, lane);
@@ -691,7 +694,8 @@ k_ric_leaf_up(Loader ld, Geom g, double* __restrict__ incl, size_t istride, doub
     RicElem<NX> a;
     RicOp<NX>::identity(a);
     StepLQ<NX, NU> s;
-    staged_walk(ld, w, g.T0, L.len, lane, true, [&](const char* st) { ld.read(s, st, lane, L.b); },
+    const double aux = ld.aux(L.b);
+    staged_walk(ld, w, g.T0, L.len, lane, true, [&](const char* st) { ld.read(s, st, lane, aux); },
                 [&](int) {
                     StepElem<NX, NU> e;
                     make_step_elem(e, s);
@@ -749,7 +753,8 @@ k_ric_leaf_down(Loader ld, Geom g, const double* __restrict__ incl, size_t istri
     };
     if (S_out != nullptr && L.len > 0 && L.k0 + L.len == N) write_Sv(N);
     StepLQ<NX, NU> s;
-    staged_walk(ld, w, g.T0, L.len, lane, true, [&](const char* st) { ld.read(s, st, lane, L.b); }, [&](int j) {
+    const double aux = ld.aux(L.b);
+    staged_walk(ld, w, g.T0, L.len, lane, true, [&](const char* st) { ld.read(s, st, lane, aux); }, [&](int j) {
         StepGain<NX, NU> gn;
         ric_step_back(val, gn, s);
         const size_t t = (size_t)(L.t0 + j);
@@ -1147,14 +1152,25 @@ static int set_smem_plain(K kernel, size_t bytes) {
             return IPOC_ECUDA;
     return IPOC_OK;
 }
+// Shared-memory set-up of a leaf kernel: opt in to > 48 KB, then ask for a carve-out that just fits the
+// CTAs the register file allows — NOT the maximum: what is left over is L1, and the few spill slots of
+// the 255-register Riccati kernels are re-read every time step (with the maximum carve-out those
+// LDLs missed L1 and showed up as 18 % long-scoreboard stalls, profiles/r01).
 template <class K>
-static int set_smem(K kernel, size_t bytes) {
+static int set_smem(K kernel, size_t bytes, int threads) {
     if (bytes > 48 * 1024)
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
             return IPOC_ECUDA;
-    // ask for the largest shared-memory carve-out so that two CTAs (8 warps) fit per SM
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) !=
         cudaSuccess)
+        return IPOC_ECUDA;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, bytes) != cudaSuccess) return IPOC_ECUDA;
+    if (nb < 1) nb = 1;
+    const size_t need = (size_t)nb * (bytes + 1024);
+    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
+    if (pct > 100) pct = 100;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess)
         return IPOC_ECUDA;
     return IPOC_OK;
 }
@@ -1226,7 +1242,7 @@ static int run_bwd_up(const Plan& p, const NewtonWs& w, const Loader& ld, cudaSt
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_ric_leaf_up<NX, NU, Loader>;
-    if (int rc = set_smem(kern, ll.smem)) return rc;
+    if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.ric.incl, (size_t)p.slots, w.ric.agg[0],
                                               (size_t)p.g.batch * p.g.nW);
     IPOC_LAUNCH_CHECK_N("k_ric_leaf_up", st);
@@ -1244,7 +1260,7 @@ static int run_bwd_down(const Plan& p, const NewtonWs& w, const Loader& ld, doub
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_ric_leaf_down<NX, NU, Loader>;
-    if (int rc = set_smem(kern, ll.smem)) return rc;
+    if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     const bool fwd = want_fwd_agg && !p.g.per_lane;
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.ric.incl, (size_t)p.slots, vals, vstride, Kx, d, S, v,
                                               w.pred_part, w.feas_part, pred, feasible, fwd ? w.aff.incl : nullptr,
@@ -1284,7 +1300,7 @@ static int run_fwd_down(const Plan& p, const NewtonWs& w, const double* A, const
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_fwd_leaf_down<NX, NU>;
-    if (int rc = set_smem(kern, ll.smem)) return rc;
+    if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.aff.incl, (size_t)p.slots, vals, vstride, x, u);
     IPOC_LAUNCH_CHECK_N("k_fwd_leaf_down", st);
     return IPOC_OK;
@@ -1342,7 +1358,7 @@ static int run_fwd_up(const Plan& p, const NewtonWs& w, const double* A, const d
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_fwd_leaf_up<NX, NU>;
-    if (int rc = set_smem(kern, ll.smem)) return rc;
+    if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.aff.incl, (size_t)p.slots, w.aff.agg[0],
                                               (size_t)p.g.batch * p.g.nW);
     IPOC_LAUNCH_CHECK_N("k_fwd_leaf_up", st);
@@ -1373,7 +1389,7 @@ static int aff_up(const Plan& p, const ScanWs& w, const double* F, const double*
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_aff_leaf_up<NX>;
-    if (int rc = set_smem(kern, ll.smem)) return rc;
+    if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, reverse, transpose, g, w.incl, (size_t)p.slots, w.agg[0],
                                               (size_t)p.g.batch * p.g.nW);
     IPOC_LAUNCH_CHECK_N("k_aff_leaf_up", st);
@@ -1390,7 +1406,7 @@ static int aff_down(const Plan& p, const ScanWs& w, const double* F, const doubl
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_aff_leaf_down<NX>;
-    if (int rc = set_smem(kern, ll.smem)) return rc;
+    if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, reverse, transpose, g, w.incl, (size_t)p.slots, vals, vstride,
                                               out);
     IPOC_LAUNCH_CHECK_N("k_aff_leaf_down", st);

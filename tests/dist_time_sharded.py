@@ -59,9 +59,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
     ms_sharded = timed(lambda: sharded.newton_step_time_sharded(seg, reg, ST, gather))
+    seg.capture(reg, ST)
+    gather_into = sharded.dist_all_gather_into()
+    dxg, dug, predg, _ = seg.step_graphed(gather_into)
+    torch.cuda.synchronize()
+    errg = max(rel(dxg, dx1[lo:hi + 1]), rel(dug, du1[lo:hi]), abs(float(predg) - float(pred1)) / abs(float(pred1)))
+    ok = ok and errg < 1e-10
+    ms_graphed = timed(lambda: seg.step_graphed(gather_into))
     ms_single = timed(lambda: noc.newton_step(*full, reg))
     print(f"[rank {rank}/{world}] N={N} nx={nx} segment=[{lo},{hi}) max rel err {max(errs):.2e} "
-          f"{'OK' if ok else 'FAIL'}  time-sharded {ms_sharded:.3f} ms vs single-GPU {ms_single:.3f} ms", flush=True)
+          f"{'OK' if ok else 'FAIL'}  time-sharded {ms_sharded:.3f} ms (graphed {ms_graphed:.3f} ms) "
+          f"vs single-GPU {ms_single:.3f} ms", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
