@@ -13,7 +13,7 @@
 //   leaf-down : only VALUES travel down ((S, v) for K2, a state vector for K1/K3): a thread applies
 //               its neighbour's stored in-warp aggregate to the value entering its warp and re-walks
 //               its chunk with the cheap seeded recursion, emitting outputs.
-// Global loads of the leaf kernels are warp-cooperative cp.async copies into a double-buffered
+// Global loads of the leaf kernels are warp-cooperative cp.async copies into a per-warp
 // shared-memory stage (rows padded to an odd number of 16-byte units -> conflict-free LDS.128):
 // each lane needs ITS OWN chunk's time step, i.e. a stride-T0 gather; fetching it with per-lane
 // loads costs 32 L1 wavefronts per instruction and made the first version L1-bound (profiles/r01a).
