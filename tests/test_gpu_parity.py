@@ -367,6 +367,69 @@ def test_parallel_rollout_equals_serial(problem, N):
     assert relerr(N_(xp), N_(xs)) < 1e-11
 
 
+def test_reference_helper_functions(golden):
+    """`noc_to_lqt`, `check_traj_feasibility`, `par_costates`, `compute_derivatives` keep the reference's
+    signatures and values (torch tensors for jnp arrays)."""
+    from ipoc_b200 import noc, problems
+    g = golden("step_cartpole_N100")
+    N = g["controls"].shape[0]
+    ocp = problems.make_cartpole(1.0 / N)
+    x, u = T(g["states"]), T(g["controls"])
+    d = noc.compute_derivatives(ocp, x, u, float(g["bp"]))
+    for f in d._fields:
+        assert np.max(np.abs(N_(getattr(d, f)) - g["d_" + f])) <= 1e-11 * max(1.0, np.max(np.abs(g["d_" + f]))), f
+    lam = noc.par_costates(ocp, x[-1], d)
+    assert relerr(N_(lam), g["ref_costates_par"]) < 1e-12
+    ru, Q, R, M = noc.compute_lqr_params(lam, d)
+    lqt = noc.noc_to_lqt(ru, Q, R + float(g["ref_reg"]) * torch.eye(1, dtype=torch.float64, device=DEV), M, d.fx, d.fu)
+    assert relerr(N_(lqt.r), g["ref_lqt_r"]) < 1e-10 and relerr(N_(lqt.s), g["ref_lqt_s"]) < 1e-10
+    assert lqt.H.shape == (N, 4, 4) and lqt.Z.shape == (N, 1, 1) and torch.equal(lqt.XT, Q[0])
+    dx, du, pred, feas, _ = noc.par_Newton(x, d, float(g["reg_param"]), ru, Q, R, M)
+    assert bool(noc.check_traj_feasibility(ocp, x + dx, u + du)) == bool(g["ref_new_feasible"])
+    nc, ncr = float(ocp.total_cost(x + dx, u + du, float(g["bp"]))), float(g["ref_new_cost"])
+    # an infeasible trial gives log(negative) = NaN in the reference too; the `where` of :159-163 masks it
+    assert (np.isnan(nc) and np.isnan(ncr)) or abs(nc - ncr) <= 1e-9 * abs(ncr)
+
+
+def test_host_buffer_entry_point_and_error_codes():
+    """`ipoc_newton_step_host_f64` (pinned host buffers) equals the resident call; bad calls return codes."""
+    import ctypes
+    from ipoc_b200 import noc, _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(4)
+    N, nx, nu = 1500, 4, 1
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu)
+    host = [torch.as_tensor(np.ascontiguousarray(a)).pin_memory() for a in (fx, fu, ru, Q, R, M)]
+    reg = torch.tensor([0.4], dtype=torch.float64).pin_memory()
+    dx = torch.empty(N + 1, nx, dtype=torch.float64).pin_memory()
+    du = torch.empty(N, nu, dtype=torch.float64).pin_memory()
+    pred = torch.empty(1, dtype=torch.float64).pin_memory()
+    feas = torch.empty(1, dtype=torch.int32).pin_memory()
+    nbytes = L.ipoc_newton_step_host_scratch_bytes(N, nx, nu, 1)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    hp = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = L.ipoc_newton_step_host_f64(N, nx, nu, 1, *(hp(t) for t in host), hp(reg), hp(dx), hp(du), hp(pred), hp(feas),
+                                     hp(scratch), nbytes, _lib.stream_ptr())
+    assert rc == 0
+    torch.cuda.synchronize()
+    dx2, du2, _, _, pred2, feas2 = noc.newton_step(*(T(a) for a in (fx, fu, ru, Q, R, M)), T([0.4]))
+    assert torch.equal(dx.to(DEV), dx2) and torch.equal(du.to(DEV), du2) and float(pred) == float(pred2)
+    # workspace too small / unsupported dimension / misaligned pointer are error CODES, not crashes
+    dev = [T(a) for a in (fx, fu, ru, Q, R, M)]
+    o = dict(dtype=torch.float64, device=DEV)
+    outs = [torch.empty(N + 1, nx, **o), torch.empty(N, nu, **o), torch.empty(N, nu, nx, **o), torch.empty(N, nu, **o),
+            torch.empty(1, **o), torch.empty(1, dtype=torch.int32, device=DEV)]
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    dp = lambda t: ctypes.c_void_p(t.data_ptr())
+    regd = T([0.4])
+    call = lambda nx_, wsb, fxp: L.ipoc_newton_step_f64(N, nx_, nu, 1, fxp, *(dp(t) for t in dev[1:]), dp(regd),
+                                                        *(dp(t) for t in outs), dp(ws), wsb, _lib.stream_ptr())
+    assert call(nx, 64, dp(dev[0])) == -2                      # IPOC_EWORKSPACE
+    assert call(5, 1 << 20, dp(dev[0])) == -1                  # IPOC_EUNSUPPORTED_DIM
+    assert call(nx, 1 << 20, ctypes.c_void_p(dev[0].data_ptr() + 8)) == -6   # IPOC_EALIGN
+    assert b"workspace" in L.ipoc_strerror(-2)
+
+
 def test_cpu_tensors_are_rejected():
     from ipoc_b200 import noc, _lib
     rng = np.random.default_rng(0)
