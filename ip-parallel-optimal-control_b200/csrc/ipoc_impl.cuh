@@ -42,6 +42,15 @@ extern int g_literal_lqt;   // 0: q = 0, p = ru (default); 1: literal noc_to_lqt
 void prof_mark(const char* name, cudaStream_t st);   // no-op unless profiling is armed
 
 constexpr int kLeafThreads = 128;
+#ifndef IPOC_NS_RIC_UP
+#define IPOC_NS_RIC_UP 1
+#endif
+#ifndef IPOC_NS_RIC_DOWN
+#define IPOC_NS_RIC_DOWN 1
+#endif
+#ifndef IPOC_NS_LIGHT
+#define IPOC_NS_LIGHT 3
+#endif
 #ifndef IPOC_RIC_MINB
 #define IPOC_RIC_MINB 1
 #endif
@@ -444,25 +453,32 @@ IPOC_DEV WarpSmem warp_smem(char* smem, const Geom& g, int warp_in_block, long l
     return w;
 }
 
-// Walk over the T steps of a chunk (uniform trip count; lanes with shorter chunks idle) with ONE
-// shared stage per warp: fetch(stage) copies the lane's row into registers, after which the stage
-// is free again, so the copies of the NEXT step are issued before compute(j) runs and have the
-// whole compute time to land.  (A second stage would buy no extra overlap and halve the number of
-// resident warps the shared memory allows.)
-template <class Ld, class F1, class F2>
+// Walk over the T steps of a chunk (uniform trip count; lanes with shorter chunks idle) through a ring
+// of NS shared stages per warp: fetch(stage) copies the lane's row into registers, after which that
+// stage is free again, so the copies of step it+NS are issued before compute(j) runs.  NS = 1 already
+// overlaps one step of arithmetic with the copies; the memory-bound kernels (K1, K3, K2's down-sweep)
+// use deeper rings to keep more bytes in flight (they were waiting on the cp.async group 40 % of the
+// time with NS = 1, profiles/r01).
+template <int NS, class Ld, class F1, class F2>
 IPOC_DEV void staged_walk(const Ld& ld, const WarpSmem& w, int T, int len, int lane, bool reverse, F1&& fetch,
                           F2&& compute) {
-    ld.issue(w.stage0_s, w.map, reverse ? T - 1 : 0, lane);
-    cp_async_commit();
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        if (s < T) ld.issue(w.stage0_s + s * Ld::STAGE_BYTES, w.map, reverse ? T - 1 - s : s, lane);
+        cp_async_commit();
+    }
+    int slot = 0;
     for (int it = 0; it < T; ++it) {
         const int j = reverse ? T - 1 - it : it;
-        cp_async_wait<0>();
+        cp_async_wait<NS - 1>();
         __syncwarp();
-        if (j < len) fetch(w.stage0);
+        if (j < len) fetch(w.stage0 + slot * Ld::STAGE_BYTES);
         __syncwarp();
-        if (it + 1 < T) ld.issue(w.stage0_s, w.map, reverse ? j - 1 : j + 1, lane);
+        if (it + NS < T)
+            ld.issue(w.stage0_s + slot * Ld::STAGE_BYTES, w.map, reverse ? j - NS : j + NS, lane);
         cp_async_commit();
         if (j < len) compute(j);
+        slot = (slot + 1 == NS) ? 0 : slot + 1;
     }
 }
 
@@ -693,14 +709,15 @@ k_ric_leaf_up(Loader ld, Geom g, double* __restrict__ incl, size_t istride, doub
     const WarpSmem w = warp_smem(smem, g, wib, wg);
     RicElem<NX> a;
     RicOp<NX>::identity(a);
-    StepLQ<NX, NU> s;
+    StepElem<NX, NU> e;   // formed in the fetch phase: smaller than the raw step, lives across the copy issue
     const double aux = ld.aux(L.b);
-    staged_walk(ld, w, g.T0, L.len, lane, true, [&](const char* st) { ld.read(s, st, lane, aux); },
-                [&](int) {
-                    StepElem<NX, NU> e;
+    staged_walk<IPOC_NS_RIC_UP>(ld, w, g.T0, L.len, lane, true,
+                [&](const char* st) {
+                    StepLQ<NX, NU> s;
+                    ld.read(s, st, lane, aux);
                     make_step_elem(e, s);
-                    ric_prepend_step(a, e);
-                });
+                },
+                [&](int) { ric_prepend_step(a, e); });
     warp_scan<RicOp<NX>>(a, reinterpret_cast<double*>(w.stage0), lane, true);
     soa_store(a, incl, istride, (size_t)L.slot);
     if (lane == 0) soa_store(a, agg1, a1stride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
@@ -754,7 +771,7 @@ k_ric_leaf_down(Loader ld, Geom g, const double* __restrict__ incl, size_t istri
     if (S_out != nullptr && L.len > 0 && L.k0 + L.len == N) write_Sv(N);
     StepLQ<NX, NU> s;
     const double aux = ld.aux(L.b);
-    staged_walk(ld, w, g.T0, L.len, lane, true, [&](const char* st) { ld.read(s, st, lane, aux); }, [&](int j) {
+    staged_walk<IPOC_NS_RIC_DOWN>(ld, w, g.T0, L.len, lane, true, [&](const char* st) { ld.read(s, st, lane, aux); }, [&](int j) {
         StepGain<NX, NU> gn;
         ric_step_back(val, gn, s);
         const size_t t = (size_t)(L.t0 + j);
@@ -849,7 +866,7 @@ k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, 
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = xv.r[i];
     double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU], cv[NX];
-    staged_walk(ld, w, g.T0, L.len, lane, false,
+    staged_walk<IPOC_NS_LIGHT>(ld, w, g.T0, L.len, lane, false,
                 [&](const char* st) { read_fwd_step<NX, NU>(ld, st, lane, Am, Bm, Km, dv, cv); }, [&](int j) {
         double u[NU], xn[NX];
 #pragma unroll
@@ -892,7 +909,7 @@ k_fwd_leaf_up(FwdLoader<NX, NU> ld, Geom g, double* __restrict__ fincl, size_t f
     AffElem<NX> fa;
     AffOp<NX>::identity(fa);
     double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU], cv[NX];
-    staged_walk(ld, w, g.T0, L.len, lane, false,
+    staged_walk<IPOC_NS_LIGHT>(ld, w, g.T0, L.len, lane, false,
                 [&](const char* st) { read_fwd_step<NX, NU>(ld, st, lane, Am, Bm, Km, dv, cv); }, [&](int) {
         AffElem<NX> se;
 #pragma unroll
@@ -930,8 +947,9 @@ k_aff_leaf_up(AffLoader<NX> ld, int reverse, int transpose, Geom g, double* __re
     AffElem<NX> a;
     AffOp<NX>::identity(a);
     AffElem<NX> se;
-    staged_walk(ld, w, g.T0, L.len, lane, reverse != 0, [&](const char* st) { ld.read(se, st, lane, transpose); },
-                [&](int) { AffOp<NX>::compose(a, a, se); });
+    staged_walk<IPOC_NS_LIGHT>(ld, w, g.T0, L.len, lane, reverse != 0,
+                               [&](const char* st) { ld.read(se, st, lane, transpose); },
+                               [&](int) { AffOp<NX>::compose(a, a, se); });
     warp_scan<AffOp<NX>>(a, reinterpret_cast<double*>(w.stage0), lane, reverse != 0);
     soa_store(a, incl, istride, (size_t)L.slot);
     if (reverse) {
@@ -977,8 +995,8 @@ k_aff_leaf_down(AffLoader<NX> ld, int reverse, int transpose, Geom g, const doub
         if (L.len > 0 && L.k0 == 0) st_vec<NX>(ob, x.r);
     }
     AffElem<NX> se;
-    staged_walk(ld, w, g.T0, L.len, lane, reverse != 0, [&](const char* st) { ld.read(se, st, lane, transpose); },
-                [&](int j) {
+    staged_walk<IPOC_NS_LIGHT>(ld, w, g.T0, L.len, lane, reverse != 0,
+                               [&](const char* st) { ld.read(se, st, lane, transpose); }, [&](int j) {
                     AffOp<NX>::apply(x, se, x);
                     st_vec<NX>(ob + (size_t)(L.k0 + j + (reverse ? 0 : 1)) * NX, x.r);
                 });
@@ -1117,12 +1135,12 @@ struct LeafLaunch {
     unsigned grid;
     size_t smem;
 };
-static LeafLaunch leaf_launch(const Plan& p, int stage_bytes, size_t scratch_bytes = 0) {
+static LeafLaunch leaf_launch(const Plan& p, int stage_bytes, size_t scratch_bytes = 0, int nstages = 1) {
     // Warps of a leaf CTA never synchronise with each other, so the CTA size is free: take the
     // smallest CTA that still reaches the largest number of resident warps per SM under the
     // shared-memory limit (228 KB per SM, 1 KB reserved per CTA, at most 32 CTAs) — small CTAs
     // balance the single wave better.
-    size_t body = (size_t)stage_bytes;   // one stage; the scan scratch reuses the area after the walk
+    size_t body = (size_t)stage_bytes * nstages;   // stage ring; the scan scratch reuses the area after the walk
     if (body < scratch_bytes) body = scratch_bytes;
     const size_t per_warp = (size_t)kTabBytes + body;
     const size_t sm_bytes = 228 * 1024;
@@ -1238,7 +1256,7 @@ static void leaf_values(const Plan& p, const ScanWs& w, const double*& vals, siz
 // ---- K2 (+K3 aggregates) for any loader ---------------------------------------------------
 template <int NX, int NU, class Loader>
 static int run_bwd_up(const Plan& p, const NewtonWs& w, const Loader& ld, cudaStream_t st) {
-    const LeafLaunch ll = leaf_launch(p, Loader::STAGE_BYTES, scan_scratch_bytes<RicOp<NX>>());
+    const LeafLaunch ll = leaf_launch(p, Loader::STAGE_BYTES, scan_scratch_bytes<RicOp<NX>>(), IPOC_NS_RIC_UP);
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_ric_leaf_up<NX, NU, Loader>;
@@ -1256,7 +1274,7 @@ static int run_bwd_down(const Plan& p, const NewtonWs& w, const Loader& ld, doub
     const double* vals;
     size_t vstride;
     leaf_values(p, w.ric, vals, vstride);
-    const LeafLaunch ll = leaf_launch(p, Loader::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>());
+    const LeafLaunch ll = leaf_launch(p, Loader::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>(), IPOC_NS_RIC_DOWN);
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_ric_leaf_down<NX, NU, Loader>;
@@ -1296,7 +1314,7 @@ static int run_fwd_down(const Plan& p, const NewtonWs& w, const double* A, const
     size_t vstride;
     leaf_values(p, w.aff, vals, vstride);
     FwdLoader<NX, NU> ld{A, B, c, Kx, d};
-    const LeafLaunch ll = leaf_launch(p, FwdLoader<NX, NU>::STAGE_BYTES, 0);
+    const LeafLaunch ll = leaf_launch(p, FwdLoader<NX, NU>::STAGE_BYTES, 0, IPOC_NS_LIGHT);
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_fwd_leaf_down<NX, NU>;
@@ -1354,7 +1372,7 @@ template <int NX, int NU>
 static int run_fwd_up(const Plan& p, const NewtonWs& w, const double* A, const double* B, const double* c,
                       const double* Kx, const double* d, cudaStream_t st) {
     FwdLoader<NX, NU> ld{A, B, c, Kx, d};
-    const LeafLaunch ll = leaf_launch(p, FwdLoader<NX, NU>::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>());
+    const LeafLaunch ll = leaf_launch(p, FwdLoader<NX, NU>::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>(), IPOC_NS_LIGHT);
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_fwd_leaf_up<NX, NU>;
@@ -1385,7 +1403,7 @@ template <int NX>
 static int aff_up(const Plan& p, const ScanWs& w, const double* F, const double* c, int reverse, int transpose,
                   cudaStream_t st) {
     AffLoader<NX> ld{F, c};
-    const LeafLaunch ll = leaf_launch(p, AffLoader<NX>::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>());
+    const LeafLaunch ll = leaf_launch(p, AffLoader<NX>::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>(), IPOC_NS_LIGHT);
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_aff_leaf_up<NX>;
@@ -1402,7 +1420,7 @@ static int aff_down(const Plan& p, const ScanWs& w, const double* F, const doubl
     size_t vstride;
     leaf_values(p, w, vals, vstride);
     AffLoader<NX> ld{F, c};
-    const LeafLaunch ll = leaf_launch(p, AffLoader<NX>::STAGE_BYTES, 0);
+    const LeafLaunch ll = leaf_launch(p, AffLoader<NX>::STAGE_BYTES, 0, IPOC_NS_LIGHT);
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_aff_leaf_down<NX>;
