@@ -5,11 +5,13 @@
 // Scan organisation (all three scans: K1 costates, K2 Riccati, K3 forward): hierarchical
 // reduce / seeded re-scan.
 //   leaf-up   : a thread folds `T0` consecutive time steps sequentially (work-optimal); the 32
-//               thread aggregates of a warp are then scanned with shuffles (Kogge-Stone) inside
-//               the same kernel, where the latency hides behind the other resident warps; every
-//               thread stores its in-warp inclusive aggregate, every warp its total.
+//               thread aggregates of a warp are then scanned (Kogge-Stone, operands exchanged
+//               through the warp's shared scratch) inside the same kernel, where the latency hides
+//               behind the other resident warps; every thread stores its in-warp inclusive
+//               aggregate, every warp its total.
 //   levels    : warp totals are folded by mid kernels only when there are more than `top_max` of
-//               them; a single CTA per sequence scans the rest (shuffles + smem warp carries).
+//               them; a single CTA per sequence scans the rest (in-warp scans + a short serial
+//               chain of `apply` across warps).
 //   leaf-down : only VALUES travel down ((S, v) for K2, a state vector for K1/K3): a thread applies
 //               its neighbour's stored in-warp aggregate to the value entering its warp and re-walks
 //               its chunk with the cheap seeded recursion, emitting outputs.
@@ -72,23 +74,6 @@ IPOC_DEV void soa_store(const T& t, double* __restrict__ base, size_t stride, si
 #pragma unroll
     for (int c = 0; c < SZ; ++c) base[(size_t)c * stride + idx] = t.r[c];
 }
-template <class T>
-IPOC_DEV T shfl_down_all(const T& t, int delta) {
-    constexpr int SZ = sizeof(T) / sizeof(double);
-    T o;
-#pragma unroll
-    for (int c = 0; c < SZ; ++c) o.r[c] = __shfl_down_sync(0xffffffffu, t.r[c], delta);
-    return o;
-}
-template <class T>
-IPOC_DEV T shfl_up_all(const T& t, int delta) {
-    constexpr int SZ = sizeof(T) / sizeof(double);
-    T o;
-#pragma unroll
-    for (int c = 0; c < SZ; ++c) o.r[c] = __shfl_up_sync(0xffffffffu, t.r[c], delta);
-    return o;
-}
-
 // contiguous per-step loads: CNT doubles at p (16-byte aligned when CNT is even)
 template <int CNT>
 IPOC_DEV void ld_vec(double* dst, const double* __restrict__ p) {
@@ -373,7 +358,6 @@ __host__ __device__ constexpr int row_gran(int cnt) { return (cnt % 2 == 0) ? 16
 __host__ __device__ constexpr int row_cpr(int cnt) { return cnt * 8 / row_gran(cnt); }
 __host__ __device__ constexpr int row_pitch(int cnt) { return (row_cpr(cnt) % 2 == 1) ? cnt * 8 : cnt * 8 + row_gran(cnt); }
 __host__ __device__ constexpr int arr_bytes(int cnt) { return (32 * row_pitch(cnt) + 15) / 16 * 16; }
-constexpr int kTabBytes = 0;   // (rows are addressed arithmetically, see RowMap)
 
 IPOC_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int NKEEP>
@@ -1142,7 +1126,7 @@ static LeafLaunch leaf_launch(const Plan& p, int stage_bytes, size_t scratch_byt
     // balance the single wave better.
     size_t body = (size_t)stage_bytes * nstages;   // stage ring; the scan scratch reuses the area after the walk
     if (body < scratch_bytes) body = scratch_bytes;
-    const size_t per_warp = (size_t)kTabBytes + body;
+    const size_t per_warp = body;
     const size_t sm_bytes = 228 * 1024;
     int best_wpc = 1, best_warps = 0;
     for (int wpc = 1; wpc <= kLeafThreads / 32; wpc *= 2) {

@@ -90,7 +90,8 @@ class GraphedNewton:
         return bool(rec[0] != 0), float(rec[1]), float(rec[2]), float(rec[3]), float(rec[4])
 
 
-_cache = {}
+_cache = {}          # insertion-ordered; bounded so that throw-away OCP closures cannot pile up graphs
+_CACHE_MAX = 8
 
 
 def get(ocp: OCP, N, nx, nu, device, x, u, bp):
@@ -110,5 +111,7 @@ def get(ocp: OCP, N, nx, nu, device, x, u, bp):
             g = False
         else:
             g._keepalive = ocp
+        while len(_cache) >= _CACHE_MAX:
+            _cache.pop(next(iter(_cache)))
         _cache[key] = g
     return g
