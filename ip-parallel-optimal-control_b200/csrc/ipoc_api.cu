@@ -150,54 +150,90 @@ k_reduce_final(const double* __restrict__ partials, int nblk, int has_ru, int ha
     }
 }
 
-// one CTA per problem, slice = everything, finalisation in the same launch (N*width <= 4096)
-static __global__ void __launch_bounds__(kRedThreads)
+// Small problems: one CTA of 1024 threads per problem does the slice reduction and the finalisation
+// in a single launch (N*width <= 65536).  Four independent accumulators per thread keep enough loads
+// in flight; the combination order is fixed, so the result is bit-reproducible.
+constexpr int kRedSingleThreads = 1024;
+static __global__ void __launch_bounds__(kRedSingleThreads)
 k_reduce_single(const double* __restrict__ ru, const double* __restrict__ cu, const double* __restrict__ cons,
                 int N, int nu, int nc, double* __restrict__ hu_norm, double* __restrict__ cu_norm,
                 int32_t* __restrict__ traj_feasible, const double* __restrict__ rp, double* __restrict__ reg) {
-    __shared__ double s_max[kRedThreads];
-    __shared__ double s_sq[kRedThreads];
-    __shared__ int s_ok[kRedThreads];
-    const int b = blockIdx.x, t = threadIdx.x;
+    __shared__ double s_max[32];
+    __shared__ double s_sq[32];
+    __shared__ int s_ok[32];
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    constexpr int NT = kRedSingleThreads;
     double mx = 0.0, sq = 0.0;
     int ok = 1;
     if (ru != nullptr) {
         const double* p = ru + (size_t)b * N * nu;
-        for (int i = t; i < N * nu; i += kRedThreads) mx = nan_max(mx, fabs(p[i]));
+        const int n = N * nu;
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+        int i = t;
+        for (; i + 3 * NT < n; i += 4 * NT) {
+            m0 = nan_max(m0, fabs(p[i]));
+            m1 = nan_max(m1, fabs(p[i + NT]));
+            m2 = nan_max(m2, fabs(p[i + 2 * NT]));
+            m3 = nan_max(m3, fabs(p[i + 3 * NT]));
+        }
+        for (; i < n; i += NT) m0 = nan_max(m0, fabs(p[i]));
+        mx = nan_max(nan_max(m0, m1), nan_max(m2, m3));
     }
     if (cu != nullptr) {
         const double* p = cu + (size_t)b * N * nu;
-        for (int i = t; i < N * nu; i += kRedThreads) sq += p[i] * p[i];
+        const int n = N * nu;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int i = t;
+        for (; i + 3 * NT < n; i += 4 * NT) {
+            a0 += p[i] * p[i];
+            a1 += p[i + NT] * p[i + NT];
+            a2 += p[i + 2 * NT] * p[i + 2 * NT];
+            a3 += p[i + 3 * NT] * p[i + 3 * NT];
+        }
+        for (; i < n; i += NT) a0 += p[i] * p[i];
+        sq = (a0 + a1) + (a2 + a3);
     }
     if (cons != nullptr) {
         const double* p = cons + (size_t)b * N * nc;
-        for (int i = t; i < N * nc; i += kRedThreads) ok &= (p[i] <= 0.0) ? 1 : 0;
+        const int n = N * nc;
+        for (int i = t; i < n; i += NT) ok &= (p[i] <= 0.0) ? 1 : 0;
     }
-    s_max[t] = mx;
-    s_sq[t] = sq;
-    s_ok[t] = ok;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+    }
+    if (lane == 0) {
+        s_max[w] = mx;
+        s_sq[w] = sq;
+        s_ok[w] = ok;
+    }
     __syncthreads();
-    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
-        if (t < o) {
-            s_max[t] = nan_max(s_max[t], s_max[t + o]);
-            s_sq[t] += s_sq[t + o];
-            s_ok[t] &= s_ok[t + o];
+    if (w == 0) {
+        mx = s_max[lane];
+        sq = s_sq[lane];
+        ok = s_ok[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            ok &= __shfl_xor_sync(0xffffffffu, ok, o);
         }
-        __syncthreads();
-    }
-    if (t == 0) {
-        if (ru != nullptr) hu_norm[b] = s_max[0];
-        if (cu != nullptr) {
-            const double nrm = sqrt(s_sq[0]);
-            cu_norm[b] = nrm;
-            if (rp != nullptr && reg != nullptr) reg[b] = rp[b] * nrm;   // ref :117
+        if (lane == 0) {
+            if (ru != nullptr) hu_norm[b] = mx;
+            if (cu != nullptr) {
+                const double nrm = sqrt(sq);
+                cu_norm[b] = nrm;
+                if (rp != nullptr && reg != nullptr) reg[b] = rp[b] * nrm;   // ref :117
+            }
+            if (cons != nullptr) traj_feasible[b] = ok;
         }
-        if (cons != nullptr) traj_feasible[b] = s_ok[0];
     }
 }
 
 static int reduce_blocks(int N, int width, int batch) {
-    if ((long long)N * width <= 4096) return 1;
+    if ((long long)N * width <= 65536) return 1;
     long long per_problem = ((long long)N * width + 8191) / 8192;   // >= 8192 entries per block
     long long cap = (148LL * 8 + batch - 1) / batch;                // fill the chip, not more
     long long n = per_problem < cap ? per_problem : cap;
@@ -354,7 +390,7 @@ int ipoc_reductions_f64(int N, int nu, int nc, int batch, const double* ru, cons
     cudaStream_t st_ = (cudaStream_t)stream;
     double* partials = (double*)ws;
     if (nblk == 1) {   // small problem: one launch does slice reduction and finalisation
-        k_reduce_single<<<batch, kRedThreads, 0, st_>>>(ru, cu, cons, N, nu, nc, hu_norm, cu_norm, traj_feasible, rp,
+        k_reduce_single<<<batch, kRedSingleThreads, 0, st_>>>(ru, cu, cons, N, nu, nc, hu_norm, cu_norm, traj_feasible, rp,
                                                        reg);
         IPOC_API_LAUNCH_CHECK(st_);
         return IPOC_OK;
