@@ -653,27 +653,39 @@ struct AffLoader {
     }
 };
 
-// Terminal value function per problem -> SoA seed (stride = batch).
-// ST: full (nx,nx) matrix at ST + b*st_stride (symmetrised), vT at vT + b*nx (NULL = 0).
+// Seed construction as a side job of the first CTA of the up-sweep kernel (saves a launch): the seeds
+// are only consumed by kernels that run after the up-sweep.
+struct SeedJob {
+    const double* ST;      // NULL = no job
+    size_t st_stride;
+    const double* vT;
+    int batch;
+    double* seed;
+    double* zero_aff_seed;
+};
 template <int NX>
-__global__ void k_ric_seed(const double* __restrict__ ST, size_t st_stride,
-                           const double* __restrict__ vT, int batch, double* __restrict__ seed,
-                           double* __restrict__ zero_aff_seed) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= batch) return;
-    if (zero_aff_seed != nullptr) {
+IPOC_DEV void make_ric_seed(const SeedJob& sj, int b) {
+    if (sj.zero_aff_seed != nullptr) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) zero_aff_seed[(size_t)i * batch + b] = 0.0;
+        for (int i = 0; i < NX; ++i) sj.zero_aff_seed[(size_t)i * sj.batch + b] = 0.0;
     }
     RicVal<NX> v;
-    const double* s = ST + (size_t)b * st_stride;
+    const double* s = sj.ST + (size_t)b * sj.st_stride;
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
 #pragma unroll
         for (int j = i; j < NX; ++j) v.S(i, j) = 0.5 * (s[i * NX + j] + s[j * NX + i]);
-        v.v(i) = (vT != nullptr) ? vT[(size_t)b * NX + i] : 0.0;
+        v.v(i) = (sj.vT != nullptr) ? sj.vT[(size_t)b * NX + i] : 0.0;
     }
-    soa_store(v, seed, (size_t)batch, (size_t)b);
+    soa_store(v, sj.seed, (size_t)sj.batch, (size_t)b);
+}
+
+// Terminal value function per problem -> SoA seed (stride = batch).
+// ST: full (nx,nx) matrix at ST + b*st_stride (symmetrised), vT at vT + b*nx (NULL = 0).
+template <int NX>
+__global__ void k_ric_seed(SeedJob sj) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < sj.batch) make_ric_seed<NX>(sj, b);
 }
 
 // ------------------------------------------------------------------ K2 leaf kernels
@@ -684,8 +696,10 @@ __global__ void k_ric_seed(const double* __restrict__ ST, size_t st_stride,
 template <int NX, int NU, class Loader>
 __global__ void __launch_bounds__(kLeafThreads, IPOC_RIC_MINB)
 k_ric_leaf_up(Loader ld, Geom g, double* __restrict__ incl, size_t istride, double* __restrict__ agg1,
-              size_t a1stride) {
+              size_t a1stride, SeedJob sj) {
     extern __shared__ __align__(16) char smem[];
+    if (sj.ST != nullptr && blockIdx.x == 0)
+        for (int b = threadIdx.x; b < sj.batch; b += blockDim.x) make_ric_seed<NX>(sj, b);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     if (wg >= total_warps(g)) return;
@@ -1239,14 +1253,15 @@ static void leaf_values(const Plan& p, const ScanWs& w, const double*& vals, siz
 
 // ---- K2 (+K3 aggregates) for any loader ---------------------------------------------------
 template <int NX, int NU, class Loader>
-static int run_bwd_up(const Plan& p, const NewtonWs& w, const Loader& ld, cudaStream_t st) {
+static int run_bwd_up(const Plan& p, const NewtonWs& w, const Loader& ld, cudaStream_t st,
+                      SeedJob sj = SeedJob{nullptr, 0, nullptr, 0, nullptr, nullptr}) {
     const LeafLaunch ll = leaf_launch(p, Loader::STAGE_BYTES, scan_scratch_bytes<RicOp<NX>>(), IPOC_NS_RIC_UP);
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_ric_leaf_up<NX, NU, Loader>;
     if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.ric.incl, (size_t)p.slots, w.ric.agg[0],
-                                              (size_t)p.g.batch * p.g.nW);
+                                              (size_t)p.g.batch * p.g.nW, sj);
     IPOC_LAUNCH_CHECK_N("k_ric_leaf_up", st);
     return IPOC_OK;
 }
@@ -1278,9 +1293,12 @@ static int run_bwd_down(const Plan& p, const NewtonWs& w, const Loader& ld, doub
 
 template <int NX, int NU, class Loader>
 static int run_bwd(const Plan& p, const NewtonWs& w, const Loader& ld, double* Kx, double* d, double* S, double* v,
-                   double* pred, int32_t* feasible, bool want_fwd_agg, cudaStream_t st, bool defer_pred = false) {
-    if (!p.g.per_lane) {
-        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st)) return rc;
+                   double* pred, int32_t* feasible, bool want_fwd_agg, cudaStream_t st, bool defer_pred, SeedJob sj) {
+    if (p.g.per_lane) {   // no up-sweep to piggy-back on
+        k_ric_seed<NX><<<grid_for(sj.batch, 128), 128, 0, st>>>(sj);
+        IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
+    } else {
+        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st, sj)) return rc;
         if (p.nlev > 0)
             if (int rc = run_levels<RicOp<NX>>(p, w.ric, false, false, st)) return rc;
     }
@@ -1319,17 +1337,15 @@ static int newton_step_impl(int N, int batch, const double* fx, const double* fu
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     // terminal value function: XT = Q[0], HT = I, rT = 0 (ref noc/par_interior_point_newton.py:73-75);
     // zero initial deviation dx_0 = 0 (:122) — both seeds in one launch
-    k_ric_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(Q, (size_t)N * NX * NX, nullptr, batch, w.ric.seed,
-                                                        w.aff.seed);
-    IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
+    const SeedJob sj{Q, (size_t)N * NX * NX, nullptr, batch, w.ric.seed, w.aff.seed};
     // the pred / feasibility partials are folded by K3's top scan when there is one
     const bool defer = p.nlev > 0;
     if (g_literal_lqt) {
         NewtonLoader<NX, NU, true> ld{fx, fu, ru, Q, R, M, reg};
-        if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer)) return rc;
+        if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer, sj)) return rc;
     } else {
         NewtonLoader<NX, NU, false> ld{fx, fu, ru, Q, R, M, reg};
-        if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer)) return rc;
+        if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer, sj)) return rc;
     }
     PredJob pj{nullptr, nullptr, 0, nullptr, nullptr};
     if (defer) pj = PredJob{w.pred_part, w.feas_part, p.g.nW, pred, feasible};
@@ -1346,10 +1362,9 @@ static int lqt_bwd_impl(int N, int batch, const double* A, const double* B, cons
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
-    k_ric_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(ST, (size_t)NX * NX, vT, batch, w.ric.seed, nullptr);
-    IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
+    const SeedJob sj{ST, (size_t)NX * NX, vT, batch, w.ric.seed, nullptr};
     LqtLoader<NX, NU> ld{A, B, c, X, U, M, q, pp};
-    return run_bwd<NX, NU>(p, w, ld, Kx, d, S, v, pred, feasible, false, st);
+    return run_bwd<NX, NU>(p, w, ld, Kx, d, S, v, pred, feasible, false, st, false, sj);
 }
 
 template <int NX, int NU>
@@ -1494,7 +1509,7 @@ static int newton_bwd_apply_impl(int N, int rank, int nranks, const double* fx, 
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     // terminal seed of the whole horizon, pushed back through the later ranks' aggregates
     double* seed0 = w.scratch;   // RicVal packed
-    k_ric_seed<NX><<<1, 32, 0, st>>>(ST, (size_t)NX * NX, nullptr, 1, seed0, nullptr);
+    k_ric_seed<NX><<<1, 32, 0, st>>>(SeedJob{ST, (size_t)NX * NX, nullptr, 1, seed0, nullptr});
     IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
     k_chain_seed<RicOp<NX>><<<1, 32, 0, st>>>(carries, nranks - 1, -1, nranks - 1 - rank, seed0, w.ric.seed);
     IPOC_LAUNCH_CHECK_N("k_chain_seed_ric", st);
