@@ -209,6 +209,32 @@ int ipoc_newton_step_host_f64(int N, int nx, int nu, int batch,
                               double* dx, double* du, double* pred, int32_t* feasible,
                               void* dws, size_t dws_bytes, ipoc_stream_t stream);
 
+/* ---- optional built-in plants (SURVEY §8f "next" #4) -------------------------------------------
+ * Fused evaluation of the user functions of the reference's two example problems
+ * (ref examples/pendulum_runtime.py:19-72, examples/cartpole_runtime.py:18-81; dynamics =
+ * euler(ode, Ts), stage cost with log barrier on |u| <= bound), as a fast path BESIDE the host
+ * framework's autodiff (which remains the general path for user-defined OCPs):
+ *   ipoc_plant_derivatives_f64: the ten `Derivatives` tensors of ref noc/optimal_control_problem.py:13-23
+ *       (what ref noc/par_interior_point_newton.py:13-28 gets from vmapped grad/hessian/jacrev) via
+ *       second-order forward-mode autodiff in registers, plus lamT = grad final_cost(x_N) (may be NULL).
+ *       x (batch,N+1,nx), u (batch,N,nu), bp = device scalar.
+ *   ipoc_plant_cost_f64: total_cost (ref examples/cartpole_runtime.py:48-51) and all(constraints<=0)
+ *       (ref noc/par_interior_point_newton.py:45-47) per problem, fixed summation order.
+ *   ipoc_plant_rollout_f64: serial rollout (ref noc/utils.py:57-63), one thread per problem.
+ */
+enum { IPOC_PLANT_PENDULUM = 1, IPOC_PLANT_CARTPOLE = 2 };
+int ipoc_plant_dims(int plant, int* nx, int* nu, int* nc);
+int ipoc_plant_derivatives_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
+                               const double* x, const double* u,
+                               double* cx, double* cu, double* cxx, double* cuu, double* cxu,
+                               double* fx, double* fu, double* fxx, double* fuu, double* fxu, double* lamT,
+                               ipoc_stream_t stream);
+int ipoc_plant_cost_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
+                        const double* x, const double* u, double* total_cost, int32_t* feasible,
+                        ipoc_stream_t stream);
+int ipoc_plant_rollout_f64(int plant, int N, int batch, double Ts, const double* x0, const double* u,
+                           double* x, ipoc_stream_t stream);
+
 /* Number of kernels the library has launched since load (for launch accounting in bench.py). */
 unsigned long long ipoc_launch_count(void);
 

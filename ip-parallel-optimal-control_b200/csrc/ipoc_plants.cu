@@ -1,0 +1,299 @@
+// Optional fast path for the reference's two example plants (SURVEY.md §8f "next" #4): the per-time-step
+// `Derivatives` (ref noc/optimal_control_problem.py:13-23), the total cost / feasibility of a trajectory
+// and the serial rollout, as fused kernels.  Derivatives come from second-order forward-mode autodiff in
+// registers (ipoc_jet.cuh) applied to the plant written ONCE as a template — the same expressions, in the
+// same order, as the example scripts (ref examples/pendulum_runtime.py:19-72, cartpole_runtime.py:18-81).
+// User-defined OCPs keep going through the host framework's autodiff; this path only serves OCPs built by
+// ipoc_b200.problems.make_pendulum / make_cartpole and is cross-checked against torch.func in the tests.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/ipoc.h"
+#include "ipoc_jet.cuh"
+
+namespace ipoc {
+
+extern unsigned long long g_launches;
+void prof_mark(const char* name, cudaStream_t st);
+
+struct PlantParams {
+    double Ts, bound;
+};
+
+// ---------------------------------------------------------------- pendulum (nx=2, nu=1, nc=2)
+struct Pendulum {
+    static constexpr int NX = 2, NU = 1, NC = 2;
+    template <class T>
+    __device__ __forceinline__ static void ode(const T (&x)[NX], const T (&u)[NU], T (&out)[NX]) {
+        const double gravity = 9.81, length = 1.0, mass = 1.0, damping = 1e-3;
+        out[0] = x[1];
+        out[1] = (-gravity / length) * jsin(x[0]) + (u[0] - damping * x[1]) / (mass * length * length);
+    }
+    template <class T>
+    __device__ __forceinline__ static T state_cost(const T (&x)[NX]) {
+        const double pi = 3.141592653589793;
+        const T e0 = jwrap(x[0]) - pi, e1 = x[1] - 0.0;
+        return (0.5 * e0) * 1e0 * e0 + (0.5 * e1) * 1e-1 * e1;
+    }
+};
+
+// ---------------------------------------------------------------- cartpole (nx=4, nu=1, nc=2)
+struct Cartpole {
+    static constexpr int NX = 4, NU = 1, NC = 2;
+    template <class T>
+    __device__ __forceinline__ static void ode(const T (&x)[NX], const T (&u)[NU], T (&out)[NX]) {
+        const double gravity = 9.81, pole_length = 0.5, cart_mass = 10.0, pole_mass = 1.0;
+        const double total_mass = cart_mass + pole_mass;
+        const T sth = jsin(x[1]), cth = jcos(x[1]);
+        const T w2 = x[3] * x[3];
+        out[0] = x[2];
+        out[1] = x[3];
+        out[2] = (u[0] + (pole_mass * sth) * (pole_length * w2 + gravity * cth)) / (cart_mass + pole_mass * (sth * sth));
+        out[3] = (-u[0] * cth - (((pole_mass * pole_length) * w2) * cth) * sth - (total_mass * gravity) * sth) /
+                 (pole_length * cart_mass + (pole_length * pole_mass) * (sth * sth));
+    }
+    template <class T>
+    __device__ __forceinline__ static T state_cost(const T (&x)[NX]) {
+        const double pi = 3.141592653589793;
+        const T e0 = x[0] - 0.0, e1 = jwrap(x[1]) - pi, e2 = x[2] - 0.0, e3 = x[3] - 0.0;
+        return (0.5 * e0) * 1e0 * e0 + (0.5 * e1) * 1e1 * e1 + (0.5 * e2) * 1e-1 * e2 + (0.5 * e3) * 1e-1 * e3;
+    }
+};
+
+// stage cost = state cost + 1/2 u' (1e-3) u - bp * sum log(-constraints),  constraints = (u - ub, -u - ub)
+template <class P, class T>
+__device__ __forceinline__ T stage_cost(const T (&x)[P::NX], const T (&u)[P::NU], double bp, double ub) {
+    T c = P::state_cost(x) + (0.5 * u[0]) * 1e-3 * u[0];
+    const T m0 = -(u[0] - ub), m1 = -(-u[0] - ub);
+    return c - bp * (jlog(m0) + jlog(m1));
+}
+
+// ---------------------------------------------------------------- derivatives
+// one thread per (problem, time step); variables z = (x, u)
+template <class P>
+__global__ void __launch_bounds__(128)
+k_plant_derivs(PlantParams pp, const double* __restrict__ bp_ptr, int N, int batch,
+               const double* __restrict__ X, const double* __restrict__ U,
+               double* __restrict__ cx, double* __restrict__ cu, double* __restrict__ cxx, double* __restrict__ cuu,
+               double* __restrict__ cxu, double* __restrict__ fx, double* __restrict__ fu, double* __restrict__ fxx,
+               double* __restrict__ fuu, double* __restrict__ fxu, double* __restrict__ lamT) {
+    constexpr int NX = P::NX, NU = P::NU, NV = NX + NU;
+    using J = Jet<NV>;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * N) return;
+    const int b = (int)(g / N), k = (int)(g % N);
+    const double bp = *bp_ptr;
+    const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
+    const double* up = U + (size_t)g * NU;
+    J x[NX], u[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = J::var(xp[i], i);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) u[a] = J::var(up[a], NX + a);
+    {   // dynamics: euler(ode, Ts)  (ref noc/utils.py:50-54)
+        J o[NX];
+        P::ode(x, u, o);
+#pragma unroll
+        for (int r = 0; r < NX; ++r) {
+            const J f = x[r] + pp.Ts * o[r];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                fx[((size_t)g * NX + r) * NX + i] = f.g[i];
+#pragma unroll
+                for (int j = 0; j < NX; ++j) fxx[(((size_t)g * NX + r) * NX + i) * NX + j] = f.hess(i, j);
+#pragma unroll
+                for (int a = 0; a < NU; ++a) fxu[(((size_t)g * NX + r) * NX + i) * NU + a] = f.hess(i, NX + a);
+            }
+#pragma unroll
+            for (int a = 0; a < NU; ++a) {
+                fu[((size_t)g * NX + r) * NU + a] = f.g[NX + a];
+#pragma unroll
+                for (int c = 0; c < NU; ++c) fuu[(((size_t)g * NX + r) * NU + a) * NU + c] = f.hess(NX + a, NX + c);
+            }
+        }
+    }
+    {   // stage cost
+        const J c = stage_cost<P, J>(x, u, bp, pp.bound);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            cx[(size_t)g * NX + i] = c.g[i];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) cxx[((size_t)g * NX + i) * NX + j] = c.hess(i, j);
+#pragma unroll
+            for (int a = 0; a < NU; ++a) cxu[((size_t)g * NX + i) * NU + a] = c.hess(i, NX + a);
+        }
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+            cu[(size_t)g * NU + a] = c.g[NX + a];
+#pragma unroll
+            for (int cc = 0; cc < NU; ++cc) cuu[((size_t)g * NU + a) * NU + cc] = c.hess(NX + a, NX + cc);
+        }
+    }
+    if (k == N - 1 && lamT != nullptr) {   // lambda_N = grad final_cost(x_N)  (ref noc/costates.py:35)
+        const double* xn = X + ((size_t)b * (N + 1) + N) * NX;
+        J xe[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xe[i] = J::var(xn[i], i);
+        const J c = P::state_cost(xe);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) lamT[(size_t)b * NX + i] = c.g[i];
+    }
+}
+
+// ---------------------------------------------------------------- total cost + feasibility
+// total_cost = final_cost(x_N) + sum_k stage_cost(x_k, u_k, bp); feasible = all(constraints <= 0).
+// One CTA of 1024 threads per problem; fixed summation order (thread-strided partials, shuffle trees).
+template <class P>
+__global__ void __launch_bounds__(1024)
+k_plant_cost(PlantParams pp, const double* __restrict__ bp_ptr, int N, const double* __restrict__ X,
+             const double* __restrict__ U, double* __restrict__ total, int32_t* __restrict__ feasible) {
+    constexpr int NX = P::NX, NU = P::NU;
+    __shared__ double s_sum[32];
+    __shared__ int s_ok[32];
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const double bp = *bp_ptr;
+    double acc = 0.0;
+    int ok = 1;
+    for (int k = t; k < N; k += 1024) {
+        double x[NX], u[NU];
+        const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = xp[i];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) u[a] = U[((size_t)b * N + k) * NU + a];
+        acc += stage_cost<P, double>(x, u, bp, pp.bound);
+        ok &= ((u[0] - pp.bound) <= 0.0 && (-u[0] - pp.bound) <= 0.0) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+    }
+    if (lane == 0) {
+        s_sum[w] = acc;
+        s_ok[w] = ok;
+    }
+    __syncthreads();
+    if (w == 0) {
+        acc = s_sum[lane];
+        ok = s_ok[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+        }
+        if (lane == 0) {
+            double xn[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) xn[i] = X[((size_t)b * (N + 1) + N) * NX + i];
+            total[b] = P::state_cost(xn) + acc;
+            feasible[b] = ok;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- serial rollout, one thread per problem
+template <class P>
+__global__ void k_plant_rollout(PlantParams pp, int N, int batch, const double* __restrict__ x0,
+                                const double* __restrict__ U, double* __restrict__ X) {
+    constexpr int NX = P::NX, NU = P::NU;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    double x[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = x0[(size_t)b * NX + i];
+    double* xo = X + (size_t)b * (N + 1) * NX;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xo[i] = x[i];
+    for (int k = 0; k < N; ++k) {
+        double u[NU], o[NX];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) u[a] = U[((size_t)b * N + k) * NU + a];
+        P::ode(x, u, o);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            x[i] = x[i] + pp.Ts * o[i];
+            xo[(size_t)(k + 1) * NX + i] = x[i];
+        }
+    }
+}
+
+#define PLANT_CHECK(st)                                              \
+    do {                                                             \
+        ++g_launches;                                                \
+        prof_mark(__func__, st);                                     \
+        if (cudaPeekAtLastError() != cudaSuccess) return IPOC_ECUDA; \
+    } while (0)
+
+template <class P>
+static int derivs_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U, double* cx,
+                       double* cu, double* cxx, double* cuu, double* cxu, double* fx, double* fu, double* fxx,
+                       double* fuu, double* fxu, double* lamT, cudaStream_t st) {
+    const long long n = (long long)N * batch;
+    k_plant_derivs<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pp, bp, N, batch, X, U, cx, cu, cxx, cuu, cxu, fx, fu,
+                                                                 fxx, fuu, fxu, lamT);
+    PLANT_CHECK(st);
+    return IPOC_OK;
+}
+template <class P>
+static int cost_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
+                     double* total, int32_t* feasible, cudaStream_t st) {
+    k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible);
+    PLANT_CHECK(st);
+    return IPOC_OK;
+}
+template <class P>
+static int rollout_impl(PlantParams pp, int N, int batch, const double* x0, const double* U, double* X,
+                        cudaStream_t st) {
+    k_plant_rollout<P><<<(batch + 31) / 32, 32, 0, st>>>(pp, N, batch, x0, U, X);
+    PLANT_CHECK(st);
+    return IPOC_OK;
+}
+
+}  // namespace ipoc
+
+using namespace ipoc;
+
+extern "C" {
+
+int ipoc_plant_dims(int plant, int* nx, int* nu, int* nc) {
+    if (plant == IPOC_PLANT_PENDULUM) { *nx = Pendulum::NX; *nu = Pendulum::NU; *nc = Pendulum::NC; return IPOC_OK; }
+    if (plant == IPOC_PLANT_CARTPOLE) { *nx = Cartpole::NX; *nu = Cartpole::NU; *nc = Cartpole::NC; return IPOC_OK; }
+    return IPOC_EINVAL;
+}
+
+int ipoc_plant_derivatives_f64(int plant, int N, int batch, double Ts, double bound, const double* bp, const double* x,
+                               const double* u, double* cx, double* cu, double* cxx, double* cuu, double* cxu,
+                               double* fx, double* fu, double* fxx, double* fuu, double* fxu, double* lamT,
+                               ipoc_stream_t stream) {
+    if (N < 1 || batch < 1 || !bp || !x || !u || !cx || !cu || !cxx || !cuu || !cxu || !fx || !fu || !fxx || !fuu || !fxu)
+        return IPOC_EINVAL;
+    const PlantParams pp{Ts, bound};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plant == IPOC_PLANT_PENDULUM)
+        return derivs_impl<Pendulum>(pp, bp, N, batch, x, u, cx, cu, cxx, cuu, cxu, fx, fu, fxx, fuu, fxu, lamT, st);
+    if (plant == IPOC_PLANT_CARTPOLE)
+        return derivs_impl<Cartpole>(pp, bp, N, batch, x, u, cx, cu, cxx, cuu, cxu, fx, fu, fxx, fuu, fxu, lamT, st);
+    return IPOC_EINVAL;
+}
+
+int ipoc_plant_cost_f64(int plant, int N, int batch, double Ts, double bound, const double* bp, const double* x,
+                        const double* u, double* total_cost, int32_t* feasible, ipoc_stream_t stream) {
+    if (N < 1 || batch < 1 || !bp || !x || !u || !total_cost || !feasible) return IPOC_EINVAL;
+    const PlantParams pp{Ts, bound};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plant == IPOC_PLANT_PENDULUM) return cost_impl<Pendulum>(pp, bp, N, batch, x, u, total_cost, feasible, st);
+    if (plant == IPOC_PLANT_CARTPOLE) return cost_impl<Cartpole>(pp, bp, N, batch, x, u, total_cost, feasible, st);
+    return IPOC_EINVAL;
+}
+
+int ipoc_plant_rollout_f64(int plant, int N, int batch, double Ts, const double* x0, const double* u, double* x,
+                           ipoc_stream_t stream) {
+    if (N < 1 || batch < 1 || !x0 || !u || !x) return IPOC_EINVAL;
+    const PlantParams pp{Ts, 0.0};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plant == IPOC_PLANT_PENDULUM) return rollout_impl<Pendulum>(pp, N, batch, x0, u, x, st);
+    if (plant == IPOC_PLANT_CARTPOLE) return rollout_impl<Cartpole>(pp, N, batch, x0, u, x, st);
+    return IPOC_EINVAL;
+}
+
+}  // extern "C"

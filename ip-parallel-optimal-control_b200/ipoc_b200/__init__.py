@@ -12,6 +12,6 @@ from .noc import (compute_derivatives, compute_lqr_params, check_traj_feasibilit
                   par_costates, par_Newton, newton_oc, par_interior_point_optimal_control,
                   newton_step, affine_scan, reductions, accept_update)
 from .utils import wrap_angle, euler, discretize_dynamics, rollout, rollout_parallel, runge_kutta  # noqa: F401
-from . import problems  # noqa: F401
+from . import problems, plants  # noqa: F401
 
 __version__ = "0.1.0"

@@ -16,6 +16,7 @@ from torch.func import vmap, grad, hessian, jacrev
 from . import _lib as L
 from .optimal_control_problem import OCP, Derivatives
 from .noc import reductions, newton_step, accept_update, affine_scan
+from . import plants
 
 
 def rollout_batched(dynamics, controls, initial_states):
@@ -63,7 +64,11 @@ def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
     -> (x (B,N+1,nx), u (B,N,nu), iterations (B,) int64)"""
     dev = controls.device
     u = L.dev_f64(controls)
-    x = rollout_batched(ocp.dynamics, u, initial_states.to(dev))                   # :133
+    plant = plants.plant_of(ocp)
+    if plant is not None:
+        x = plants.rollout(plant, u, initial_states.to(dev))                       # :133
+    else:
+        x = rollout_batched(ocp.dynamics, u, initial_states.to(dev))
     B = u.shape[0]
     o = dict(dtype=torch.float64, device=dev)
     rp = torch.ones(B, **o)                                                        # :134
@@ -75,9 +80,14 @@ def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
     lamT_fn = vmap(grad(ocp.final_cost))
     active = torch.ones(B, dtype=torch.bool, device=dev)                           # members still in the Newton loop
     while bool(active.any()):                                                      # :199-202 (per member)
-        cost = total_cost(x, u, barrier_param)                                     # :142
-        d = compute_derivatives_batched(ocp, x, u, barrier_param)                  # :145
-        lam = affine_scan(d.fx, d.cx, lamT_fn(x[:, -1]), reverse=True, transpose=True)   # :147
+        if plant is not None:
+            d, lamT = plants.derivatives(plant, x, u, barrier_param)               # :145
+            cost, _ = plants.cost(plant, x, u, barrier_param)                      # :142
+        else:
+            cost = total_cost(x, u, barrier_param)
+            d = compute_derivatives_batched(ocp, x, u, barrier_param)
+            lamT = lamT_fn(x[:, -1])
+        lam = affine_scan(d.fx, d.cx, lamT, reverse=True, transpose=True)          # :147
         ru, Q, R, M = compute_lqr_params_batched(lam, d)                           # :149
         hu, cu_norm, _ = reductions(ru=ru, cu=d.cu)                                # :158, :116
         inner = torch.zeros(B, dtype=torch.int64, device=dev)
@@ -86,9 +96,12 @@ def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
         while bool(act_in.any()):                                                  # :177-182 (per member)
             dx, du, _, _, pred, bwd_feas = newton_step(d.fx, d.fu, ru, Q, R, M, rp * cu_norm)   # :153
             cx_try, cu_try = x + dx, u + du                                        # :156-157
-            cons = cons_fn(cx_try[:, :-1], cu_try)
-            _, _, traj_feas = reductions(cons=cons.reshape(B, cons.shape[1], -1))  # :160
-            new_cost = total_cost(cx_try, cu_try, barrier_param)                   # :161
+            if plant is not None:
+                new_cost, traj_feas = plants.cost(plant, cx_try, cu_try, barrier_param)   # :160-161
+            else:
+                cons = cons_fn(cx_try[:, :-1], cu_try)
+                _, _, traj_feas = reductions(cons=cons.reshape(B, cons.shape[1], -1))
+                new_cost = total_cost(cx_try, cu_try, barrier_param)
             succ, _ = accept_update(cost, new_cost.contiguous(), traj_feas, pred, bwd_feas, rp, r_inc,
                                     active=act_in.to(torch.int32))                 # :159-173, active members only
             m = act_in.view(B, 1, 1)

@@ -35,10 +35,8 @@ class GraphedNewton:
 
     # ---- loop bodies (same statements as noc.newton_oc) ------------------------------------------------
     def _iteration(self):
-        ocp = self.ocp
-        self.cost = ocp.total_cost(self.x, self.u, self.bp).reshape(1)             # :142
-        self.d = noc.compute_derivatives(ocp, self.x, self.u, self.bp)             # :145
-        lam = noc.par_costates(ocp, self.x[-1], self.d)                            # :147
+        self.cost, self.d, lamT = noc.eval_iteration(self.ocp, self.x, self.u, self.bp)   # :142, :145
+        lam = noc.affine_scan(self.d.fx, self.d.cx, lamT, reverse=True, transpose=True)   # :147
         self.ru, self.Q, self.R, self.M = noc.compute_lqr_params(lam, self.d)      # :149
         self.hu, self.cu_norm, _ = noc.reductions(ru=self.ru, cu=self.d.cu)        # :158, :116
 
@@ -48,9 +46,7 @@ class GraphedNewton:
                                                        self.rp * self.cu_norm)     # :153
         self.tu = self.u + du                                                      # :156
         self.tx = self.x + dx                                                      # :157
-        cons = vmap(ocp.constraints)(self.tx[:-1], self.tu)                        # :160
-        _, _, traj_feas = noc.reductions(cons=cons.reshape(cons.shape[0], -1))
-        new_cost = ocp.total_cost(self.tx, self.tu, self.bp).reshape(1)            # :161
+        new_cost, traj_feas = noc.eval_trial(ocp, self.tx, self.tu, self.bp)       # :159-163
         succ, gain = noc.accept_update(self.cost, new_cost, traj_feas, pred, bwd_feas, self.rp, self.r_inc)
         self.rec = torch.stack((succ[0].to(torch.float64), self.hu[0], new_cost[0], pred[0], gain[0]))
 
@@ -96,8 +92,9 @@ _CACHE_MAX = 8
 
 def get(ocp: OCP, N, nx, nu, device, x, u, bp):
     """Captured bodies for this problem/horizon (cached on the identity of the OCP's callables)."""
+    from . import plants
     key = (id(ocp.dynamics), id(ocp.stage_cost), id(ocp.final_cost), id(ocp.constraints), id(ocp.total_cost),
-           N, nx, nu, str(device))
+           N, nx, nu, str(device), plants.ENABLED)
     g = _cache.get(key)
     if g is None:
         g = GraphedNewton(ocp, N, nx, nu, device)

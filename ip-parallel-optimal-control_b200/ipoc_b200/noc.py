@@ -16,6 +16,7 @@ from . import _lib as L
 from .optimal_control_problem import OCP, Derivatives
 from .paroc import LQT, par_bwd_pass, par_fwd_pass  # noqa: F401  (re-exported, as the reference imports them)
 from .utils import rollout, rollout_parallel
+from . import plants
 
 
 # ------------------------------------------------------------------ A1: derivatives (host framework)
@@ -169,6 +170,42 @@ def par_Newton(nominal_states, d: Derivatives, reg_param, ru, Q, R, M):
     return dx, du, pred[0], feas[0] != 0, ru
 
 
+# ------------------------------------------------------------------ user-function evaluation of one iteration / trial
+def eval_iteration(ocp: OCP, x, u, bp):
+    """cost (1,), Derivatives, lambda_N for the current iterate — ref :142, :145, costates.py:35.
+    Host-framework autodiff in general; one fused kernel each for the built-in plants (plants.py)."""
+    plant = plants.plant_of(ocp)
+    if plant is not None:
+        d, lamT = plants.derivatives(plant, x, u, bp)
+        cost, _ = plants.cost(plant, x, u, bp)
+        return cost, d, lamT
+    cost = ocp.total_cost(x, u, bp).reshape(1)
+    d = compute_derivatives(ocp, x, u, bp)
+    return cost, d, grad(ocp.final_cost)(x[-1])
+
+
+def eval_trial(ocp: OCP, tx, tu, bp):
+    """new cost (1,) and trajectory feasibility (1,) int32 of a trial iterate — ref :159-163."""
+    plant = plants.plant_of(ocp)
+    if plant is not None:
+        return plants.cost(plant, tx, tu, bp)
+    cons = vmap(ocp.constraints)(tx[:-1], tu)                            # :160
+    _, _, traj_feas = reductions(cons=cons.reshape(cons.shape[0], -1))
+    return ocp.total_cost(tx, tu, bp).reshape(1), traj_feas              # :161 (masked to inf by A8)
+
+
+def initial_rollout(ocp: OCP, u, initial_state, parallel_rollout_from=2000):
+    """states of the nominal rollout (ref :133): device kernel for the built-in plants, the parallel
+    Newton-on-the-rollout scan for long horizons, else the serial host loop."""
+    plant = plants.plant_of(ocp)
+    N = u.shape[0]
+    if plant is not None and N <= 20000:
+        return plants.rollout(plant, u, initial_state.to(u.device))
+    if N >= parallel_rollout_from:
+        return rollout_parallel(ocp.dynamics, u, initial_state.to(u.device))[0]
+    return rollout(ocp.dynamics, u, initial_state.to(u.device))
+
+
 # ------------------------------------------------------------------ driver loops
 def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, barrier_param: float, trace=None,
               stage: int = 0, use_graphs: bool = True, parallel_rollout_from: int = 2000):
@@ -179,12 +216,7 @@ def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, bar
     sequence of statements."""
     dev = controls.device
     u = L.dev_f64(controls)
-    if u.shape[0] >= parallel_rollout_from:
-        # same states as the serial rollout (its fixed point), computed with the forward scan kernel;
-        # the serial Python loop would dominate the solve time at long horizons
-        x, _ = rollout_parallel(ocp.dynamics, u, initial_state.to(dev))
-    else:
-        x = rollout(ocp.dynamics, u, initial_state.to(dev))             # :133
+    x = initial_rollout(ocp, u, initial_state, parallel_rollout_from)   # :133
     if use_graphs:
         from . import graphed
         g = graphed.get(ocp, u.shape[0], x.shape[1], u.shape[1], dev, x, u, barrier_param)
@@ -195,9 +227,8 @@ def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, bar
     r_inc = torch.full((1,), 2.0, **o)                                   # :135
     iteration, Hu_norm = 0, 1.0
     while not (Hu_norm < 1e-4 or iteration > 1000):                      # :199-202
-        cost = ocp.total_cost(x, u, barrier_param).reshape(1)            # :142
-        d = compute_derivatives(ocp, x, u, barrier_param)                # :145
-        lam = par_costates(ocp, x[-1], d)                                # :147
+        cost, d, lamT = eval_iteration(ocp, x, u, barrier_param)         # :142, :145
+        lam = affine_scan(d.fx, d.cx, lamT, reverse=True, transpose=True)   # :147
         ru, Q, R, M = compute_lqr_params(lam, d)                         # :149
         hu, cu_norm, _ = reductions(ru=ru, cu=d.cu)                      # :158 (pre-step ru), :116
         success, inner = False, 0
@@ -206,9 +237,7 @@ def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, bar
             dx, du, _, _, pred, bwd_feas = newton_step(d.fx, d.fu, ru, Q, R, M, rp * cu_norm)   # :153
             tu = u + du                                                  # :156
             tx = x + dx                                                  # :157
-            cons = vmap(ocp.constraints)(tx[:-1], tu)                    # :160
-            _, _, traj_feas = reductions(cons=cons.reshape(cons.shape[0], -1))
-            new_cost = ocp.total_cost(tx, tu, barrier_param).reshape(1)  # :161 (masked to inf by A8)
+            new_cost, traj_feas = eval_trial(ocp, tx, tu, barrier_param)  # :159-163
             rp_before = rp.clone() if trace is not None else None
             succ, gain = accept_update(cost, new_cost, traj_feas, pred, bwd_feas, rp, r_inc)    # :159-173
             inner += 1                                                   # :174

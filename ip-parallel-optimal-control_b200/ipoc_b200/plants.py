@@ -1,0 +1,98 @@
+"""Optional fast path for the reference's two example plants (SURVEY.md §8f "next" #4).
+
+OCPs built by `problems.make_pendulum` / `problems.make_cartpole` carry a tag on their dynamics callable;
+for those the per-step `Derivatives`, the total cost / feasibility of a trajectory and the serial rollout
+are single fused kernels of libipoc.so (csrc/ipoc_plants.cu: second-order forward-mode autodiff in
+registers) instead of a few hundred host-framework kernels.  User-defined OCPs are untouched and keep going
+through `torch.func`.  Set `ENABLED = False` to force the autodiff path everywhere (the tests run both and
+compare them).
+"""
+import ctypes
+import torch
+from . import _lib as L
+from .optimal_control_problem import Derivatives
+
+ENABLED = True
+PLANT_IDS = {"pendulum": 1, "cartpole": 2}
+
+
+def tag(dynamics, name, Ts, bound):
+    dynamics._ipoc_plant = {"name": name, "id": PLANT_IDS[name], "Ts": float(Ts), "bound": float(bound)}
+    return dynamics
+
+
+def plant_of(ocp):
+    """Plant descriptor of a built-in OCP, or None (also None when the fast path is disabled)."""
+    if not ENABLED:
+        return None
+    return getattr(ocp.dynamics, "_ipoc_plant", None)
+
+
+def _bp_tensor(bp, dev):
+    if isinstance(bp, torch.Tensor):
+        return bp.to(device=dev, dtype=torch.float64).reshape(1).contiguous()
+    return torch.tensor([float(bp)], dtype=torch.float64, device=dev)
+
+
+def _dims(plant):
+    nx, nu, nc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    L.check(L.lib().ipoc_plant_dims(plant["id"], ctypes.byref(nx), ctypes.byref(nu), ctypes.byref(nc)))
+    return nx.value, nu.value, nc.value
+
+
+def derivatives(plant, states, controls, bp):
+    """-> (Derivatives, lamT): same tensors (index order (output, wrt_1, wrt_2)) as
+    `noc.compute_derivatives` + grad final_cost(x_N).  states (N+1,nx) / controls (N,nu), or batched."""
+    x, u = L.dev_f64(states), L.dev_f64(controls)
+    batched = x.dim() == 3
+    if not batched:
+        x, u = x.unsqueeze(0), u.unsqueeze(0)
+    B, N = u.shape[0], u.shape[1]
+    nx, nu, _ = _dims(plant)
+    dev = x.device
+    o = dict(dtype=torch.float64, device=dev)
+    shapes = dict(cx=(nx,), cu=(nu,), cxx=(nx, nx), cuu=(nu, nu), cxu=(nx, nu), fx=(nx, nx), fu=(nx, nu),
+                  fxx=(nx, nx, nx), fuu=(nx, nu, nu), fxu=(nx, nx, nu))
+    outs = {k: torch.empty((B, N) + sh, **o) for k, sh in shapes.items()}
+    lamT = torch.empty(B, nx, **o)
+    bpt = _bp_tensor(bp, dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().ipoc_plant_derivatives_f64(
+            plant["id"], N, B, plant["Ts"], plant["bound"], L.ptr(bpt), L.ptr(x), L.ptr(u),
+            *(L.ptr(outs[k]) for k in Derivatives._fields), L.ptr(lamT), L.stream_ptr()))
+    if not batched:
+        return Derivatives(*(outs[k][0] for k in Derivatives._fields)), lamT[0]
+    return Derivatives(*(outs[k] for k in Derivatives._fields)), lamT
+
+
+def cost(plant, states, controls, bp):
+    """-> (total_cost (B,), feasible (B,) int32) of trajectories: final cost + sum of stage costs (log barrier
+    included; NaN where infeasible, as in the reference) and all(constraints <= 0)."""
+    x, u = L.dev_f64(states), L.dev_f64(controls)
+    if x.dim() == 2:
+        x, u = x.unsqueeze(0), u.unsqueeze(0)
+    B, N = u.shape[0], u.shape[1]
+    dev = x.device
+    total = torch.empty(B, dtype=torch.float64, device=dev)
+    feas = torch.empty(B, dtype=torch.int32, device=dev)
+    bpt = _bp_tensor(bp, dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().ipoc_plant_cost_f64(plant["id"], N, B, plant["Ts"], plant["bound"], L.ptr(bpt), L.ptr(x),
+                                            L.ptr(u), L.ptr(total), L.ptr(feas), L.stream_ptr()))
+    return total, feas
+
+
+def rollout(plant, controls, initial_state):
+    """Serial rollout on the device, one thread per problem (ref noc/utils.py:57-63)."""
+    u = L.dev_f64(controls)
+    x0 = L.dev_f64(initial_state, u.device)
+    batched = u.dim() == 3
+    if not batched:
+        u, x0 = u.unsqueeze(0), x0.unsqueeze(0)
+    B, N = u.shape[0], u.shape[1]
+    nx = x0.shape[-1]
+    x = torch.empty(B, N + 1, nx, dtype=torch.float64, device=u.device)
+    with torch.cuda.device(u.device):
+        L.check(L.lib().ipoc_plant_rollout_f64(plant["id"], N, B, plant["Ts"], L.ptr(x0.contiguous()), L.ptr(u), L.ptr(x),
+                                               L.stream_ptr()))
+    return x if batched else x[0]

@@ -68,7 +68,9 @@ def make_pendulum(Ts: float, control_bound: float = 5.0) -> OCP:
         acc = -gravity / length * torch.sin(position) + (action - damping * velocity) / (mass * length ** 2)
         return torch.hstack((velocity, acc))
 
-    return OCP(euler(ode, Ts), constraints, stage_cost, final_cost, total_cost)
+    from . import plants
+    return OCP(plants.tag(euler(ode, Ts), "pendulum", Ts, control_bound), constraints, stage_cost, final_cost,
+               total_cost)
 
 
 def pendulum_x0(dtype=torch.float64, device="cpu"):
@@ -109,7 +111,9 @@ def make_cartpole(Ts: float, control_bound: float = 50.0) -> OCP:
                     - total_mass * gravity * sth) / (pole_length * cart_mass + pole_length * pole_mass * sth ** 2)
         return torch.hstack((cart_velocity, pole_velocity, cart_acc, pole_acc))
 
-    return OCP(euler(ode, Ts), constraints, stage_cost, final_cost, total_cost)
+    from . import plants
+    return OCP(plants.tag(euler(ode, Ts), "cartpole", Ts, control_bound), constraints, stage_cost, final_cost,
+               total_cost)
 
 
 def cartpole_x0(dtype=torch.float64, device="cpu"):

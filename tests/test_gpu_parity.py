@@ -28,12 +28,14 @@ def N_(t):
 
 @pytest.fixture(autouse=True)
 def _reset_tuning():
-    from ipoc_b200 import _lib
+    from ipoc_b200 import _lib, plants
     _lib.lib().ipoc_set_tuning(0, 0, 0)
     _lib.lib().ipoc_set_literal_lqt(0)
+    plants.ENABLED = True
     yield
     _lib.lib().ipoc_set_tuning(0, 0, 0)
     _lib.lib().ipoc_set_literal_lqt(0)
+    plants.ENABLED = True
 
 
 def oracle_newton(fx, fu, ru, Q, R, M, reg):
@@ -428,6 +430,48 @@ def test_host_buffer_entry_point_and_error_codes():
     assert call(5, 1 << 20, dp(dev[0])) == -1                  # IPOC_EUNSUPPORTED_DIM
     assert call(nx, 1 << 20, ctypes.c_void_p(dev[0].data_ptr() + 8)) == -6   # IPOC_EALIGN
     assert b"workspace" in L.ipoc_strerror(-2)
+
+
+@pytest.mark.parametrize("name", STEP_FIXTURES)
+def test_plant_kernels_vs_reference_fixtures(golden, name):
+    """Built-in plant kernels (in-register forward-mode autodiff, cost, rollout) against the values the
+    reference's own definitions produced (golden fixtures) and against the host-framework autodiff."""
+    from ipoc_b200 import noc, problems, plants
+    g = golden(name)
+    N = g["controls"].shape[0]
+    ocp = problems.make_pendulum(1.0 / N) if "pendulum" in name else problems.make_cartpole(1.0 / N)
+    plant = plants.plant_of(ocp)
+    assert plant is not None
+    x, u, bp = T(g["states"]), T(g["controls"]), float(g["bp"])
+    d, lamT = plants.derivatives(plant, x, u, bp)
+    for f in d._fields:
+        ref = g["d_" + f]
+        assert N_(getattr(d, f)).shape == ref.shape, f
+        assert np.max(np.abs(N_(getattr(d, f)) - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref))), f
+    assert relerr(N_(lamT), g["ref_lamT"]) < 1e-13
+    cost, feas = plants.cost(plant, x, u, bp)
+    assert abs(float(cost) - float(g["ref_cost"])) <= 1e-12 * abs(float(g["ref_cost"])) and bool(feas[0])
+    if "warm" not in name:
+        xr = plants.rollout(plant, u, T(g["x0"]))
+        assert relerr(N_(xr), g["states"]) < 1e-13
+    # batched call == per-problem call
+    xb, ub = torch.stack((x, x)), torch.stack((u, u * 0.5))
+    db, _ = plants.derivatives(plant, xb, ub, bp)
+    assert torch.equal(db.fxx[0], d.fxx) and torch.equal(db.cuu[0], d.cuu)
+
+
+@pytest.mark.parametrize("name", ["solve_pendulum_N100", "solve_cartpole_N40"])
+def test_full_solve_with_autodiff_path(golden, name):
+    """The general (host-framework autodiff) path, with the plant kernels switched off, still reproduces the
+    reference driver's iterate and iteration count."""
+    from ipoc_b200 import noc, problems, plants
+    plants.ENABLED = False
+    g = golden(name)
+    N = g["u0"].shape[0]
+    ocp = problems.make_pendulum(1.0 / N) if "pendulum" in name else problems.make_cartpole(1.0 / N)
+    assert plants.plant_of(ocp) is None
+    u, its = noc.par_interior_point_optimal_control(ocp, T(g["u0"]), T(g["x0"]))
+    assert its == int(g["refp_iterations"]) and relerr(N_(u), g["refp_opt_u"]) < 1e-9
 
 
 def test_cpu_tensors_are_rejected():
