@@ -140,6 +140,17 @@ int ipoc_reductions_f64(int N, int nu, int nc, int batch,
                         const double* rp, double* reg,
                         void* ws, size_t ws_bytes, ipoc_stream_t stream);
 
+/* ---- A3: LQ parameters of the Newton step (optional fusion of a host-framework step) --------------
+ * Replaces `compute_lqr_params` (ref noc/par_interior_point_newton.py:31-42): with l = lam[k+1],
+ *   ru = cu + fu' l,  Q = cxx + sum_o l_o fxx[o],  R = cuu + sum_o l_o fuu[o],  M = cxu + sum_o l_o fxu[o].
+ *   in : lam (N+1,nx), cu (N,nu), cxx (N,nx,nx), cuu (N,nu,nu), cxu (N,nx,nu), fu (N,nx,nu),
+ *        fxx (N,nx,nx,nx), fuu (N,nx,nu,nu), fxu (N,nx,nx,nu)     out: ru, Q, R, M
+ */
+int ipoc_lqr_params_f64(int N, int nx, int nu, int batch, const double* lam,
+                        const double* cu, const double* cxx, const double* cuu, const double* cxu,
+                        const double* fu, const double* fxx, const double* fuu, const double* fxu,
+                        double* ru, double* Q, double* R, double* M, ipoc_stream_t stream);
+
 /* ---- A8: scalar accept / regularisation update, on device --------------------------------
  * (ref noc/par_interior_point_newton.py:159-173) for `batch` independent problems:
  *   new_cost = traj_feasible ? new_cost : inf;  rho = (new_cost - cost) / pred;

@@ -240,6 +240,44 @@ static int reduce_blocks(int N, int width, int batch) {
     return (int)(n < 1 ? 1 : n);
 }
 
+// A3: ru = cu + fu' l, Q = cxx + sum_o l_o fxx[o], R = cuu + sum_o l_o fuu[o], M = cxu + sum_o l_o fxu[o]
+// with l = lambda_{k+1} (ref noc/par_interior_point_newton.py:31-42; tensordot contracts the OUTPUT index).
+// One thread per (problem, time step); purely streaming (about 1.4 KB per step at nx = 4).
+static __global__ void __launch_bounds__(128)
+k_lqr_params(int N, int nx, int nu, int batch, const double* __restrict__ lam, const double* __restrict__ cu,
+             const double* __restrict__ cxx, const double* __restrict__ cuu, const double* __restrict__ cxu,
+             const double* __restrict__ fu, const double* __restrict__ fxx, const double* __restrict__ fuu,
+             const double* __restrict__ fxu, double* __restrict__ ru, double* __restrict__ Q,
+             double* __restrict__ R, double* __restrict__ M) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * N) return;
+    const int b = (int)(g / N), k = (int)(g % N);
+    const double* l = lam + ((size_t)b * (N + 1) + k + 1) * nx;
+    double lv[8];
+    for (int o = 0; o < nx; ++o) lv[o] = l[o];
+    for (int a = 0; a < nu; ++a) {
+        double v = cu[(size_t)g * nu + a];
+        for (int o = 0; o < nx; ++o) v += fu[((size_t)g * nx + o) * nu + a] * lv[o];
+        ru[(size_t)g * nu + a] = v;
+    }
+    const int nxx = nx * nx, nuu = nu * nu, nxu = nx * nu;
+    for (int i = 0; i < nxx; ++i) {
+        double v = cxx[(size_t)g * nxx + i];
+        for (int o = 0; o < nx; ++o) v += lv[o] * fxx[((size_t)g * nx + o) * nxx + i];
+        Q[(size_t)g * nxx + i] = v;
+    }
+    for (int i = 0; i < nuu; ++i) {
+        double v = cuu[(size_t)g * nuu + i];
+        for (int o = 0; o < nx; ++o) v += lv[o] * fuu[((size_t)g * nx + o) * nuu + i];
+        R[(size_t)g * nuu + i] = v;
+    }
+    for (int i = 0; i < nxu; ++i) {
+        double v = cxu[(size_t)g * nxu + i];
+        for (int o = 0; o < nx; ++o) v += lv[o] * fxu[((size_t)g * nx + o) * nxu + i];
+        M[(size_t)g * nxu + i] = v;
+    }
+}
+
 static __global__ void k_accept_update(int batch, const double* __restrict__ cost, const double* __restrict__ new_cost,
                                 const int32_t* __restrict__ traj_feasible, const double* __restrict__ pred,
                                 const int32_t* __restrict__ bwd_feasible, const int32_t* __restrict__ active,
@@ -399,6 +437,18 @@ int ipoc_reductions_f64(int N, int nu, int nc, int batch, const double* ru, cons
     IPOC_API_LAUNCH_CHECK(st_);
     k_reduce_final<<<batch, kRedThreads, 0, st_>>>(partials, nblk, ru != nullptr, cu != nullptr, cons != nullptr,
                                                    hu_norm, cu_norm, traj_feasible, rp, reg);
+    IPOC_API_LAUNCH_CHECK(st_);
+    return IPOC_OK;
+}
+
+int ipoc_lqr_params_f64(int N, int nx, int nu, int batch, const double* lam, const double* cu, const double* cxx,
+                        const double* cuu, const double* cxu, const double* fu, const double* fxx, const double* fuu,
+                        const double* fxu, double* ru, double* Q, double* R, double* M, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && nx >= 1 && nx <= 8 && nu >= 1 && lam && cu && cxx && cuu && cxu && fu && fxx && fuu && fxu && ru && Q && R && M);
+    cudaStream_t st_ = (cudaStream_t)stream;
+    const long long n = (long long)N * batch;
+    k_lqr_params<<<(unsigned)((n + 127) / 128), 128, 0, st_>>>(N, nx, nu, batch, lam, cu, cxx, cuu, cxu, fu, fxx, fuu, fxu,
+                                                              ru, Q, R, M);
     IPOC_API_LAUNCH_CHECK(st_);
     return IPOC_OK;
 }

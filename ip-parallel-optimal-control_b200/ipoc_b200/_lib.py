@@ -27,6 +27,7 @@ _SIGS = {
     "ipoc_affine_scan_f64": (_I, [_I] * 5 + [_P] * 4 + [_P, _SZ, _P]),
     "ipoc_reductions_f64": (_I, [_I] * 4 + [_P] * 8 + [_P, _SZ, _P]),
     "ipoc_accept_update_f64": (_I, [_I] + [_P] * 10 + [_P]),
+    "ipoc_lqr_params_f64": (_I, [_I] * 4 + [_P] * 13 + [_P]),
     "ipoc_newton_bwd_reduce_f64": (_I, [_I] * 3 + [_P] * 8 + [_P, _SZ, _P]),
     "ipoc_newton_bwd_apply_f64": (_I, [_I] * 5 + [_P] * 14 + [_P, _SZ, _P]),
     "ipoc_newton_fwd_apply_f64": (_I, [_I] * 5 + [_P] * 7 + [_P, _SZ, _P]),

@@ -15,7 +15,7 @@ import torch
 from torch.func import vmap, grad, hessian, jacrev
 from . import _lib as L
 from .optimal_control_problem import OCP, Derivatives
-from .noc import reductions, newton_step, accept_update, affine_scan
+from .noc import reductions, newton_step, accept_update, affine_scan, compute_lqr_params
 from . import plants
 
 
@@ -88,7 +88,7 @@ def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
             d = compute_derivatives_batched(ocp, x, u, barrier_param)
             lamT = lamT_fn(x[:, -1])
         lam = affine_scan(d.fx, d.cx, lamT, reverse=True, transpose=True)          # :147
-        ru, Q, R, M = compute_lqr_params_batched(lam, d)                           # :149
+        ru, Q, R, M = compute_lqr_params(lam, d)                                   # :149 (one streaming kernel)
         hu, cu_norm, _ = reductions(ru=ru, cu=d.cu)                                # :158, :116
         inner = torch.zeros(B, dtype=torch.int64, device=dev)
         act_in = active.clone()                                                    # members still in the attempt loop

@@ -38,7 +38,25 @@ def compute_derivatives(ocp: OCP, states: torch.Tensor, controls: torch.Tensor, 
 
 # ------------------------------------------------------------------ A3: LQ parameters (host framework)
 def compute_lqr_params(lagrange_multipliers: torch.Tensor, d: Derivatives):
-    """ref noc/par_interior_point_newton.py:31-42 (tensordot contracts the OUTPUT index)."""
+    """ref noc/par_interior_point_newton.py:31-42 (tensordot contracts the OUTPUT index).
+    CUDA tensors go through one streaming kernel (ipoc_lqr_params_f64); the einsum form below is the
+    same arithmetic for anything else.  Accepts (N, ...) or (B, N, ...)."""
+    if lagrange_multipliers.is_cuda:
+        lam = L.dev_f64(lagrange_multipliers)
+        t = [L.dev_f64(a) for a in (d.cu, d.cxx, d.cuu, d.cxu, d.fu, d.fxx, d.fuu, d.fxu)]
+        batched = lam.dim() == 3
+        if not batched:
+            lam = lam.unsqueeze(0)
+            t = [a.unsqueeze(0) for a in t]
+        Bn, N, nu = t[0].shape[0], t[0].shape[1], t[0].shape[2]
+        nx = lam.shape[-1]
+        o = dict(dtype=torch.float64, device=lam.device)
+        ru, Q = torch.empty(Bn, N, nu, **o), torch.empty(Bn, N, nx, nx, **o)
+        R, M = torch.empty(Bn, N, nu, nu, **o), torch.empty(Bn, N, nx, nu, **o)
+        with torch.cuda.device(lam.device):
+            L.check(L.lib().ipoc_lqr_params_f64(N, nx, nu, Bn, L.ptr(lam), *(L.ptr(a) for a in t), L.ptr(ru), L.ptr(Q),
+                                                L.ptr(R), L.ptr(M), L.stream_ptr()))
+        return (ru, Q, R, M) if batched else (ru[0], Q[0], R[0], M[0])
     l = lagrange_multipliers[1:]
     ru = d.cu + torch.einsum("tou,to->tu", d.fu, l)
     Q = d.cxx + torch.einsum("to,toij->tij", l, d.fxx)
