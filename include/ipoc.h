@@ -240,6 +240,16 @@ int ipoc_plant_derivatives_f64(int plant, int N, int batch, double Ts, double bo
                                double* cx, double* cu, double* cxx, double* cuu, double* cxu,
                                double* fx, double* fu, double* fxx, double* fuu, double* fxu, double* lamT,
                                ipoc_stream_t stream);
+/* Fused A1 + A3 for the built-in plants: ru, Q, R, M of ref noc/par_interior_point_newton.py:31-42 are the
+ * first/second derivatives of the Hamiltonian H = stage_cost + lam[k+1]' f(x,u), so the 130-double
+ * `Derivatives` record never has to exist:  linearize (before the costate scan) -> fx, fu, cx, cu, lamT;
+ * hamiltonian (after it, lam (batch,N+1,nx)) -> ru, Q, R, M. */
+int ipoc_plant_linearize_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
+                             const double* x, const double* u, double* fx, double* fu, double* cx, double* cu,
+                             double* lamT, ipoc_stream_t stream);
+int ipoc_plant_hamiltonian_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
+                               const double* x, const double* u, const double* lam,
+                               double* ru, double* Q, double* R, double* M, ipoc_stream_t stream);
 int ipoc_plant_cost_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
                         const double* x, const double* u, double* total_cost, int32_t* feasible,
                         ipoc_stream_t stream);

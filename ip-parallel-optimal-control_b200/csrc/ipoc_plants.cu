@@ -139,6 +139,118 @@ k_plant_derivs(PlantParams pp, const double* __restrict__ bp_ptr, int N, int bat
     }
 }
 
+// ---------------------------------------------------------------- linearisation + Hamiltonian (fused A1+A3)
+// What the Newton step actually consumes is fx, fu, ru, Q, R, M (+ cx for the costates, cu for the
+// regularisation scale), and  Q = cxx + sum_o l_o fxx[o]  etc. (ref noc/par_interior_point_newton.py:31-42)
+// are exactly the second derivatives of the Hamiltonian  H(x,u) = stage_cost(x,u) + l' f(x,u)  with
+// l = lambda_{k+1}.  So two small passes replace the 130-double `Derivatives` record and the contraction:
+//   pass 1 (before the costate scan): fx, fu, cx, cu, lambda_N            (25 doubles per step)
+//   pass 2 (after it):                ru = H_u, Q = H_xx, R = H_uu, M = H_xu   (22 doubles per step)
+template <int CNT>
+__device__ __forceinline__ void store_row(double* __restrict__ p, const double* v) {
+    if constexpr (CNT % 2 == 0) {
+        double2* p2 = reinterpret_cast<double2*>(p);
+#pragma unroll
+        for (int i = 0; i < CNT / 2; ++i) p2[i] = make_double2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; ++i) p[i] = v[i];
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(128)
+k_plant_linearize(PlantParams pp, const double* __restrict__ bp_ptr, int N, int batch,
+                  const double* __restrict__ X, const double* __restrict__ U, double* __restrict__ fx,
+                  double* __restrict__ fu, double* __restrict__ cx, double* __restrict__ cu,
+                  double* __restrict__ lamT) {
+    constexpr int NX = P::NX, NU = P::NU, NV = NX + NU;
+    using J = Jet<NV>;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * N) return;
+    const int b = (int)(g / N), k = (int)(g % N);
+    const double bp = *bp_ptr;
+    const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
+    J x[NX], u[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = J::var(xp[i], i);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) u[a] = J::var(U[(size_t)g * NU + a], NX + a);
+    J o[NX];
+    P::ode(x, u, o);
+    double fxv[NX * NX], fuv[NX * NU], cxv[NX], cuv[NU];
+#pragma unroll
+    for (int r = 0; r < NX; ++r) {
+        const J f = x[r] + pp.Ts * o[r];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) fxv[r * NX + i] = f.g[i];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) fuv[r * NU + a] = f.g[NX + a];
+    }
+    const J c = stage_cost<P, J>(x, u, bp, pp.bound);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) cxv[i] = c.g[i];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) cuv[a] = c.g[NX + a];
+    store_row<NX * NX>(fx + (size_t)g * NX * NX, fxv);
+    store_row<NX * NU>(fu + (size_t)g * NX * NU, fuv);
+    store_row<NX>(cx + (size_t)g * NX, cxv);
+    store_row<NU>(cu + (size_t)g * NU, cuv);
+    if (k == N - 1 && lamT != nullptr) {
+        const double* xn = X + ((size_t)b * (N + 1) + N) * NX;
+        J xe[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xe[i] = J::var(xn[i], i);
+        const J ce = P::state_cost(xe);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) lamT[(size_t)b * NX + i] = ce.g[i];
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(128)
+k_plant_hamiltonian(PlantParams pp, const double* __restrict__ bp_ptr, int N, int batch,
+                    const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ lam,
+                    double* __restrict__ ru, double* __restrict__ Q, double* __restrict__ R,
+                    double* __restrict__ M) {
+    constexpr int NX = P::NX, NU = P::NU, NV = NX + NU;
+    using J = Jet<NV>;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * N) return;
+    const int b = (int)(g / N), k = (int)(g % N);
+    const double bp = *bp_ptr;
+    const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
+    const double* lp = lam + ((size_t)b * (N + 1) + k + 1) * NX;
+    J x[NX], u[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = J::var(xp[i], i);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) u[a] = J::var(U[(size_t)g * NU + a], NX + a);
+    J o[NX];
+    P::ode(x, u, o);
+    J H = stage_cost<P, J>(x, u, bp, pp.bound);
+#pragma unroll
+    for (int r = 0; r < NX; ++r) H = H + lp[r] * (x[r] + pp.Ts * o[r]);
+    double ruv[NU], Qv[NX * NX], Rv[NU * NU], Mv[NX * NU];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+        ruv[a] = H.g[NX + a];
+#pragma unroll
+        for (int c = 0; c < NU; ++c) Rv[a * NU + c] = H.hess(NX + a, NX + c);
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) Qv[i * NX + j] = H.hess(i, j);
+#pragma unroll
+        for (int a = 0; a < NU; ++a) Mv[i * NU + a] = H.hess(i, NX + a);
+    }
+    store_row<NU>(ru + (size_t)g * NU, ruv);
+    store_row<NX * NX>(Q + (size_t)g * NX * NX, Qv);
+    store_row<NU * NU>(R + (size_t)g * NU * NU, Rv);
+    store_row<NX * NU>(M + (size_t)g * NX * NU, Mv);
+}
+
 // ---------------------------------------------------------------- total cost + feasibility
 // total_cost = final_cost(x_N) + sum_k stage_cost(x_k, u_k, bp); feasible = all(constraints <= 0).
 // One CTA of 1024 threads per problem; fixed summation order (thread-strided partials, shuffle trees).
@@ -235,6 +347,22 @@ static int derivs_impl(PlantParams pp, const double* bp, int N, int batch, const
     return IPOC_OK;
 }
 template <class P>
+static int linearize_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
+                          double* fx, double* fu, double* cx, double* cu, double* lamT, cudaStream_t st) {
+    const long long n = (long long)N * batch;
+    k_plant_linearize<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pp, bp, N, batch, X, U, fx, fu, cx, cu, lamT);
+    PLANT_CHECK(st);
+    return IPOC_OK;
+}
+template <class P>
+static int hamiltonian_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
+                            const double* lam, double* ru, double* Q, double* R, double* M, cudaStream_t st) {
+    const long long n = (long long)N * batch;
+    k_plant_hamiltonian<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pp, bp, N, batch, X, U, lam, ru, Q, R, M);
+    PLANT_CHECK(st);
+    return IPOC_OK;
+}
+template <class P>
 static int cost_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
                      double* total, int32_t* feasible, cudaStream_t st) {
     k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible);
@@ -273,6 +401,28 @@ int ipoc_plant_derivatives_f64(int plant, int N, int batch, double Ts, double bo
         return derivs_impl<Pendulum>(pp, bp, N, batch, x, u, cx, cu, cxx, cuu, cxu, fx, fu, fxx, fuu, fxu, lamT, st);
     if (plant == IPOC_PLANT_CARTPOLE)
         return derivs_impl<Cartpole>(pp, bp, N, batch, x, u, cx, cu, cxx, cuu, cxu, fx, fu, fxx, fuu, fxu, lamT, st);
+    return IPOC_EINVAL;
+}
+
+int ipoc_plant_linearize_f64(int plant, int N, int batch, double Ts, double bound, const double* bp, const double* x,
+                             const double* u, double* fx, double* fu, double* cx, double* cu, double* lamT,
+                             ipoc_stream_t stream) {
+    if (N < 1 || batch < 1 || !bp || !x || !u || !fx || !fu || !cx || !cu) return IPOC_EINVAL;
+    const PlantParams pp{Ts, bound};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plant == IPOC_PLANT_PENDULUM) return linearize_impl<Pendulum>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, st);
+    if (plant == IPOC_PLANT_CARTPOLE) return linearize_impl<Cartpole>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, st);
+    return IPOC_EINVAL;
+}
+
+int ipoc_plant_hamiltonian_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
+                               const double* x, const double* u, const double* lam, double* ru, double* Q,
+                               double* R, double* M, ipoc_stream_t stream) {
+    if (N < 1 || batch < 1 || !bp || !x || !u || !lam || !ru || !Q || !R || !M) return IPOC_EINVAL;
+    const PlantParams pp{Ts, bound};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plant == IPOC_PLANT_PENDULUM) return hamiltonian_impl<Pendulum>(pp, bp, N, batch, x, u, lam, ru, Q, R, M, st);
+    if (plant == IPOC_PLANT_CARTPOLE) return hamiltonian_impl<Cartpole>(pp, bp, N, batch, x, u, lam, ru, Q, R, M, st);
     return IPOC_EINVAL;
 }
 

@@ -37,6 +37,8 @@ _SIGS = {
     "ipoc_newton_step_host_f64": (_I, [_I] * 4 + [_P] * 11 + [_P, _SZ, _P]),
     "ipoc_plant_dims": (_I, [_I] + [ctypes.POINTER(ctypes.c_int)] * 3),
     "ipoc_plant_derivatives_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 14 + [_P]),
+    "ipoc_plant_linearize_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 8 + [_P]),
+    "ipoc_plant_hamiltonian_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 8 + [_P]),
     "ipoc_plant_cost_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 5 + [_P]),
     "ipoc_plant_rollout_f64": (_I, [_I, _I, _I, ctypes.c_double] + [_P] * 3 + [_P]),
     "ipoc_profile_begin": (_I, [_P]),

@@ -15,7 +15,7 @@ import torch
 from torch.func import vmap, grad, hessian, jacrev
 from . import _lib as L
 from .optimal_control_problem import OCP, Derivatives
-from .noc import reductions, newton_step, accept_update, affine_scan, compute_lqr_params
+from .noc import reductions, newton_step, accept_update, eval_iteration
 from . import plants
 
 
@@ -49,16 +49,6 @@ def compute_derivatives_batched(ocp: OCP, states, controls, bp) -> Derivatives:
     return Derivatives(*(t.reshape((B, N) + tuple(t.shape[1:])).contiguous() for t in flat))
 
 
-def compute_lqr_params_batched(lam, d: Derivatives):
-    """ref noc/par_interior_point_newton.py:31-42 with a leading batch axis."""
-    l = lam[:, 1:]
-    ru = d.cu + torch.einsum("btou,bto->btu", d.fu, l)
-    Q = d.cxx + torch.einsum("bto,btoij->btij", l, d.fxx)
-    R = d.cuu + torch.einsum("bto,btoij->btij", l, d.fuu)
-    M = d.cxu + torch.einsum("bto,btoij->btij", l, d.fxu)
-    return ru.contiguous(), Q.contiguous(), R.contiguous(), M.contiguous()
-
-
 def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
     """Per-member semantics of ref noc/par_interior_point_newton.py:127-225 for a batch.
     -> (x (B,N+1,nx), u (B,N,nu), iterations (B,) int64)"""
@@ -77,24 +67,15 @@ def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
     hu_norm = torch.ones(B, **o)
     total_cost = vmap(ocp.total_cost, in_dims=(0, 0, None))
     cons_fn = vmap(vmap(ocp.constraints))
-    lamT_fn = vmap(grad(ocp.final_cost))
     active = torch.ones(B, dtype=torch.bool, device=dev)                           # members still in the Newton loop
     while bool(active.any()):                                                      # :199-202 (per member)
-        if plant is not None:
-            d, lamT = plants.derivatives(plant, x, u, barrier_param)               # :145
-            cost, _ = plants.cost(plant, x, u, barrier_param)                      # :142
-        else:
-            cost = total_cost(x, u, barrier_param)
-            d = compute_derivatives_batched(ocp, x, u, barrier_param)
-            lamT = lamT_fn(x[:, -1])
-        lam = affine_scan(d.fx, d.cx, lamT, reverse=True, transpose=True)          # :147
-        ru, Q, R, M = compute_lqr_params(lam, d)                                   # :149 (one streaming kernel)
-        hu, cu_norm, _ = reductions(ru=ru, cu=d.cu)                                # :158, :116
+        cost, fx, fu, cu, ru, Q, R, M = eval_iteration(ocp, x, u, barrier_param)   # :142-149
+        hu, cu_norm, _ = reductions(ru=ru, cu=cu)                                  # :158, :116
         inner = torch.zeros(B, dtype=torch.int64, device=dev)
         act_in = active.clone()                                                    # members still in the attempt loop
         tx, tu = x.clone(), u.clone()
         while bool(act_in.any()):                                                  # :177-182 (per member)
-            dx, du, _, _, pred, bwd_feas = newton_step(d.fx, d.fu, ru, Q, R, M, rp * cu_norm)   # :153
+            dx, du, _, _, pred, bwd_feas = newton_step(fx, fu, ru, Q, R, M, rp * cu_norm)       # :153
             cx_try, cu_try = x + dx, u + du                                        # :156-157
             if plant is not None:
                 new_cost, traj_feas = plants.cost(plant, cx_try, cu_try, barrier_param)   # :160-161

@@ -35,14 +35,13 @@ class GraphedNewton:
 
     # ---- loop bodies (same statements as noc.newton_oc) ------------------------------------------------
     def _iteration(self):
-        self.cost, self.d, lamT = noc.eval_iteration(self.ocp, self.x, self.u, self.bp)   # :142, :145
-        lam = noc.affine_scan(self.d.fx, self.d.cx, lamT, reverse=True, transpose=True)   # :147
-        self.ru, self.Q, self.R, self.M = noc.compute_lqr_params(lam, self.d)      # :149
-        self.hu, self.cu_norm, _ = noc.reductions(ru=self.ru, cu=self.d.cu)        # :158, :116
+        (self.cost, self.fx, self.fu, cu, self.ru, self.Q, self.R,
+         self.M) = noc.eval_iteration(self.ocp, self.x, self.u, self.bp)           # :142-149
+        self.hu, self.cu_norm, _ = noc.reductions(ru=self.ru, cu=cu)               # :158, :116
 
     def _attempt(self):
-        ocp, d = self.ocp, self.d
-        dx, du, _, _, pred, bwd_feas = noc.newton_step(d.fx, d.fu, self.ru, self.Q, self.R, self.M,
+        ocp = self.ocp
+        dx, du, _, _, pred, bwd_feas = noc.newton_step(self.fx, self.fu, self.ru, self.Q, self.R, self.M,
                                                        self.rp * self.cu_norm)     # :153
         self.tu = self.u + du                                                      # :156
         self.tx = self.x + dx                                                      # :157

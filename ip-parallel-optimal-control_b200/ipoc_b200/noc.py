@@ -190,16 +190,30 @@ def par_Newton(nominal_states, d: Derivatives, reg_param, ru, Q, R, M):
 
 # ------------------------------------------------------------------ user-function evaluation of one iteration / trial
 def eval_iteration(ocp: OCP, x, u, bp):
-    """cost (1,), Derivatives, lambda_N for the current iterate — ref :142, :145, costates.py:35.
-    Host-framework autodiff in general; one fused kernel each for the built-in plants (plants.py)."""
+    """Everything one Newton iteration needs from the user functions at the iterate (x, u):
+    -> cost (1,), fx, fu, cu, ru, Q, R, M   (ref :142, :145, :147, :149; K1 runs inside).
+    General OCPs: host-framework autodiff (`compute_derivatives`), costate scan, `compute_lqr_params`.
+    Built-in plants (plants.py): first-order pass -> costate scan -> Hamiltonian pass; the full
+    `Derivatives` record is never materialised.  Works for (N, ...) and (B, N, ...) iterates."""
     plant = plants.plant_of(ocp)
     if plant is not None:
-        d, lamT = plants.derivatives(plant, x, u, bp)
+        fx, fu, cx, cu, lamT = plants.linearize(plant, x, u, bp)
         cost, _ = plants.cost(plant, x, u, bp)
-        return cost, d, lamT
-    cost = ocp.total_cost(x, u, bp).reshape(1)
-    d = compute_derivatives(ocp, x, u, bp)
-    return cost, d, grad(ocp.final_cost)(x[-1])
+        lam = affine_scan(fx, cx, lamT, reverse=True, transpose=True)   # :147
+        ru, Q, R, M = plants.hamiltonian(plant, x, u, lam, bp)          # :149
+        return cost, fx, fu, cu, ru, Q, R, M
+    if x.dim() == 3:
+        from .batched import compute_derivatives_batched
+        cost = vmap(ocp.total_cost, in_dims=(0, 0, None))(x, u, bp)
+        d = compute_derivatives_batched(ocp, x, u, bp)
+        lamT = vmap(grad(ocp.final_cost))(x[:, -1])
+    else:
+        cost = ocp.total_cost(x, u, bp).reshape(1)
+        d = compute_derivatives(ocp, x, u, bp)
+        lamT = grad(ocp.final_cost)(x[-1])
+    lam = affine_scan(d.fx, d.cx, lamT, reverse=True, transpose=True)   # :147
+    ru, Q, R, M = compute_lqr_params(lam, d)                            # :149
+    return cost, d.fx, d.fu, d.cu, ru, Q, R, M
 
 
 def eval_trial(ocp: OCP, tx, tu, bp):
@@ -245,14 +259,12 @@ def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, bar
     r_inc = torch.full((1,), 2.0, **o)                                   # :135
     iteration, Hu_norm = 0, 1.0
     while not (Hu_norm < 1e-4 or iteration > 1000):                      # :199-202
-        cost, d, lamT = eval_iteration(ocp, x, u, barrier_param)         # :142, :145
-        lam = affine_scan(d.fx, d.cx, lamT, reverse=True, transpose=True)   # :147
-        ru, Q, R, M = compute_lqr_params(lam, d)                         # :149
-        hu, cu_norm, _ = reductions(ru=ru, cu=d.cu)                      # :158 (pre-step ru), :116
+        cost, fx, fu, cu, ru, Q, R, M = eval_iteration(ocp, x, u, barrier_param)   # :142-149
+        hu, cu_norm, _ = reductions(ru=ru, cu=cu)                        # :158 (pre-step ru), :116
         success, inner = False, 0
         tx, tu = x, u
         while not (success or inner > 500):                              # :177-182
-            dx, du, _, _, pred, bwd_feas = newton_step(d.fx, d.fu, ru, Q, R, M, rp * cu_norm)   # :153
+            dx, du, _, _, pred, bwd_feas = newton_step(fx, fu, ru, Q, R, M, rp * cu_norm)   # :153
             tu = u + du                                                  # :156
             tx = x + dx                                                  # :157
             new_cost, traj_feas = eval_trial(ocp, tx, tu, barrier_param)  # :159-163

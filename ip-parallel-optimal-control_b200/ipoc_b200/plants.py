@@ -65,6 +65,52 @@ def derivatives(plant, states, controls, bp):
     return Derivatives(*(outs[k] for k in Derivatives._fields)), lamT
 
 
+def _prep(states, controls):
+    x, u = L.dev_f64(states), L.dev_f64(controls)
+    batched = x.dim() == 3
+    if not batched:
+        x, u = x.unsqueeze(0), u.unsqueeze(0)
+    return x, u, batched
+
+
+def linearize(plant, states, controls, bp):
+    """First-order pass (before the costate scan) -> fx, fu, cx, cu, lamT."""
+    x, u, batched = _prep(states, controls)
+    B, N = u.shape[0], u.shape[1]
+    nx, nu, _ = _dims(plant)
+    o = dict(dtype=torch.float64, device=x.device)
+    fx, fu = torch.empty(B, N, nx, nx, **o), torch.empty(B, N, nx, nu, **o)
+    cx, cu, lamT = torch.empty(B, N, nx, **o), torch.empty(B, N, nu, **o), torch.empty(B, nx, **o)
+    bpt = _bp_tensor(bp, x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().ipoc_plant_linearize_f64(plant["id"], N, B, plant["Ts"], plant["bound"], L.ptr(bpt), L.ptr(x),
+                                                 L.ptr(u), L.ptr(fx), L.ptr(fu), L.ptr(cx), L.ptr(cu), L.ptr(lamT),
+                                                 L.stream_ptr()))
+    out = (fx, fu, cx, cu, lamT)
+    return out if batched else tuple(t[0] for t in out)
+
+
+def hamiltonian(plant, states, controls, lam, bp):
+    """Second-order pass (after the costate scan): ru, Q, R, M = H_u, H_xx, H_uu, H_xu of
+    H = stage_cost + lam[k+1]' f  (== compute_lqr_params, ref noc/par_interior_point_newton.py:31-42)."""
+    x, u, batched = _prep(states, controls)
+    lam = L.dev_f64(lam)
+    if not batched:
+        lam = lam.unsqueeze(0)
+    B, N = u.shape[0], u.shape[1]
+    nx, nu, _ = _dims(plant)
+    o = dict(dtype=torch.float64, device=x.device)
+    ru, Q = torch.empty(B, N, nu, **o), torch.empty(B, N, nx, nx, **o)
+    R, M = torch.empty(B, N, nu, nu, **o), torch.empty(B, N, nx, nu, **o)
+    bpt = _bp_tensor(bp, x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().ipoc_plant_hamiltonian_f64(plant["id"], N, B, plant["Ts"], plant["bound"], L.ptr(bpt), L.ptr(x),
+                                                   L.ptr(u), L.ptr(lam), L.ptr(ru), L.ptr(Q), L.ptr(R), L.ptr(M),
+                                                   L.stream_ptr()))
+    out = (ru, Q, R, M)
+    return out if batched else tuple(t[0] for t in out)
+
+
 def cost(plant, states, controls, bp):
     """-> (total_cost (B,), feasible (B,) int32) of trajectories: final cost + sum of stage costs (log barrier
     included; NaN where infeasible, as in the reference) and all(constraints <= 0)."""

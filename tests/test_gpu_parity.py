@@ -454,6 +454,14 @@ def test_plant_kernels_vs_reference_fixtures(golden, name):
     if "warm" not in name:
         xr = plants.rollout(plant, u, T(g["x0"]))
         assert relerr(N_(xr), g["states"]) < 1e-13
+    # fused first-order + Hamiltonian passes == compute_lqr_params of the reference
+    fx, fu, cx, cu, lamT2 = plants.linearize(plant, x, u, bp)
+    assert torch.equal(fx, d.fx) and torch.equal(fu, d.fu) and torch.equal(cx, d.cx) and torch.equal(cu, d.cu)
+    ru, Q, R, M = plants.hamiltonian(plant, x, u, T(g["ref_costates_par"]), bp)
+    for got, key in ((ru, "ref_ru"), (Q, "ref_Q"), (R, "ref_R"), (M, "ref_M")):
+        assert np.max(np.abs(N_(got) - g[key])) <= 1e-12 * max(1.0, np.max(np.abs(g[key]))), key
+    ru2, Q2, R2, M2 = noc.compute_lqr_params(T(g["ref_costates_par"]), d)     # streaming A3 kernel on Derivatives
+    assert relerr(N_(Q2), g["ref_Q"]) < 1e-13 and relerr(N_(ru2), g["ref_ru"]) < 1e-13
     # batched call == per-problem call
     xb, ub = torch.stack((x, x)), torch.stack((u, u * 0.5))
     db, _ = plants.derivatives(plant, xb, ub, bp)
