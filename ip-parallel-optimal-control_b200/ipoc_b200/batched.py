@@ -15,7 +15,7 @@ import torch
 from torch.func import vmap, grad, hessian, jacrev
 from . import _lib as L
 from .optimal_control_problem import OCP, Derivatives
-from .noc import reductions, newton_step, accept_update, eval_iteration
+from .noc import reductions, newton_step, accept_update, eval_iteration, eval_trial
 from . import plants
 
 
@@ -51,52 +51,56 @@ def compute_derivatives_batched(ocp: OCP, states, controls, bp) -> Derivatives:
 
 def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
     """Per-member semantics of ref noc/par_interior_point_newton.py:127-225 for a batch.
-    -> (x (B,N+1,nx), u (B,N,nu), iterations (B,) int64)"""
+    -> (x (B,N+1,nx), u (B,N,nu), iterations (B,) int64)
+
+    Members leave the two loops at different times; the work is COMPACTED to the members still inside
+    (index_select of the active rows), so a few hard members with hundreds of rejected attempts do not
+    drag the whole batch through every attempt."""
     dev = controls.device
-    u = L.dev_f64(controls)
+    u_all = L.dev_f64(controls).clone()
     plant = plants.plant_of(ocp)
     if plant is not None:
-        x = plants.rollout(plant, u, initial_states.to(dev))                       # :133
+        x_all = plants.rollout(plant, u_all, initial_states.to(dev))               # :133
     else:
-        x = rollout_batched(ocp.dynamics, u, initial_states.to(dev))
-    B = u.shape[0]
+        x_all = rollout_batched(ocp.dynamics, u_all, initial_states.to(dev))
+    B = u_all.shape[0]
     o = dict(dtype=torch.float64, device=dev)
-    rp = torch.ones(B, **o)                                                        # :134
-    r_inc = torch.full((B,), 2.0, **o)                                             # :135
+    rp_all = torch.ones(B, **o)                                                    # :134
+    rinc_all = torch.full((B,), 2.0, **o)                                          # :135
     iters = torch.zeros(B, dtype=torch.int64, device=dev)
-    hu_norm = torch.ones(B, **o)
-    total_cost = vmap(ocp.total_cost, in_dims=(0, 0, None))
-    cons_fn = vmap(vmap(ocp.constraints))
-    active = torch.ones(B, dtype=torch.bool, device=dev)                           # members still in the Newton loop
-    while bool(active.any()):                                                      # :199-202 (per member)
+    act = torch.arange(B, device=dev)                                              # members still in the Newton loop
+    while act.numel() > 0:                                                         # :199-202 (per member)
+        full = act.numel() == B
+        x, u = (x_all, u_all) if full else (x_all[act], u_all[act])
         cost, fx, fu, cu, ru, Q, R, M = eval_iteration(ocp, x, u, barrier_param)   # :142-149
         hu, cu_norm, _ = reductions(ru=ru, cu=cu)                                  # :158, :116
-        inner = torch.zeros(B, dtype=torch.int64, device=dev)
-        act_in = active.clone()                                                    # members still in the attempt loop
+        na = act.numel()
+        rp, rinc = rp_all[act], rinc_all[act]
         tx, tu = x.clone(), u.clone()
-        while bool(act_in.any()):                                                  # :177-182 (per member)
-            dx, du, _, _, pred, bwd_feas = newton_step(fx, fu, ru, Q, R, M, rp * cu_norm)       # :153
-            cx_try, cu_try = x + dx, u + du                                        # :156-157
-            if plant is not None:
-                new_cost, traj_feas = plants.cost(plant, cx_try, cu_try, barrier_param)   # :160-161
+        inner = torch.zeros(na, dtype=torch.int64, device=dev)
+        sub = torch.arange(na, device=dev)                                         # members still in the attempt loop
+        while sub.numel() > 0:                                                     # :177-182 (per member)
+            if sub.numel() == na:
+                a = (fx, fu, ru, Q, R, M, x, u, cost, cu_norm)
             else:
-                cons = cons_fn(cx_try[:, :-1], cu_try)
-                _, _, traj_feas = reductions(cons=cons.reshape(B, cons.shape[1], -1))
-                new_cost = total_cost(cx_try, cu_try, barrier_param)
-            succ, _ = accept_update(cost, new_cost.contiguous(), traj_feas, pred, bwd_feas, rp, r_inc,
-                                    active=act_in.to(torch.int32))                 # :159-173, active members only
-            m = act_in.view(B, 1, 1)
-            tx = torch.where(m, cx_try, tx)                                        # :175 (kept regardless of success)
-            tu = torch.where(m, cu_try, tu)
-            inner = inner + act_in.to(torch.int64)                                 # :174
-            act_in = act_in & ~((succ != 0) | (inner > 500))
-        m = active.view(B, 1, 1)
-        x = torch.where(m, tx, x)                                                  # :184
-        u = torch.where(m, tu, u)
-        hu_norm = torch.where(active, hu, hu_norm)
-        iters = iters + active.to(torch.int64)                                     # :194
-        active = active & ~((hu_norm < 1e-4) | (iters > 1000))
-    return x, u, iters
+                a = tuple(t.index_select(0, sub) for t in (fx, fu, ru, Q, R, M, x, u, cost, cu_norm))
+            rp_s, rinc_s = rp[sub].contiguous(), rinc[sub].contiguous()
+            dx, du, _, _, pred, bwd_feas = newton_step(*a[:6], rp_s * a[9])        # :153
+            cx_try, cu_try = a[6] + dx, a[7] + du                                  # :156-157
+            new_cost, traj_feas = eval_trial(ocp, cx_try, cu_try, barrier_param)   # :159-163
+            succ, _ = accept_update(a[8].contiguous(), new_cost.contiguous(), traj_feas, pred, bwd_feas, rp_s,
+                                    rinc_s)                                        # :159-173
+            rp[sub], rinc[sub] = rp_s, rinc_s
+            tx[sub], tu[sub] = cx_try, cu_try                                      # :175 (kept regardless of success)
+            inner[sub] += 1                                                        # :174
+            sub = sub[~((succ != 0) | (inner[sub] > 500))]
+        if full:
+            x_all, u_all, rp_all, rinc_all = tx, tu, rp, rinc                      # :184
+        else:
+            x_all[act], u_all[act], rp_all[act], rinc_all[act] = tx, tu, rp, rinc
+        iters[act] += 1                                                            # :194
+        act = act[~((hu < 1e-4) | (iters[act] > 1000))]
+    return x_all, u_all, iters
 
 
 def par_interior_point_optimal_control_batched(ocp: OCP, controls, initial_states):

@@ -221,6 +221,10 @@ def eval_trial(ocp: OCP, tx, tu, bp):
     plant = plants.plant_of(ocp)
     if plant is not None:
         return plants.cost(plant, tx, tu, bp)
+    if tx.dim() == 3:
+        cons = vmap(vmap(ocp.constraints))(tx[:, :-1], tu)
+        _, _, traj_feas = reductions(cons=cons.reshape(cons.shape[0], cons.shape[1], -1))
+        return vmap(ocp.total_cost, in_dims=(0, 0, None))(tx, tu, bp), traj_feas
     cons = vmap(ocp.constraints)(tx[:-1], tu)                            # :160
     _, _, traj_feas = reductions(cons=cons.reshape(cons.shape[0], -1))
     return ocp.total_cost(tx, tu, bp).reshape(1), traj_feas              # :161 (masked to inf by A8)
