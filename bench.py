@@ -143,7 +143,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = 1   # the NumPy port is effectively single-threaded (batched small LAPACK solves); host has os.cpu_count()
     inp = cpu_inputs(N_HEADLINE)
     dt = time_cpu(inp, args.steps, args.warmup)
     val = 1.0 / dt
@@ -155,7 +155,7 @@ def run_reference(args):
                    "note": "reference (JAX+paroc) not installable here: NumPy oracle port on host CPU"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} full passes at N=10000 after {args.warmup} warm-up; NumPy "
-                                   f"(batched LAPACK small solves, threads as NumPy/OpenBLAS chooses; {cores} cores)"},
+                                   f"(batched small LAPACK solves: effectively 1 thread; host has {os.cpu_count()} cores)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -425,10 +425,10 @@ def run_ours(args):
         inp = cpu_inputs(N_HEADLINE)
         n_cpu = 20
         dt = time_cpu(inp, n_cpu, 2)
-        cores = os.cpu_count() or 1
-        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{n_cpu} full passes at N=10000 (NumPy oracle: JAX-order associative scans, batched small "
-                         f"solves), {cores} host cores available, ms_per_step={dt * 1e3:.1f}"}
+                         f"LAPACK solves, effectively single-threaded; host has {os.cpu_count()} cores), "
+                         f"ms_per_step={dt * 1e3:.1f}"}
 
     if rank == 0:
         line = {

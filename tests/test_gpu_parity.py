@@ -482,6 +482,65 @@ def test_full_solve_with_autodiff_path(golden, name):
     assert its == int(g["refp_iterations"]) and relerr(N_(u), g["refp_opt_u"]) < 1e-9
 
 
+def _custom_ocp(Ts, bad_constants=False):
+    """A user-defined 3-state problem (not one of the built-ins): general autodiff path, nx = 3 kernels."""
+    from ipoc_b200.optimal_control_problem import OCP
+    from ipoc_b200.utils import euler
+    from torch.func import vmap
+
+    def ode(x, u):
+        return torch.hstack((x[1], -x[0] - 0.1 * x[1] - 0.1 * x[0] ** 3 + u[0], torch.sin(x[0]) - x[2]))
+
+    def constraints(x, u):
+        return torch.hstack((u - 2.0, -u - 2.0))
+
+    def stage_cost(x, u, bp):
+        if bad_constants:   # builds a tensor from a Python list on every call: H2D copy, not graph-capturable
+            w = torch.tensor([1.0, 0.1, 0.5], dtype=x.dtype, device=x.device)
+        else:
+            w = torch.stack((x[0] * 0 + 1.0, x[0] * 0 + 0.1, x[0] * 0 + 0.5))
+        return 0.5 * torch.sum(w * x * x) + 0.5 * 1e-2 * (u @ u) - bp * torch.sum(torch.log(-constraints(x, u)))
+
+    def final_cost(x):
+        return 0.5 * (x @ x)
+
+    def total_cost(xs, us, bp):
+        return final_cost(xs[-1]) + torch.sum(vmap(stage_cost, in_dims=(0, 0, None))(xs[:-1], us, bp))
+
+    return OCP(euler(ode, Ts), constraints, stage_cost, final_cost, total_cost)
+
+
+def test_user_defined_ocp_matches_oracle_driver():
+    """End to end on a problem that is NOT built in: host-framework autodiff + nx=3 kernels + graphs vs the
+    NumPy oracle driver (same iterate, same Newton iteration count)."""
+    from ipoc_b200 import noc, plants
+    from oracle.autodiff import Evaluator
+    N = 30
+    ocp = _custom_ocp(0.05)
+    assert plants.plant_of(ocp) is None
+    rng = np.random.default_rng(2)
+    u0 = 0.1 * rng.standard_normal((N, 1))
+    x0 = np.array([1.0, -0.5, 0.3])
+    uo, ito = noc_np.par_interior_point_optimal_control(Evaluator(ocp), u0, x0)
+    ug, itg = noc.par_interior_point_optimal_control(ocp, T(u0), T(x0))
+    assert itg == ito and relerr(N_(ug), uo) < 1e-8
+
+
+def test_graph_capture_failure_falls_back_to_eager():
+    from ipoc_b200 import noc
+    import warnings
+    N = 12
+    ocp = _custom_ocp(0.05, bad_constants=True)
+    rng = np.random.default_rng(3)
+    u0, x0 = T(0.1 * rng.standard_normal((N, 1))), T([0.5, 0.0, 0.1])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        ug, itg = noc.par_interior_point_optimal_control(ocp, u0, x0)
+    assert any("capture" in str(m.message) for m in w)
+    ue, ite = noc.par_interior_point_optimal_control(ocp, u0, x0, use_graphs=False)
+    assert itg == ite and relerr(N_(ug), N_(ue)) < 1e-12
+
+
 def test_cpu_tensors_are_rejected():
     from ipoc_b200 import noc, _lib
     rng = np.random.default_rng(0)
