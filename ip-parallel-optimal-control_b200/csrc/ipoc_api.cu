@@ -79,16 +79,19 @@ k_reduce_partial(const double* __restrict__ ru, const double* __restrict__ cu, c
     if (ru != nullptr) {
         const double* p = ru + (size_t)b * N * nu;
         slice((long long)N * nu, lo, hi);
+#pragma unroll 4
         for (long long i = lo + t; i < hi; i += kRedThreads) mx = nan_max(mx, fabs(p[i]));
     }
     if (cu != nullptr) {
         const double* p = cu + (size_t)b * N * nu;
         slice((long long)N * nu, lo, hi);
+#pragma unroll 4
         for (long long i = lo + t; i < hi; i += kRedThreads) sq += p[i] * p[i];
     }
     if (cons != nullptr) {
         const double* p = cons + (size_t)b * N * nc;
         slice((long long)N * nc, lo, hi);
+#pragma unroll 4
         for (long long i = lo + t; i < hi; i += kRedThreads) ok &= (p[i] <= 0.0) ? 1 : 0;
     }
     s_max[t] = mx;
@@ -234,7 +237,7 @@ k_reduce_single(const double* __restrict__ ru, const double* __restrict__ cu, co
 
 static int reduce_blocks(int N, int width, int batch) {
     if ((long long)N * width <= 65536) return 1;
-    long long per_problem = ((long long)N * width + 8191) / 8192;   // >= 8192 entries per block
+    long long per_problem = ((long long)N * width + 2047) / 2048;   // >= 2048 entries per block
     long long cap = (148LL * 8 + batch - 1) / batch;                // fill the chip, not more
     long long n = per_problem < cap ? per_problem : cap;
     return (int)(n < 1 ? 1 : n);
