@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <math.h>
 #include "ipoc_math.cuh"
 #include "../../include/ipoc.h"
 #include "ipoc_dispatch.h"
@@ -1042,8 +1043,14 @@ static Plan make_plan(int N, int batch, bool force_scan = false, int target_thre
         } else {
             long long want = (target_threads + batch - 1) / batch;   // chunks per sequence to fill the chip
             want = ((want + 31) / 32) * 32;                          // whole warps
-            if (want < 32) want = 32;
-            long long t = ((long long)N + want - 1) / want;
+            if (want <= 64) want = 32;   // one warp per sequence: no level scan at all beats two half-filled warps
+            long long t = ((long long)N + want - 1) / want;          // one resident wave of leaf warps
+            // below one wave the pass is latency-bound: leaf time grows with T0, the top scan with
+            // N / (32 T0) — measured optimum T0 ~ sqrt(N) / 32 (4 @1e4, 8 @1e5, 16 @3e5, 32 @1e6)
+            // chunks of a multiple of 8 steps keep the staged rows sector-aligned (measurably faster)
+            const long long t_lat = (long long)(sqrt((double)N) / 256.0 + 0.5) * 8;
+            if (t > 4) t = ((t + 7) / 8) * 8;
+            if (t < t_lat) t = t_lat;
             T0 = (int)(t < 4 ? 4 : t);
         }
     }
