@@ -11,8 +11,9 @@ on the LQ tensors of BASELINE.json configs[1]: constrained cartpole, nx=4, nu=1,
 `value` : whole-job Newton steps/s with inputs resident in HBM (CUDA-graph replay of one pass, L2
           flushed between timed steps); N > 1: every rank runs its own independent OCP (batch-sharded
           mode, no data-path collective) -> weak scaling, value = sum over ranks.
-`e2e`   : same metric through the C-ABI host wrapper (ipoc_newton_step_host_f64): pinned HOST buffers,
-          H2D + kernels + D2H inside the timed region.
+`e2e`   : the same pass from HOST memory (runner.HostNewtonPass): all inputs in one pinned host arena,
+          H2D + the pass's kernels + D2H of the results inside the timed region (one CUDA graph); the
+          K2+K3-only host-buffer C call (ipoc_newton_step_host_f64) is reported next to it.
 `--impl reference`: the reference path on the host CPU.  The reference itself (JAX + paroc) cannot be
           installed here, so this times the NumPy oracle port (oracle/), labelled kind="port".
 """
@@ -65,6 +66,43 @@ def peaks():
     if os.path.exists(path):
         return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ host placement
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` BEFORE any pinned host memory is
+    allocated (first touch then places the staging arenas on the GPU's NUMA node; a remote node costs
+    the host<->device copies of the e2e number more than 2x on these boxes).  Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "nvml affinity empty or outside the cpuset; unchanged"
+        os.sched_setaffinity(0, allowed)
+        return f"bound to {len(allowed)} CPUs local to GPU {index} ({allowed[0]}..{allowed[-1]})"
+    except Exception as e:   # measurement hygiene only
+        return f"unchanged ({type(e).__name__})"
+
+
+def h2d_probe(dev, mb=64):
+    """Pinned host -> device copy bandwidth (GB/s) as seen by this process: context for the e2e number."""
+    import torch
+    h = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+    d = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    a.record()
+    for _ in range(4):
+        d.copy_(h, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize(dev)
+    return 4 * (mb << 20) / (a.elapsed_time(b) * 1e-3) / 1e9
 
 
 # ------------------------------------------------------------------------------ clocks sampler
@@ -174,6 +212,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    numa = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -256,10 +295,28 @@ def run_ours(args):
                                                  hp(du_h), hp(pred_h), hp(feas_h), hp(scratch), scratch_bytes,
                                                  _lib.stream_ptr()))
 
-    ms_e2e = float(np.mean(time_steps(e2e_step, args.steps, args.warmup, do_flush=True)))
-    h2d = sum(t.numel() * 8 for t in host.values()) + 8
-    d2h = dx_h.numel() * 8 + du_h.numel() * 8 + 8 + 4
+    ms_host_call = float(np.mean(time_steps(e2e_step, args.steps, args.warmup, do_flush=True)))
+    h2d_call = sum(t.numel() * 8 for t in host.values()) + 8
+    d2h_call = dx_h.numel() * 8 + du_h.numel() * 8 + 8 + 4
     torch.cuda.synchronize(dev)
+
+    # ---- end to end of the WHOLE pass (same work as `value`): every input in one pinned host arena,
+    #      one H2D copy + the pass + one D2H copy of the results, captured into one CUDA graph
+    from ipoc_b200.runner import HostNewtonPass
+    hpass = HostNewtonPass(w, dev)
+    hpass.capture()
+    ms_e2e = float(np.mean(time_steps(hpass.replay, args.steps, args.warmup, do_flush=True)))
+    h2d_gbps = h2d_probe(dev)
+    h2d, d2h = hpass.h2d_bytes, hpass.d2h_bytes
+    for q in (npass, hpass.inner):       # rp / r_inc evolve from pass to pass: compare one pass from equal state
+        q.rp.fill_(1.0)
+        q.r_inc.fill_(2.0)
+    npass.replay()
+    hpass.replay()
+    torch.cuda.synchronize(dev)
+    e2e_check = max(float((hpass.results["dx"].to(dev) - npass.dx).abs().max()),
+                    float((hpass.results["lam"].to(dev) - npass.lam).abs().max()),
+                    float((hpass.results["du"].to(dev) - npass.du).abs().max()))
     from ipoc_b200 import noc
     dx_res = noc.newton_step(w["fx"], w["fu"], w["ru"], w["Q"], w["R"], w["M"], reg_h.to(dev))[0]
     dx_check = float((dx_h.to(dev) - dx_res).abs().max())   # host-buffer path == resident path on the same inputs
@@ -442,8 +499,15 @@ def run_ours(args):
                        "launch": "CUDA-graph replay of one pass", "seed": 1},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e_all, "api": "ipoc_newton_step_host_f64 (K2+K3, pinned host buffers)",
-                    "check_max_abs_dx_diff_vs_resident": dx_check},
+                    "ms_per_step": ms_e2e_all,
+                    "api": "runner.HostNewtonPass: one pinned host arena -> H2D, the same pass as `value` "
+                           "(K1+K4+K2+K3+K4+A8 through the C ABI), D2H of lam/dx/du/scalars; one CUDA graph",
+                    "check_max_abs_diff_vs_resident": e2e_check,
+                    "host_placement": numa, "pinned_h2d_GBps_probe": h2d_gbps,
+                    "newton_step_host_call": {
+                        "api": "ipoc_newton_step_host_f64 (K2+K3 only, six pinned host buffers, eager)",
+                        "ms_per_step": ms_host_call, "h2d_bytes_per_step": h2d_call,
+                        "d2h_bytes_per_step": d2h_call, "check_max_abs_dx_diff_vs_resident": dx_check}},
             "gpu_launches": launches_per_pass * args.steps,
             "launches_per_step": launches_per_pass,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
