@@ -81,6 +81,72 @@ IPOC_DEV void lu_solve(double (&W)[N][N], double (&X)[N][R]) {
     }
 }
 
+// Factor-once / substitute-many form of the same elimination (same pivot rule, same operation
+// order per right-hand side, so results are bit-identical to lu_solve): W is overwritten by its LU
+// factors (unit-lower multipliers below the diagonal), inv = reciprocal pivots, perm[i] = original
+// index of the row now in position i.  The caller builds its right-hand sides directly in pivot
+// order (row i of X = original row perm[i]) — a runtime-indexed load of the operands instead of a
+// cascade of predicated register swaps over every right-hand-side column — and calls lu_subst.
+template <int N>
+IPOC_DEV void lu_factor(double (&W)[N][N], double (&inv)[N], int (&perm)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) perm[i] = i;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        if (k < N - 1) {
+            int p = k;
+            double best = fabs(W[k][k]);
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const double v = fabs(W[i][k]);
+                if (v > best) { best = v; p = i; }
+            }
+            if (p != k) {
+#pragma unroll
+                for (int i = k + 1; i < N; ++i) {
+                    const bool sw = (p == i);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const double a = W[k][j], b = W[i][j];
+                        W[k][j] = sw ? b : a;
+                        W[i][j] = sw ? a : b;
+                    }
+                    const int pa = perm[k], pb = perm[i];
+                    perm[k] = sw ? pb : pa;
+                    perm[i] = sw ? pa : pb;
+                }
+            }
+        }
+        inv[k] = 1.0 / W[k][k];
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const double m = W[i][k] * inv[k];
+            W[i][k] = m;
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) W[i][j] -= m * W[k][j];
+        }
+    }
+}
+template <int N, int R>
+IPOC_DEV void lu_subst(const double (&W)[N][N], const double (&inv)[N], double (&X)[N][R]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int i = k + 1; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < R; ++j) X[i][j] -= W[i][k] * X[k][j];
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            double s = X[k][j];
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) s -= W[k][i] * X[i][j];
+            X[k][j] = s * inv[k];
+        }
+    }
+}
+
 // Positive-definiteness of a small symmetric matrix (leading principal minors via elimination
 // without pivoting).  Any NaN makes it false.  Stands in for `all(eigh(G) > 0)`
 // (ref noc/seq_interior_point_newton.py:52-53).
@@ -273,31 +339,43 @@ struct RicOp {
         const E1& e1 = second;
         const E2& e2 = first;
         Elem o;
-        double W[NX][NX];
-        // right-hand sides: [A1 (NX) | b1 | C1 eta2 | C1 A2' (NX)]
-        double X[NX][2 * NX + 2];
+        double W[NX][NX], inv[NX];
+        int perm[NX];
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
                 double w = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < NX; ++k) w += e1.C(i, k) * e2.J(k, j);
+                W[i][j] = w;
+            }
+        }
+        lu_factor<NX>(W, inv, perm);
+        // right-hand sides [A1 (NX) | b1 | C1 eta2 | C1 A2' (NX)], built in pivot order: row i is the
+        // original row perm[i] of e1 (a runtime-indexed read of the operand view)
+        double X[NX][2 * NX + 2];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const int r = perm[i];
+            double c1[NX];
+#pragma unroll
+            for (int k = 0; k < NX; ++k) c1[k] = e1.C(r, k);
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
                 double ca = 0.0;
 #pragma unroll
-                for (int k = 0; k < NX; ++k) {
-                    w += e1.C(i, k) * e2.J(k, j);
-                    ca += e1.C(i, k) * e2.A(j, k);   // (C1 A2')_{ij}
-                }
-                W[i][j] = w;
-                X[i][j] = e1.A(i, j);
+                for (int k = 0; k < NX; ++k) ca += c1[k] * e2.A(j, k);   // (C1 A2')_{rj}
+                X[i][j] = e1.A(r, j);
                 X[i][NX + 2 + j] = ca;
             }
             double s = 0.0;
 #pragma unroll
-            for (int k = 0; k < NX; ++k) s += e1.C(i, k) * e2.eta(k);
-            X[i][NX] = e1.b(i);
+            for (int k = 0; k < NX; ++k) s += c1[k] * e2.eta(k);
+            X[i][NX] = e1.b(r);
             X[i][NX + 1] = s;
         }
-        lu_solve<NX, 2 * NX + 2>(W, X);
+        lu_subst<NX, 2 * NX + 2>(W, inv, X);
         double JX[NX][NX + 1];   // J2 [XA | xb]
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
@@ -342,9 +420,6 @@ struct RicOp {
             }
         }
         out = o;
-    }
-    IPOC_DEV static void compose(Elem& out, const Elem& first, const Elem& second) {
-        compose_t<Elem, Elem>(out, first, second);
     }
 
     // Push a value function (S, v) at the end of segment e back to its start:
