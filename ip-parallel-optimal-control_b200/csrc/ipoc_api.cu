@@ -321,7 +321,7 @@ static __global__ void k_accept_update(int batch, const double* __restrict__ cos
 // =================================================================== C ABI
 using namespace ipoc;
 
-#define IPOC_FOR_NX(X) X(1) X(2) X(3) X(4) X(6) X(8)
+#define IPOC_FOR_NX(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 
 extern "C" {
 

@@ -7,11 +7,14 @@
 
 namespace ipoc {
 
-// nu values instantiated for this NX
-#if IPOC_NX == 2 || IPOC_NX == 4
-#define IPOC_FOR_NU(X) X(1) X(2)
-#else
+// nu values instantiated for this NX (every extra pair costs compile time: the leaf kernels are
+// instantiated per (NX, NU) and per loader)
+#if IPOC_NX == 1
 #define IPOC_FOR_NU(X) X(1)
+#elif IPOC_NX == 6
+#define IPOC_FOR_NU(X) X(1) X(2) X(3)
+#else
+#define IPOC_FOR_NU(X) X(1) X(2)
 #endif
 constexpr int NXc = IPOC_NX;
 

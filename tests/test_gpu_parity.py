@@ -54,7 +54,8 @@ def test_library_loaded_and_supported():
     assert b"no CPU fallback" in L.ipoc_strerror(-1)
 
 
-@pytest.mark.parametrize("nx,nu", [(2, 1), (4, 1), (3, 1), (2, 2), (4, 2), (1, 1), (6, 1), (8, 1)])
+@pytest.mark.parametrize("nx,nu", [(2, 1), (4, 1), (3, 1), (2, 2), (4, 2), (1, 1), (6, 1), (8, 1),
+                                   (3, 2), (5, 1), (5, 2), (6, 2), (6, 3), (7, 1), (7, 2), (8, 2)])
 @pytest.mark.parametrize("N", [1, 2, 3, 31, 32, 33, 500])
 def test_newton_step_vs_oracle(nx, nu, N):
     from ipoc_b200 import noc
@@ -427,7 +428,7 @@ def test_host_buffer_entry_point_and_error_codes():
     call = lambda nx_, wsb, fxp: L.ipoc_newton_step_f64(N, nx_, nu, 1, fxp, *(dp(t) for t in dev[1:]), dp(regd),
                                                         *(dp(t) for t in outs), dp(ws), wsb, _lib.stream_ptr())
     assert call(nx, 64, dp(dev[0])) == -2                      # IPOC_EWORKSPACE
-    assert call(5, 1 << 20, dp(dev[0])) == -1                  # IPOC_EUNSUPPORTED_DIM
+    assert call(9, 1 << 20, dp(dev[0])) == -1                  # IPOC_EUNSUPPORTED_DIM
     assert call(nx, 1 << 20, ctypes.c_void_p(dev[0].data_ptr() + 8)) == -6   # IPOC_EALIGN
     assert b"workspace" in L.ipoc_strerror(-2)
 
