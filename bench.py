@@ -456,6 +456,43 @@ def run_ours(args):
             except Exception as e:
                 batched_solves.append({"problem": prob_, "error": repr(e)[:200]})
 
+    # ---- BASELINE config 3 as written (ref examples/linear_mpc_parallel.py:67-81): 5000 receding-horizon steps,
+    #      each = par_bwd_pass + par_fwd_pass on the T = 5 double-integrator LQT; the whole loop is timed, like the
+    #      reference does (after one untimed run).  CPU side: the oracle's par passes on a 300-step sample.
+    mpc = None
+    if rank == 0 and world == 1 and not args.no_solve:
+        try:
+            from ipoc_b200 import problems as _pb3
+            from ipoc_b200.paroc import LQT as _LQT
+            from ipoc_b200.mpc import MpcLoop
+            fields_, x0m = _pb3.make_mpc_lqt_terms(T=5, device=dev)
+            mpc = {"steps": 5000, "horizon_T": 5, "unroll_per_graph": 100}
+            for label, serial in (("par", False), ("seq", True)):
+                loop = MpcLoop(_LQT(*fields_), unroll=100, serial=serial)
+                loop.run(x0m, 5000)
+                torch.cuda.synchronize(dev)
+                tm = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    xs_m, us_m = loop.run(x0m, 5000)
+                    torch.cuda.synchronize(dev)
+                    tm.append(time.perf_counter() - t0)
+                mpc[f"{label}_loop_seconds"] = float(np.median(tm))
+                mpc[f"{label}_final_state"] = [float(v) for v in xs_m[-1]]
+            if not args.no_cpu:
+                from oracle import paroc_np as _pn
+                lq_ = _pn.LQT(*(f.cpu().numpy() for f in fields_))
+                xk = x0m.cpu().numpy()
+                t0 = time.perf_counter()
+                for _ in range(300):
+                    Kx_, d_ = _pn.par_bwd_pass(lq_)[:2]
+                    _, xo_ = _pn.par_fwd_pass(lq_, xk, Kx_, d_)
+                    xk = xo_[1]
+                mpc["cpu_port_seconds_per_5000_steps"] = (time.perf_counter() - t0) * 5000 / 300
+                mpc["cpu_port_sample"] = "300 MPC steps of the NumPy oracle's par passes, scaled to 5000"
+        except Exception as e:
+            mpc = {"error": repr(e)[:200]}
+
     # ---- B3 proxy: the same Newton step as a log-depth tree scan of batched torch ops on this
     #      GPU — structurally what XLA:GPU emits for lax.associative_scan; NOT the reference (JAX is absent).
     proxy = None
@@ -525,6 +562,7 @@ def run_ours(args):
             "solves": solves,
             "solves_note": "built-in plant kernels (fused derivatives/cost/rollout) " + ("ON" if plant_fast_path else "off"),
             "batched_solves": batched_solves,
+            "mpc": mpc,
         }
         if cpu:
             line["cpu_baseline"] = cpu

@@ -1,0 +1,105 @@
+"""Receding-horizon loop of the reference's linear MPC example (BASELINE config 3,
+ref examples/linear_mpc_parallel.py:67-81): every MPC step runs `par_bwd_pass(lqt)` and
+`par_fwd_pass(lqt, x, Kx, d)` on a fixed LQT problem and keeps `x_par[1]`, `u_par[0]`.
+
+In the reference the loop is a `jax.lax.scan` inside one XLA executable; here `unroll` consecutive MPC
+steps are captured into ONE CUDA graph: step i reads its initial state straight from the trajectory
+buffer of step i-1 (`x_{i-1}[1]`), so the graph contains nothing but the kernels of the two passes, and
+a 5000-step simulation is 5000/unroll graph launches.  As in the reference, the backward pass is
+recomputed every step even though the problem does not change ("as written").
+"""
+import torch
+from . import _lib as L
+from .paroc import LQT, _effective
+
+
+class MpcLoop:
+    def __init__(self, lqt: LQT, unroll: int = 100, serial: bool = False):
+        """serial=True runs the `seq_bwd_pass` / `seq_fwd_pass` twins (one chunk per horizon)."""
+        lqt = LQT(*(L.dev_f64(t) for t in lqt))
+        if lqt.A.dim() != 3:
+            raise L.IpocError("MpcLoop takes one (unbatched) LQT problem")
+        self.dev = dev = lqt.A.device
+        self.T, self.nx, self.nu = lqt.A.shape[0], lqt.A.shape[1], lqt.B.shape[-1]
+        L.require_supported(self.nx, self.nu)
+        self.unroll, self.serial = int(unroll), bool(serial)
+        # H, Z, r, s folded once (host-framework glue of the wrapper; the passes themselves run every step)
+        self.A, self.B, self.c = (t.unsqueeze(0).contiguous() for t in (lqt.A, lqt.B, lqt.c))
+        self.eff = tuple(L.dev_f64(t.unsqueeze(0)).contiguous() for t in _effective(lqt))
+        o = dict(dtype=torch.float64, device=dev)
+        T, nx, nu, K = self.T, self.nx, self.nu, self.unroll
+        self.Kx, self.d = torch.empty(1, T, nu, nx, **o), torch.empty(1, T, nu, **o)
+        self.S, self.v = torch.empty(1, T + 1, nx, nx, **o), torch.empty(1, T + 1, nx, **o)
+        self.pred, self.feas = torch.empty(1, **o), torch.empty(1, dtype=torch.int32, device=dev)
+        # trajectory of every unrolled step; rows padded to an even number of doubles (the C ABI wants
+        # 16-byte aligned pointers)
+        even = lambda n: n + (n & 1)
+        self._Xp = torch.zeros(K, even((T + 1) * nx), **o)
+        self._Up = torch.zeros(K, even(T * nu), **o)
+        self.X = self._Xp[:, :(T + 1) * nx].view(K, T + 1, nx)
+        self.U = self._Up[:, :T * nu].view(K, T, nu)
+        self.xstart = torch.zeros(nx, **o)
+        self._xin = torch.zeros(K, even(nx), **o) if nx & 1 else None   # odd nx: x_{i-1}[1] is not 16-byte aligned
+        self.ws_b, self.nb_b = L.workspace(L.WS_LQT_BWD, T, nx, nu, 1, dev)
+        self.ws_f, self.nb_f = L.workspace(L.WS_LQT_FWD, T, nx, nu, 1, dev)
+        self.ws_b, self.ws_f = self.ws_b.clone(), self.ws_f.clone()   # private: the graph keeps their addresses
+        self.graph = None
+
+    def _step(self, x0, i):
+        """One MPC step: backward pass, forward pass from x0 -> trajectory i."""
+        p, lib, s = L.ptr, L.lib(), L.stream_ptr()
+        Xe, Ue, Me, q, pp, ST, vT = self.eff
+        L.check(lib.ipoc_lqt_bwd_f64(self.T, self.nx, self.nu, 1, p(self.A), p(self.B), p(self.c), p(Xe), p(Ue),
+                                     p(Me), p(q), p(pp), p(ST), p(vT), p(self.Kx), p(self.d), p(self.S), p(self.v),
+                                     p(self.pred), p(self.feas), p(self.ws_b), self.nb_b, s))
+        L.check(lib.ipoc_lqt_fwd_f64(self.T, self.nx, self.nu, 1, p(self.A), p(self.B), p(self.c), p(self.Kx),
+                                     p(self.d), p(x0), p(self.U[i]), p(self.X[i]), p(self.ws_f), self.nb_f, s))
+
+    def _chunk(self):
+        for i in range(self.unroll):
+            x0 = self.xstart if i == 0 else self.X[i - 1, 1]
+            if i > 0 and self._xin is not None:
+                x0 = self._xin[i, :self.nx].copy_(x0)
+            self._step(x0, i)
+
+    def _with_tuning(self, fn):
+        prev = L.set_tuning(leaf_chunk=self.T) if self.serial else None
+        try:
+            fn()
+        finally:
+            if prev is not None:
+                L.set_tuning(*prev)
+
+    def capture(self):
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self._with_tuning(lambda: self._step(self.xstart, 0))      # lazy initialisations outside the capture
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+
+        def cap():
+            with torch.cuda.graph(g):
+                self._chunk()
+        self._with_tuning(cap)
+        self.graph = g
+
+    def run(self, x0, steps: int, use_graph: bool = True):
+        """-> (xs (steps, nx), us (steps, nu)): the closed-loop states x_par[1] and controls u_par[0]."""
+        if use_graph and self.graph is None:
+            self.capture()
+        xs, us = [], []
+        self.xstart.copy_(L.dev_f64(x0, self.dev))
+        done = 0
+        while done < steps:
+            if use_graph:
+                self.graph.replay()
+            else:
+                self._with_tuning(self._chunk)
+            k = min(self.unroll, steps - done)
+            xs.append(self.X[:k, 1].clone())
+            us.append(self.U[:k, 0].clone())
+            self.xstart.copy_(self.X[k - 1, 1])
+            done += k
+        return torch.cat(xs), torch.cat(us)

@@ -185,6 +185,16 @@ def test_mpc_example_par_equals_seq():
         xs_seq.append(xk)
         us_seq.append(u_seq[0])
     assert relerr(xs_par, np.array(xs_seq)) < 1e-10 and relerr(us_par, np.array(us_seq)) < 1e-10
+    # the graph-unrolled loop (chunks of 7 steps, so 300 steps cross many chunk boundaries) and its serial twin
+    from ipoc_b200.mpc import MpcLoop
+    for serial in (False, True):
+        xs_g, us_g = MpcLoop(lqt, unroll=7, serial=serial).run(x0, steps)
+        assert xs_g.shape == (steps, 2) and us_g.shape == (steps, 1)
+        if not serial:
+            assert np.array_equal(N_(xs_g), xs_par) and np.array_equal(N_(us_g), us_par)
+        assert relerr(N_(xs_g), np.array(xs_seq)) < 1e-10 and relerr(N_(us_g), np.array(us_seq)) < 1e-10
+    xs_e, us_e = MpcLoop(lqt, unroll=16).run(x0, 40, use_graph=False)
+    assert np.array_equal(N_(xs_e), xs_par[:40]) and np.array_equal(N_(us_e), us_par[:40])
 
 
 @pytest.mark.parametrize("nx,nu,N,B", [(2, 1, 100, 7), (4, 1, 64, 33), (4, 1, 1000, 300), (2, 1, 1000, 40000)])
