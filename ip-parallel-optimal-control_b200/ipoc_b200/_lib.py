@@ -110,6 +110,7 @@ def stream_ptr():
 
 
 _ws_cache = {}
+_ws_retired = []
 
 
 def workspace(kind, N, nx, nu, batch, device):
@@ -120,7 +121,11 @@ def workspace(kind, N, nx, nu, batch, device):
     key = (torch.device(device).index or 0, kind)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < need:
-        buf = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=device)
+        if buf is not None:
+            # captured CUDA graphs (graphed.py, batched.py, sharded.py) hold the old buffer's address:
+            # retire it instead of freeing it, so that replaying them can never touch someone else's memory
+            _ws_retired.append(buf)
+        buf = torch.empty(int(need * 2) + 1024, dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf, need
 

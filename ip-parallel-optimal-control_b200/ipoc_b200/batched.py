@@ -49,7 +49,119 @@ def compute_derivatives_batched(ocp: OCP, states, controls, bp) -> Derivatives:
     return Derivatives(*(t.reshape((B, N) + tuple(t.shape[1:])).contiguous() for t in flat))
 
 
-def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
+class _TailGraph:
+    """Static-shape accept/reject attempt body for the LAST few members of an attempt loop.
+
+    A batched solve spends most of its attempts on a handful of hard members (cartpole, 2048 OCPs: 18.8 k of
+    19.4 k attempt trips run on <= 8 members, 13.7 k on exactly one), where the ~25 small host-framework ops and
+    the host sync of the eager trip cost 4x the kernels.  When <= K members are left, their rows are copied
+    once into static buffers and the attempt body (ref noc/par_interior_point_newton.py:153-175) is replayed
+    as one CUDA graph; finished members are frozen by their `done` flag exactly like the `select` of a
+    vmapped `lax.while_loop`, so replaying in bursts between host checks cannot change any result."""
+    K = 8
+    BURST = 4
+
+    def __init__(self, ocp, N, nx, nu, dev):
+        self.ocp = ocp
+        K = self.K
+        o = dict(dtype=torch.float64, device=dev)
+        eye = torch.eye(nx, **o)
+        self.fx = eye.repeat(K, N, 1, 1)
+        self.fu = torch.zeros(K, N, nx, nu, **o)
+        self.ru = torch.zeros(K, N, nu, **o)
+        self.Q = eye.repeat(K, N, 1, 1)
+        self.R = torch.eye(nu, **o).repeat(K, N, 1, 1)
+        self.M = torch.zeros(K, N, nx, nu, **o)
+        self.x, self.tx = torch.zeros(K, N + 1, nx, **o), torch.zeros(K, N + 1, nx, **o)
+        self.u, self.tu = torch.zeros(K, N, nu, **o), torch.zeros(K, N, nu, **o)
+        self.cost, self.cu_norm = torch.zeros(K, **o), torch.zeros(K, **o)
+        self.rp, self.rinc = torch.ones(K, **o), torch.full((K,), 2.0, **o)
+        self.inner = torch.zeros(K, dtype=torch.int64, device=dev)
+        self.done = torch.ones(K, dtype=torch.bool, device=dev)
+        self.bp = torch.zeros((), **o)
+        self.rows = (self.fx, self.fu, self.ru, self.Q, self.R, self.M, self.x, self.u, self.cost, self.cu_norm)
+        self.graph = None
+
+    def _body(self):
+        act = (~self.done).to(torch.int32)
+        m = ~self.done
+        dx, du, _, _, pred, bwd_feas = newton_step(self.fx, self.fu, self.ru, self.Q, self.R, self.M,
+                                                   self.rp * self.cu_norm)                      # :153
+        cx_try, cu_try = self.x + dx, self.u + du                                               # :156-157
+        new_cost, traj_feas = eval_trial(self.ocp, cx_try, cu_try, self.bp)                     # :159-163
+        succ, _ = accept_update(self.cost, new_cost.contiguous(), traj_feas, pred, bwd_feas, self.rp, self.rinc,
+                                active=act)                                                     # :159-173
+        self.tx.copy_(torch.where(m[:, None, None], cx_try, self.tx))                           # :175
+        self.tu.copy_(torch.where(m[:, None, None], cu_try, self.tu))
+        self.inner.add_(act.to(torch.int64))                                                    # :174
+        self.done.logical_or_(m & ((succ != 0) | (self.inner > 500)))                           # :177-182
+
+    def capture(self):
+        dev = self.fx.device
+        keep = self.done.clone()
+        self.done.fill_(True)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body()
+        self.graph = g
+        self.done.copy_(keep)
+
+    def run(self, rows, rp, rinc, tx, tu, inner, bp):
+        """rows: the k <= K members' (fx, fu, ru, Q, R, M, x, u, cost, cu_norm); the other arguments their loop
+        state.  Runs the members' attempt loops to completion -> (rp, rinc, tx, tu, inner) of the k members."""
+        k = rp.numel()
+        for dst, src in zip(self.rows, rows):
+            dst[:k].copy_(src)
+        self.rp[:k].copy_(rp)
+        self.rinc[:k].copy_(rinc)
+        self.tx[:k].copy_(tx)
+        self.tu[:k].copy_(tu)
+        self.inner[:k].copy_(inner)
+        self.done.fill_(True)
+        self.done[:k] = False
+        self.bp.fill_(float(bp))
+        while True:
+            for _ in range(self.BURST):
+                self.graph.replay()
+            if bool(self.done.all()):
+                break
+        return self.rp[:k].clone(), self.rinc[:k].clone(), self.tx[:k].clone(), self.tu[:k].clone(), \
+            self.inner[:k].clone()
+
+
+_tail_cache = {}
+
+
+def _tail_graph(ocp, N, nx, nu, dev):
+    """Captured tail body for this problem / horizon, or None if the OCP's callables cannot be captured."""
+    key = (id(ocp.dynamics), id(ocp.stage_cost), id(ocp.final_cost), id(ocp.constraints), id(ocp.total_cost),
+           N, nx, nu, str(dev), plants.ENABLED)
+    g = _tail_cache.get(key)
+    if g is None:
+        g = _TailGraph(ocp, N, nx, nu, dev)
+        try:
+            g.capture()
+            g._keepalive = ocp
+        except Exception as e:
+            import warnings
+            warnings.warn(f"ipoc_b200: CUDA-graph capture of the batched attempt body failed "
+                          f"({type(e).__name__}: {str(e)[:120]}); using eager launches")
+            torch.cuda.synchronize(dev)
+            g = False
+        while len(_tail_cache) >= 4:
+            _tail_cache.pop(next(iter(_tail_cache)))
+        _tail_cache[key] = g
+    return g or None
+
+
+def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param, use_graphs: bool = True):
     """Per-member semantics of ref noc/par_interior_point_newton.py:127-225 for a batch.
     -> (x (B,N+1,nx), u (B,N,nu), iterations (B,) int64)
 
@@ -68,6 +180,7 @@ def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
     rp_all = torch.ones(B, **o)                                                    # :134
     rinc_all = torch.full((B,), 2.0, **o)                                          # :135
     iters = torch.zeros(B, dtype=torch.int64, device=dev)
+    tail = _tail_graph(ocp, u_all.shape[1], x_all.shape[-1], u_all.shape[-1], dev) if use_graphs else None
     act = torch.arange(B, device=dev)                                              # members still in the Newton loop
     while act.numel() > 0:                                                         # :199-202 (per member)
         full = act.numel() == B
@@ -80,6 +193,11 @@ def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
         inner = torch.zeros(na, dtype=torch.int64, device=dev)
         sub = torch.arange(na, device=dev)                                         # members still in the attempt loop
         while sub.numel() > 0:                                                     # :177-182 (per member)
+            if tail is not None and sub.numel() <= tail.K:
+                rows = tuple(t.index_select(0, sub) for t in (fx, fu, ru, Q, R, M, x, u, cost, cu_norm))
+                rp[sub], rinc[sub], tx[sub], tu[sub], inner[sub] = tail.run(rows, rp[sub], rinc[sub], tx[sub],
+                                                                            tu[sub], inner[sub], barrier_param)
+                break
             if sub.numel() == na:
                 a = (fx, fu, ru, Q, R, M, x, u, cost, cu_norm)
             else:
@@ -103,7 +221,7 @@ def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param):
     return x_all, u_all, iters
 
 
-def par_interior_point_optimal_control_batched(ocp: OCP, controls, initial_states):
+def par_interior_point_optimal_control_batched(ocp: OCP, controls, initial_states, use_graphs: bool = True):
     """Batched `par_interior_point_optimal_control` (ref :228-254): controls (B,N,nu), initial_states (B,nx)
     -> (opt_u (B,N,nu), N_iterations (B,) int64)."""
     if not controls.is_cuda:
@@ -112,7 +230,7 @@ def par_interior_point_optimal_control_batched(ocp: OCP, controls, initial_state
     total = torch.zeros(controls.shape[0], dtype=torch.int64, device=controls.device)
     bp = 0.1                                                                       # :233
     while bp > 1e-4:                                                               # :243-245
-        _, u, its = newton_oc_batched(ocp, u, initial_states, bp)                  # :237
+        _, u, its = newton_oc_batched(ocp, u, initial_states, bp, use_graphs)      # :237
         bp = bp / 5                                                                # :238
         total = total + its                                                        # :239
     return u, total

@@ -364,6 +364,9 @@ def test_batched_solver_equals_per_problem_solves(problem, N, B):
         u1, it1 = noc.par_interior_point_optimal_control(ocp, T(u0s[b]), T(x0s[b]))
         assert int(itb[b]) == it1
         assert relerr(N_(ub[b]), N_(u1)) < 1e-8
+    # the graph-replayed tail of the attempt loops (<= 8 members left) against the all-eager loop
+    ue, ite = batched.par_interior_point_optimal_control_batched(ocp, T(u0s), T(x0s), use_graphs=False)
+    assert torch.equal(ite, itb) and relerr(N_(ue), N_(ub)) < 1e-9
 
 
 @pytest.mark.parametrize("problem,N", [("cartpole", 3000), ("pendulum", 2500)])
