@@ -165,6 +165,21 @@ int ipoc_accept_update_f64(int batch, const double* cost, const double* new_cost
                            double* rp, double* r_inc, int32_t* success, double* gain_ratio,
                            ipoc_stream_t stream);
 
+/* ---- attempt-loop glue of `while_inner_loop` (ref noc/par_interior_point_newton.py:151-182) for `batch`
+ * independent problems whose loops run on the device (frozen-when-done, like a vmapped lax.while_loop):
+ *   begin : active = !done (all active if done == NULL);  reg = rp * cu_norm            (ref :117, :177-182)
+ *   trial : tx = x + dx ((N+1)*nx per problem),  tu = u + du (N*nu)                      (ref :156-157)
+ *   commit: for active problems  keep_x <- tx, keep_u <- tu (ref :175, kept whether or not the attempt
+ *           succeeded), inner += 1 (:174), done |= success || inner > max_attempts (:180-181)
+ * `done` is one byte per problem (0/1), `inner` int64, `active`/`success` int32. */
+int ipoc_attempt_begin_f64(int batch, const uint8_t* done, const double* rp, const double* cu_norm,
+                           int32_t* active, double* reg, ipoc_stream_t stream);
+int ipoc_trial_point_f64(int N, int nx, int nu, int batch, const double* x, const double* dx, const double* u,
+                         const double* du, double* tx, double* tu, ipoc_stream_t stream);
+int ipoc_attempt_commit_f64(int N, int nx, int nu, int batch, const int32_t* active, const int32_t* success,
+                            const double* tx, const double* tu, double* keep_x, double* keep_u,
+                            int64_t* inner, uint8_t* done, int max_attempts, ipoc_stream_t stream);
+
 /* ---- time-sharded (multi-GPU) split-phase variants -----------------------------------------
  * A horizon of P*N steps is cut into P contiguous segments, one per rank (no reference
  * counterpart — the reference is single-device).  Each scan is: local reduce -> exchange of

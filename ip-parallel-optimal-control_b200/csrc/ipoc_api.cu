@@ -316,6 +316,48 @@ static __global__ void k_accept_update(int batch, const double* __restrict__ cos
     if (gain_ratio != nullptr) gain_ratio[b] = rho;
 }
 
+// ---- attempt-loop glue (see include/ipoc.h) ---------------------------------------------------
+static __global__ void k_attempt_begin(int batch, const uint8_t* __restrict__ done, const double* __restrict__ rp,
+                                       const double* __restrict__ cu_norm, int32_t* __restrict__ active,
+                                       double* __restrict__ reg) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    active[b] = (done == nullptr || done[b] == 0) ? 1 : 0;
+    reg[b] = rp[b] * cu_norm[b];
+}
+
+static __global__ void k_trial_point(long long nxs, long long nus, const double* __restrict__ x,
+                                     const double* __restrict__ dx, const double* __restrict__ u,
+                                     const double* __restrict__ du, double* __restrict__ tx, double* __restrict__ tu) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nxs) {
+        tx[i] = x[i] + dx[i];
+    } else if (i < nxs + nus) {
+        const long long j = i - nxs;
+        tu[j] = u[j] + du[j];
+    }
+}
+
+constexpr int kCommitThreads = 256;
+static __global__ void k_attempt_commit(long long per_x, long long per_u, int chunks, const int32_t* __restrict__ active,
+                                        const int32_t* __restrict__ success, const double* __restrict__ tx,
+                                        const double* __restrict__ tu, double* __restrict__ keep_x,
+                                        double* __restrict__ keep_u, long long* __restrict__ inner,
+                                        uint8_t* __restrict__ done, int max_attempts) {
+    const int b = blockIdx.x / chunks, ch = blockIdx.x % chunks;
+    if (!active[b]) return;                      // `active` is not written here: no block can see a changed flag
+    const long long per = per_x + per_u;
+    for (long long i = (long long)ch * kCommitThreads + threadIdx.x; i < per; i += (long long)chunks * kCommitThreads) {
+        if (i < per_x) keep_x[b * per_x + i] = tx[b * per_x + i];
+        else keep_u[b * per_u + (i - per_x)] = tu[b * per_u + (i - per_x)];
+    }
+    if (ch == 0 && threadIdx.x == 0) {
+        const long long n = inner[b] + 1;
+        inner[b] = n;
+        if (success[b] != 0 || n > max_attempts) done[b] = 1;
+    }
+}
+
 }  // namespace ipoc
 
 // =================================================================== C ABI
@@ -471,6 +513,41 @@ int ipoc_accept_update_f64(int batch, const double* cost, const double* new_cost
     k_accept_update<<<(batch + 127) / 128, 128, 0, st_>>>(batch, cost, new_cost, traj_feasible, pred,
                                                                             bwd_feasible, active, rp, r_inc, success,
                                                                             gain_ratio);
+    IPOC_API_LAUNCH_CHECK(st_);
+    return IPOC_OK;
+}
+
+int ipoc_attempt_begin_f64(int batch, const uint8_t* done, const double* rp, const double* cu_norm, int32_t* active,
+                           double* reg, ipoc_stream_t stream) {
+    CHECK_ARGS(batch >= 1 && rp && cu_norm && active && reg);
+    cudaStream_t st_ = (cudaStream_t)stream;
+    k_attempt_begin<<<(batch + 127) / 128, 128, 0, st_>>>(batch, done, rp, cu_norm, active, reg);
+    IPOC_API_LAUNCH_CHECK(st_);
+    return IPOC_OK;
+}
+
+int ipoc_trial_point_f64(int N, int nx, int nu, int batch, const double* x, const double* dx, const double* u,
+                         const double* du, double* tx, double* tu, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && nx >= 1 && nu >= 1 && batch >= 1 && x && dx && u && du && tx && tu);
+    cudaStream_t st_ = (cudaStream_t)stream;
+    const long long nxs = (long long)batch * (N + 1) * nx, nus = (long long)batch * N * nu;
+    k_trial_point<<<(unsigned)((nxs + nus + 255) / 256), 256, 0, st_>>>(nxs, nus, x, dx, u, du, tx, tu);
+    IPOC_API_LAUNCH_CHECK(st_);
+    return IPOC_OK;
+}
+
+int ipoc_attempt_commit_f64(int N, int nx, int nu, int batch, const int32_t* active, const int32_t* success,
+                            const double* tx, const double* tu, double* keep_x, double* keep_u, int64_t* inner,
+                            uint8_t* done, int max_attempts, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && nx >= 1 && nu >= 1 && batch >= 1 && active && success && tx && tu && keep_x && keep_u && inner && done);
+    cudaStream_t st_ = (cudaStream_t)stream;
+    const long long per_x = (long long)(N + 1) * nx, per_u = (long long)N * nu;
+    long long chunks = (per_x + per_u + 4 * kCommitThreads - 1) / (4 * kCommitThreads);   // ~4 entries per thread
+    const long long cap = (long long)148 * 16 / batch;
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    k_attempt_commit<<<(unsigned)(chunks * batch), kCommitThreads, 0, st_>>>(
+        per_x, per_u, (int)chunks, active, success, tx, tu, keep_x, keep_u, (long long*)inner, done, max_attempts);
     IPOC_API_LAUNCH_CHECK(st_);
     return IPOC_OK;
 }

@@ -15,7 +15,8 @@ import torch
 from torch.func import vmap, grad, hessian, jacrev
 from . import _lib as L
 from .optimal_control_problem import OCP, Derivatives
-from .noc import reductions, newton_step, accept_update, eval_iteration, eval_trial
+from .noc import (reductions, newton_step, accept_update, eval_iteration, eval_trial, attempt_begin, trial_point,
+                  attempt_commit)
 from . import plants
 
 
@@ -57,13 +58,14 @@ class _TailGraph:
     the host sync of the eager trip cost 4x the kernels.  When <= K members are left, their rows are copied
     once into static buffers and the attempt body (ref noc/par_interior_point_newton.py:153-175) is replayed
     as one CUDA graph; finished members are frozen by their `done` flag exactly like the `select` of a
-    vmapped `lax.while_loop`, so replaying in bursts between host checks cannot change any result."""
-    K = 8
-    BURST = 4
+    vmapped `lax.while_loop`, so replaying in bursts between host checks cannot change any result.
+    Two sizes are kept (SIZES): a session starts in the smallest graph that holds its members and migrates
+    to the smaller one when enough of them have finished (a replay costs roughly in proportion to K)."""
+    SIZES = (8, 32)
+    BURST = 8
 
-    def __init__(self, ocp, N, nx, nu, dev):
-        self.ocp = ocp
-        K = self.K
+    def __init__(self, ocp, N, nx, nu, dev, K):
+        self.ocp, self.K = ocp, K
         o = dict(dtype=torch.float64, device=dev)
         eye = torch.eye(nx, **o)
         self.fx = eye.repeat(K, N, 1, 1)
@@ -79,26 +81,28 @@ class _TailGraph:
         self.inner = torch.zeros(K, dtype=torch.int64, device=dev)
         self.done = torch.ones(K, dtype=torch.bool, device=dev)
         self.bp = torch.zeros((), **o)
+        self.cx, self.cu = torch.zeros(K, N + 1, nx, **o), torch.zeros(K, N, nu, **o)   # trial point
+        self.act = torch.zeros(K, dtype=torch.int32, device=dev)
+        self.succ = torch.zeros(K, dtype=torch.int32, device=dev)
+        self.reg, self.gain = torch.zeros(K, **o), torch.zeros(K, **o)
         self.rows = (self.fx, self.fu, self.ru, self.Q, self.R, self.M, self.x, self.u, self.cost, self.cu_norm)
+        self.state = (self.rp, self.rinc, self.tx, self.tu, self.inner)
         self.graph = None
 
     def _body(self):
-        act = (~self.done).to(torch.int32)
-        m = ~self.done
-        dx, du, _, _, pred, bwd_feas = newton_step(self.fx, self.fu, self.ru, self.Q, self.R, self.M,
-                                                   self.rp * self.cu_norm)                      # :153
-        cx_try, cu_try = self.x + dx, self.u + du                                               # :156-157
-        new_cost, traj_feas = eval_trial(self.ocp, cx_try, cu_try, self.bp)                     # :159-163
-        succ, _ = accept_update(self.cost, new_cost.contiguous(), traj_feas, pred, bwd_feas, self.rp, self.rinc,
-                                active=act)                                                     # :159-173
-        self.tx.copy_(torch.where(m[:, None, None], cx_try, self.tx))                           # :175
-        self.tu.copy_(torch.where(m[:, None, None], cu_try, self.tu))
-        self.inner.add_(act.to(torch.int64))                                                    # :174
-        self.done.logical_or_(m & ((succ != 0) | (self.inner > 500)))                           # :177-182
+        attempt_begin(self.done, self.rp, self.cu_norm, self.act, self.reg)                     # :117, :177-182
+        dx, du, _, _, pred, bwd_feas = newton_step(self.fx, self.fu, self.ru, self.Q, self.R, self.M, self.reg)  # :153
+        trial_point(self.x, dx, self.u, du, self.cx, self.cu)                                   # :156-157
+        new_cost, traj_feas = eval_trial(self.ocp, self.cx, self.cu, self.bp)                   # :159-163
+        with torch.cuda.device(self.rp.device):
+            L.check(L.lib().ipoc_accept_update_f64(self.K, L.ptr(self.cost), L.ptr(new_cost.contiguous()),
+                                                   L.ptr(traj_feas), L.ptr(pred), L.ptr(bwd_feas), L.ptr(self.act),
+                                                   L.ptr(self.rp), L.ptr(self.rinc), L.ptr(self.succ),
+                                                   L.ptr(self.gain), L.stream_ptr()))           # :159-173
+        attempt_commit(self.act, self.succ, self.cx, self.cu, self.tx, self.tu, self.inner, self.done)   # :174-182
 
     def capture(self):
         dev = self.fx.device
-        keep = self.done.clone()
         self.done.fill_(True)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -111,54 +115,68 @@ class _TailGraph:
         with torch.cuda.graph(g):
             self._body()
         self.graph = g
-        self.done.copy_(keep)
 
-    def run(self, rows, rp, rinc, tx, tu, inner, bp):
-        """rows: the k <= K members' (fx, fu, ru, Q, R, M, x, u, cost, cu_norm); the other arguments their loop
-        state.  Runs the members' attempt loops to completion -> (rp, rinc, tx, tu, inner) of the k members."""
-        k = rp.numel()
-        for dst, src in zip(self.rows, rows):
+    def load(self, rows, state, bp):
+        k = state[0].numel()
+        for dst, src in zip(self.rows + self.state, tuple(rows) + tuple(state)):
             dst[:k].copy_(src)
-        self.rp[:k].copy_(rp)
-        self.rinc[:k].copy_(rinc)
-        self.tx[:k].copy_(tx)
-        self.tu[:k].copy_(tu)
-        self.inner[:k].copy_(inner)
         self.done.fill_(True)
         self.done[:k] = False
         self.bp.fill_(float(bp))
-        while True:
-            for _ in range(self.BURST):
-                self.graph.replay()
-            if bool(self.done.all()):
-                break
-        return self.rp[:k].clone(), self.rinc[:k].clone(), self.tx[:k].clone(), self.tu[:k].clone(), \
-            self.inner[:k].clone()
+        return k
+
+
+def _run_tail(graphs, rows, state, bp):
+    """graphs: captured _TailGraph objects by ascending K.  rows = the k members' (fx, fu, ru, Q, R, M, x, u, cost,
+    cu_norm), state = their (rp, rinc, tx, tu, inner).  Runs the members' attempt loops to completion and
+    returns their final state."""
+    k = state[0].numel()
+    level = next(i for i, g in enumerate(graphs) if g.K >= k)
+    g = graphs[level]
+    g.load(rows, state, bp)
+    while True:
+        for _ in range(g.BURST):
+            g.graph.replay()
+        done = g.done[:k].cpu()
+        left = int(k - int(done.sum()))
+        if left == 0:
+            break
+        if level > 0 and left <= graphs[level - 1].K:      # migrate the survivors to the smaller graph
+            idx = torch.nonzero(~done).reshape(-1).to(g.done.device)
+            res = _run_tail(graphs[:level], tuple(r[:k].index_select(0, idx) for r in g.rows),
+                            tuple(t[:k].index_select(0, idx) for t in g.state), bp)
+            for dst, src in zip(g.state, res):
+                dst[idx] = src
+            break
+    return tuple(t[:k].clone() for t in g.state)
 
 
 _tail_cache = {}
 
 
-def _tail_graph(ocp, N, nx, nu, dev):
-    """Captured tail body for this problem / horizon, or None if the OCP's callables cannot be captured."""
+def _tail_graphs(ocp, N, nx, nu, dev):
+    """Captured tail bodies for this problem / horizon (ascending K), or None if the OCP's callables cannot
+    be captured."""
     key = (id(ocp.dynamics), id(ocp.stage_cost), id(ocp.final_cost), id(ocp.constraints), id(ocp.total_cost),
            N, nx, nu, str(dev), plants.ENABLED)
-    g = _tail_cache.get(key)
-    if g is None:
-        g = _TailGraph(ocp, N, nx, nu, dev)
+    gs = _tail_cache.get(key)
+    if gs is None:
         try:
-            g.capture()
-            g._keepalive = ocp
+            gs = []
+            for K in _TailGraph.SIZES:
+                g = _TailGraph(ocp, N, nx, nu, dev, K)
+                g.capture()
+                gs.append(g)
         except Exception as e:
             import warnings
             warnings.warn(f"ipoc_b200: CUDA-graph capture of the batched attempt body failed "
                           f"({type(e).__name__}: {str(e)[:120]}); using eager launches")
             torch.cuda.synchronize(dev)
-            g = False
+            gs = False
         while len(_tail_cache) >= 4:
             _tail_cache.pop(next(iter(_tail_cache)))
-        _tail_cache[key] = g
-    return g or None
+        _tail_cache[key] = gs
+    return gs or None
 
 
 def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param, use_graphs: bool = True):
@@ -180,7 +198,7 @@ def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param, use_gra
     rp_all = torch.ones(B, **o)                                                    # :134
     rinc_all = torch.full((B,), 2.0, **o)                                          # :135
     iters = torch.zeros(B, dtype=torch.int64, device=dev)
-    tail = _tail_graph(ocp, u_all.shape[1], x_all.shape[-1], u_all.shape[-1], dev) if use_graphs else None
+    tail = _tail_graphs(ocp, u_all.shape[1], x_all.shape[-1], u_all.shape[-1], dev) if use_graphs else None
     act = torch.arange(B, device=dev)                                              # members still in the Newton loop
     while act.numel() > 0:                                                         # :199-202 (per member)
         full = act.numel() == B
@@ -193,10 +211,10 @@ def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param, use_gra
         inner = torch.zeros(na, dtype=torch.int64, device=dev)
         sub = torch.arange(na, device=dev)                                         # members still in the attempt loop
         while sub.numel() > 0:                                                     # :177-182 (per member)
-            if tail is not None and sub.numel() <= tail.K:
+            if tail is not None and sub.numel() <= tail[-1].K:
                 rows = tuple(t.index_select(0, sub) for t in (fx, fu, ru, Q, R, M, x, u, cost, cu_norm))
-                rp[sub], rinc[sub], tx[sub], tu[sub], inner[sub] = tail.run(rows, rp[sub], rinc[sub], tx[sub],
-                                                                            tu[sub], inner[sub], barrier_param)
+                rp[sub], rinc[sub], tx[sub], tu[sub], inner[sub] = _run_tail(
+                    tail, rows, (rp[sub], rinc[sub], tx[sub], tu[sub], inner[sub]), barrier_param)
                 break
             if sub.numel() == na:
                 a = (fx, fu, ru, Q, R, M, x, u, cost, cu_norm)

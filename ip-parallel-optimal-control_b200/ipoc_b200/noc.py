@@ -147,6 +147,32 @@ def accept_update(cost, new_cost, traj_feasible, pred, bwd_feasible, rp, r_inc, 
     return success, gain
 
 
+# ------------------------------------------------------------------ attempt-loop glue (one launch each)
+def attempt_begin(done, rp, cu_norm, active, reg):
+    """active <- !done (int32), reg <- rp * ||cu|| (ref :117) for a batch whose attempt loops live on the device."""
+    with torch.cuda.device(rp.device):
+        L.check(L.lib().ipoc_attempt_begin_f64(rp.numel(), L.ptr(done), L.ptr(rp), L.ptr(cu_norm), L.ptr(active),
+                                               L.ptr(reg), L.stream_ptr()))
+
+
+def trial_point(x, dx, u, du, tx, tu):
+    """tx <- x + dx, tu <- u + du (ref :156-157) into preallocated buffers; (B,N+1,nx) / (B,N,nu) tensors."""
+    Bn, N, nx, nu = u.shape[0], u.shape[1], x.shape[-1], u.shape[-1]
+    with torch.cuda.device(x.device):
+        L.check(L.lib().ipoc_trial_point_f64(N, nx, nu, Bn, L.ptr(x), L.ptr(dx), L.ptr(u), L.ptr(du), L.ptr(tx),
+                                             L.ptr(tu), L.stream_ptr()))
+
+
+def attempt_commit(active, success, tx, tu, keep_x, keep_u, inner, done, max_attempts=500):
+    """For active members: keep the trial point (ref :175), inner += 1 (:174), done |= success or inner >
+    max_attempts (:180-181).  `done` is a torch.bool tensor, `inner` int64."""
+    Bn, N, nx, nu = tu.shape[0], tu.shape[1], tx.shape[-1], tu.shape[-1]
+    with torch.cuda.device(tx.device):
+        L.check(L.lib().ipoc_attempt_commit_f64(N, nx, nu, Bn, L.ptr(active), L.ptr(success), L.ptr(tx), L.ptr(tu),
+                                                L.ptr(keep_x), L.ptr(keep_u), L.ptr(inner), L.ptr(done),
+                                                int(max_attempts), L.stream_ptr()))
+
+
 # ------------------------------------------------------------------ K2 + K3: the Newton step
 def newton_step(fx, fu, ru, Q, R, M, reg):
     """Fused device Newton step on LQ data; `reg` is a device tensor (one value per problem).
