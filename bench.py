@@ -114,7 +114,7 @@ class Clocks:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -251,7 +251,6 @@ def run_ours(args):
     npass.capture()
     clocks = Clocks(local) if rank == 0 else None
     ms = time_steps(npass.replay, args.steps, args.warmup, do_flush=True)
-    clk = clocks.stop() if clocks else None
     ms_step = float(np.mean(ms))
     ms_plain = float(np.mean(time_steps(npass.run, args.steps, args.warmup, do_flush=True)))
     ms_warm = float(np.mean(time_steps(npass.replay, args.steps, args.warmup, do_flush=False)))
@@ -306,6 +305,7 @@ def run_ours(args):
     hpass = HostNewtonPass(w, dev)
     hpass.capture()
     ms_e2e = float(np.mean(time_steps(hpass.replay, args.steps, args.warmup, do_flush=True)))
+    clk = clocks.stop() if clocks else None      # sampled across every timed region of the headline workload
     h2d_gbps = h2d_probe(dev)
     h2d, d2h = hpass.h2d_bytes, hpass.d2h_bytes
     for q in (npass, hpass.inner):       # rp / r_inc evolve from pass to pass: compare one pass from equal state
@@ -595,8 +595,8 @@ def _time_local(torch, fn, flush, steps, warmup, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
