@@ -561,3 +561,66 @@ def test_cpu_tensors_are_rejected():
     fx, fu, ru, Q, R, M = (torch.as_tensor(a) for a in random_lq(rng, 8, 2, 1))
     with pytest.raises(_lib.IpocError):
         noc.newton_step(fx, fu, ru, Q, R, M, torch.tensor([0.1]))
+
+
+def test_attempt_glue_kernels_vs_torch():
+    """ipoc_attempt_begin / trial_point / attempt_commit against the few torch statements they replace
+    (ref noc/par_interior_point_newton.py:116-117, 156-157, 174-182)."""
+    from ipoc_b200 import noc
+    rng = np.random.default_rng(11)
+    B, N, nx, nu = 13, 37, 3, 2
+    done = torch.as_tensor(rng.random(B) < 0.4, device=DEV)
+    rp, cun = T(rng.random(B) + 0.1), T(rng.random(B))
+    act = torch.full((B,), -7, dtype=torch.int32, device=DEV)
+    reg = torch.zeros(B, dtype=torch.float64, device=DEV)
+    noc.attempt_begin(done, rp, cun, act, reg)
+    assert torch.equal(act, (~done).to(torch.int32)) and torch.equal(reg, rp * cun)
+    noc.attempt_begin(None, rp, cun, act, reg)
+    assert bool((act == 1).all())
+    x, dx = T(rng.standard_normal((B, N + 1, nx))), T(rng.standard_normal((B, N + 1, nx)))
+    u, du = T(rng.standard_normal((B, N, nu))), T(rng.standard_normal((B, N, nu)))
+    tx, tu = torch.zeros_like(x), torch.zeros_like(u)
+    noc.trial_point(x, dx, u, du, tx, tu)
+    assert torch.equal(tx, x + dx) and torch.equal(tu, u + du)
+    act = (~done).to(torch.int32)
+    succ = torch.as_tensor(rng.random(B) < 0.5, device=DEV).to(torch.int32)
+    inner = torch.as_tensor(rng.integers(0, 3, B), device=DEV)
+    inner[0], inner[1] = 500, 499
+    keep_x, keep_u = T(rng.standard_normal((B, N + 1, nx))), T(rng.standard_normal((B, N, nu)))
+    kx0, ku0, inner0, done0 = keep_x.clone(), keep_u.clone(), inner.clone(), done.clone()
+    noc.attempt_commit(act, succ, tx, tu, keep_x, keep_u, inner, done, max_attempts=500)
+    m = act.bool()
+    assert torch.equal(keep_x, torch.where(m[:, None, None], tx, kx0))
+    assert torch.equal(keep_u, torch.where(m[:, None, None], tu, ku0))
+    assert torch.equal(inner, inner0 + m.to(torch.int64))
+    assert torch.equal(done, done0 | (m & ((succ != 0) | (inner > 500))))
+
+
+@pytest.mark.parametrize("N", [300, 10000])
+def test_host_arena_pass_equals_resident_pass(N):
+    """`runner.HostNewtonPass` (pinned host arena -> overlapped H2D, the pass, D2H; one CUDA graph) returns
+    bit-identical results to the resident `NewtonPass` on the same inputs."""
+    from ipoc_b200 import workloads
+    from ipoc_b200.runner import NewtonPass, HostNewtonPass
+    w = workloads.newton_inputs("cartpole", N, DEV, seed=2, x0_noise=0.01)
+    res = NewtonPass(w["fx"], w["fu"], w["cx"], w["cu"], w["lamT"], w["ru"], w["Q"], w["R"], w["M"], w["cons"])
+    res.run()
+    hp = HostNewtonPass(w, DEV)
+    hp.capture()
+    for v in hp.views.values():          # the graph must read what the host arena holds at replay time
+        assert v.is_pinned()
+    hp.d_in.zero_()
+    hp.inner.rp.fill_(1.0)               # rp / r_inc evolve from pass to pass (A8): start from the same state
+    hp.inner.r_inc.fill_(2.0)
+    hp.replay()
+    torch.cuda.synchronize()
+    for k in ("lam", "dx", "du", "pred", "hu", "cu_norm", "gain", "rp", "r_inc"):
+        assert torch.equal(hp.results[k].to(DEV).reshape(-1), getattr(res, k).reshape(-1)), k
+    assert int(hp.results["bwd_feas"][0]) == int(res.bwd_feas[0]) and int(hp.results["success"][0]) == int(res.success[0])
+    hp.views["ru"].mul_(2.0)             # change an input on the host: the next replay must see it
+    hp.replay()
+    torch.cuda.synchronize()
+    res2 = NewtonPass(w["fx"], w["fu"], w["cx"], w["cu"], w["lamT"], 2.0 * w["ru"], w["Q"], w["R"], w["M"], w["cons"])
+    res2.run()
+    torch.cuda.synchronize()
+    assert torch.equal(hp.results["hu"].to(DEV), res2.hu)
