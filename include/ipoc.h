@@ -180,6 +180,17 @@ int ipoc_attempt_commit_f64(int N, int nx, int nu, int batch, const int32_t* act
                             const double* tx, const double* tu, double* keep_x, double* keep_u,
                             int64_t* inner, uint8_t* done, int max_attempts, ipoc_stream_t stream);
 
+/* ---- Newton-loop glue of `newton_oc` (ref noc/par_interior_point_newton.py:184-202) for device-resident loops:
+ * for every problem that is not finished (`outer_done` == 0) and whose attempt loop has just ended
+ * (`inner_done` != 0):  x <- tx, u <- tu (:184, taken even if no attempt succeeded), iteration += 1 (:194),
+ * inner = 0, inner_done = 0, and outer_done = 1 if hu < hu_tol or iteration > max_iterations (:199-202; `hu` is
+ * max|ru| of the iterate BEFORE the step, as in the reference).  `advanced` (int32 scratch, one per problem)
+ * receives which problems moved on.  Two launches (flags, masked copy). */
+int ipoc_newton_advance_f64(int N, int nx, int nu, int batch, const double* hu, uint8_t* inner_done,
+                            uint8_t* outer_done, int64_t* inner, int64_t* iteration, int32_t* advanced,
+                            const double* tx, const double* tu, double* x, double* u, double hu_tol,
+                            int max_iterations, ipoc_stream_t stream);
+
 /* ---- time-sharded (multi-GPU) split-phase variants -----------------------------------------
  * A horizon of P*N steps is cut into P contiguous segments, one per rank (no reference
  * counterpart — the reference is single-device).  Each scan is: local reduce -> exchange of

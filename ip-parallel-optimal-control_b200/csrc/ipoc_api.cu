@@ -358,6 +358,42 @@ static __global__ void k_attempt_commit(long long per_x, long long per_u, int ch
     }
 }
 
+static __global__ void k_newton_advance_flags(int batch, const double* __restrict__ hu, uint8_t* __restrict__ inner_done,
+                                              uint8_t* __restrict__ outer_done, long long* __restrict__ inner,
+                                              long long* __restrict__ iteration, int32_t* __restrict__ adv,
+                                              double hu_tol, int max_iter) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const int a = (outer_done[b] == 0 && inner_done[b] != 0) ? 1 : 0;
+    adv[b] = a;
+    if (a) {
+        const long long it = iteration[b] + 1;
+        iteration[b] = it;
+        inner[b] = 0;
+        inner_done[b] = 0;
+        if (hu[b] < hu_tol || it > max_iter) outer_done[b] = 1;
+    }
+}
+
+static __global__ void k_masked_copy2(long long per_x, long long per_u, int chunks, const int32_t* __restrict__ mask,
+                                      const double* __restrict__ sx, const double* __restrict__ su,
+                                      double* __restrict__ dx_, double* __restrict__ du_) {
+    const int b = blockIdx.x / chunks, ch = blockIdx.x % chunks;
+    if (!mask[b]) return;
+    const long long per = per_x + per_u;
+    for (long long i = (long long)ch * kCommitThreads + threadIdx.x; i < per; i += (long long)chunks * kCommitThreads) {
+        if (i < per_x) dx_[b * per_x + i] = sx[b * per_x + i];
+        else du_[b * per_u + (i - per_x)] = su[b * per_u + (i - per_x)];
+    }
+}
+
+static inline long long copy_chunks(long long per, int batch) {
+    long long chunks = (per + 4 * kCommitThreads - 1) / (4 * kCommitThreads);   // ~4 entries per thread
+    const long long cap = (long long)148 * 16 / batch;
+    if (chunks > cap) chunks = cap;
+    return chunks < 1 ? 1 : chunks;
+}
+
 }  // namespace ipoc
 
 // =================================================================== C ABI
@@ -542,12 +578,27 @@ int ipoc_attempt_commit_f64(int N, int nx, int nu, int batch, const int32_t* act
     CHECK_ARGS(N >= 1 && nx >= 1 && nu >= 1 && batch >= 1 && active && success && tx && tu && keep_x && keep_u && inner && done);
     cudaStream_t st_ = (cudaStream_t)stream;
     const long long per_x = (long long)(N + 1) * nx, per_u = (long long)N * nu;
-    long long chunks = (per_x + per_u + 4 * kCommitThreads - 1) / (4 * kCommitThreads);   // ~4 entries per thread
-    const long long cap = (long long)148 * 16 / batch;
-    if (chunks > cap) chunks = cap;
-    if (chunks < 1) chunks = 1;
+    const long long chunks = copy_chunks(per_x + per_u, batch);
     k_attempt_commit<<<(unsigned)(chunks * batch), kCommitThreads, 0, st_>>>(
         per_x, per_u, (int)chunks, active, success, tx, tu, keep_x, keep_u, (long long*)inner, done, max_attempts);
+    IPOC_API_LAUNCH_CHECK(st_);
+    return IPOC_OK;
+}
+
+int ipoc_newton_advance_f64(int N, int nx, int nu, int batch, const double* hu, uint8_t* inner_done,
+                            uint8_t* outer_done, int64_t* inner, int64_t* iteration, int32_t* advanced,
+                            const double* tx, const double* tu, double* x, double* u, double hu_tol,
+                            int max_iterations, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && nx >= 1 && nu >= 1 && batch >= 1 && hu && inner_done && outer_done && inner && iteration && advanced && tx && tu && x && u);
+    cudaStream_t st_ = (cudaStream_t)stream;
+    k_newton_advance_flags<<<(batch + 127) / 128, 128, 0, st_>>>(batch, hu, inner_done, outer_done, (long long*)inner,
+                                                               (long long*)iteration, advanced, hu_tol,
+                                                               max_iterations);
+    IPOC_API_LAUNCH_CHECK(st_);
+    const long long per_x = (long long)(N + 1) * nx, per_u = (long long)N * nu;
+    const long long chunks = copy_chunks(per_x + per_u, batch);
+    k_masked_copy2<<<(unsigned)(chunks * batch), kCommitThreads, 0, st_>>>(per_x, per_u, (int)chunks, advanced, tx, tu, x,
+                                                                       u);
     IPOC_API_LAUNCH_CHECK(st_);
     return IPOC_OK;
 }

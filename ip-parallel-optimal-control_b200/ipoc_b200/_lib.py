@@ -30,6 +30,7 @@ _SIGS = {
     "ipoc_attempt_begin_f64": (_I, [_I] + [_P] * 5 + [_P]),
     "ipoc_trial_point_f64": (_I, [_I] * 4 + [_P] * 6 + [_P]),
     "ipoc_attempt_commit_f64": (_I, [_I] * 4 + [_P] * 8 + [_I, _P]),
+    "ipoc_newton_advance_f64": (_I, [_I] * 4 + [_P] * 10 + [ctypes.c_double, _I, _P]),
     "ipoc_lqr_params_f64": (_I, [_I] * 4 + [_P] * 13 + [_P]),
     "ipoc_newton_bwd_reduce_f64": (_I, [_I] * 3 + [_P] * 8 + [_P, _SZ, _P]),
     "ipoc_newton_bwd_apply_f64": (_I, [_I] * 5 + [_P] * 14 + [_P, _SZ, _P]),

@@ -111,3 +111,131 @@ def get(ocp: OCP, N, nx, nu, device, x, u, bp):
             _cache.pop(next(iter(_cache)))
         _cache[key] = g
     return g
+
+
+class DeviceLoopNewton:
+    """The WHOLE `newton_oc` loop (ref noc/par_interior_point_newton.py:137-202) with its control flow on the
+    device: one CUDA graph = one accept/reject attempt preceded by the end-of-iteration
+    bookkeeping of the previous one,
+
+        advance  : if the attempt loop just ended: x <- tx, u <- tu, iteration += 1, exit test on the pre-step
+                   max|ru|                                                          (ipoc_newton_advance_f64)
+        iterate  : cost, derivatives, K1 costates, LQ parameters, K4 at (x, u)      (same statements as graph A;
+                   recomputed — idempotently — when the previous attempt was rejected)
+        attempt  : reg = rp*||cu||, K2+K3, trial point, its cost / feasibility, A8 accept + regularisation
+                   update, keep / count / inner-exit                                (the glue kernels of batched.py)
+
+    and every piece is frozen once `outer_done` is set — exactly the `select` semantics of a `lax.while_loop`
+    — so the host may run ahead: it keeps `depth` replays queued and looks at the exit flag of an OLDER
+    replay (one byte copied to pinned memory behind each replay), i.e. no host round trip sits on the critical
+    path.  Iterates and iteration counts are those of the eager loop (tests)."""
+
+    def __init__(self, ocp: OCP, N: int, nx: int, nu: int, device):
+        self.ocp, self.N, self.nx, self.nu, self.dev = ocp, N, nx, nu, torch.device(device)
+        o = dict(dtype=torch.float64, device=self.dev)
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        self.x, self.tx, self.cx = (torch.zeros(1, N + 1, nx, **o) for _ in range(3))
+        self.u, self.tu, self.cu = (torch.zeros(1, N, nu, **o) for _ in range(3))
+        self.bp = torch.zeros((), **o)
+        self.rp, self.r_inc = torch.ones(1, **o), torch.full((1,), 2.0, **o)
+        self.reg, self.gain, self.hu = torch.zeros(1, **o), torch.zeros(1, **o), torch.ones(1, **o)
+        self.act, self.succ, self.adv = torch.zeros(1, **i32), torch.zeros(1, **i32), torch.zeros(1, **i32)
+        self.inner = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.iteration = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.inner_done = torch.zeros(1, dtype=torch.bool, device=self.dev)
+        self.outer_done = torch.zeros(1, dtype=torch.bool, device=self.dev)
+        self.depth = 3 if N <= 20000 else 1      # replays kept in flight (a replay is > 1 ms for long horizons)
+        self.ring = 8
+        self.flags = torch.zeros(self.ring, dtype=torch.bool).pin_memory()
+        self.events = [torch.cuda.Event() for _ in range(self.ring)]
+        self.graph = None
+
+    def _step(self):
+        noc.newton_advance(self.hu, self.inner_done, self.outer_done, self.inner, self.iteration, self.adv,
+                           self.tx, self.tu, self.x, self.u)                               # :184-202
+        cost, fx, fu, cu, ru, Q, R, M = noc.eval_iteration(self.ocp, self.x[0], self.u[0], self.bp)   # :142-149
+        hu, cu_norm, _ = noc.reductions(ru=ru, cu=cu)                                      # :158, :116
+        self.hu.copy_(hu)
+        noc.attempt_begin(self.outer_done, self.rp, cu_norm, self.act, self.reg)           # :117
+        dx, du, _, _, pred, bwd_feas = noc.newton_step(fx, fu, ru, Q, R, M, self.reg)      # :153
+        noc.trial_point(self.x, dx.unsqueeze(0), self.u, du.unsqueeze(0), self.cx, self.cu)   # :156-157
+        new_cost, traj_feas = noc.eval_trial(self.ocp, self.cx[0], self.cu[0], self.bp)    # :159-163
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().ipoc_accept_update_f64(1, L.ptr(cost), L.ptr(new_cost.contiguous()), L.ptr(traj_feas),
+                                                   L.ptr(pred), L.ptr(bwd_feas), L.ptr(self.act), L.ptr(self.rp),
+                                                   L.ptr(self.r_inc), L.ptr(self.succ), L.ptr(self.gain),
+                                                   L.stream_ptr()))                        # :159-173
+        noc.attempt_commit(self.act, self.succ, self.cx, self.cu, self.tx, self.tu, self.inner,
+                           self.inner_done)                                                # :174-182
+
+    def _reset(self, x, u, bp):
+        self.x[0].copy_(x)
+        self.u[0].copy_(u)
+        self.tx.copy_(self.x)
+        self.tu.copy_(self.u)
+        self.bp.fill_(float(bp))
+        self.rp.fill_(1.0)                                                                 # :134
+        self.r_inc.fill_(2.0)                                                              # :135
+        self.hu.fill_(1.0)
+        self.inner.zero_()
+        self.iteration.zero_()
+        self.inner_done.zero_()
+        self.outer_done.zero_()
+
+    def capture(self, x, u, bp):
+        self._reset(x, u, bp)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._step()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step()
+        self.graph = g
+
+    def run(self, x, u, bp):
+        """-> (x, u, iterations) of `newton_oc` started at (x, u)."""
+        self._reset(x, u, bp)
+        r = 0
+        while True:
+            self.graph.replay()
+            k = r % self.ring
+            self.flags[k:k + 1].copy_(self.outer_done, non_blocking=True)
+            self.events[k].record()
+            r += 1
+            if r >= self.depth:
+                j = (r - self.depth) % self.ring
+                self.events[j].synchronize()
+                if bool(self.flags[j]):
+                    break
+        return self.x[0].clone(), self.u[0].clone(), int(self.iteration)
+
+
+_loop_cache = {}
+
+
+def get_device_loop(ocp: OCP, N, nx, nu, device, x, u, bp):
+    """Captured device-resident loop for this problem / horizon, or False if it cannot be captured."""
+    from . import plants
+    key = (id(ocp.dynamics), id(ocp.stage_cost), id(ocp.final_cost), id(ocp.constraints), id(ocp.total_cost),
+           N, nx, nu, str(device), plants.ENABLED)
+    g = _loop_cache.get(key)
+    if g is None:
+        g = DeviceLoopNewton(ocp, N, nx, nu, device)
+        try:
+            g.capture(x, u, bp)
+        except Exception as e:
+            import warnings
+            warnings.warn(f"ipoc_b200: CUDA-graph capture of the Newton loop failed ({type(e).__name__}: "
+                          f"{str(e)[:120]}); using the host-steered loop for this problem")
+            torch.cuda.synchronize(g.dev)
+            g = False
+        else:
+            g._keepalive = ocp
+        while len(_loop_cache) >= _CACHE_MAX:
+            _loop_cache.pop(next(iter(_loop_cache)))
+        _loop_cache[key] = g
+    return g

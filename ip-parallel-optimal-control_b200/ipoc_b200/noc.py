@@ -173,6 +173,19 @@ def attempt_commit(active, success, tx, tu, keep_x, keep_u, inner, done, max_att
                                                 int(max_attempts), L.stream_ptr()))
 
 
+def newton_advance(hu, inner_done, outer_done, inner, iteration, advanced, tx, tu, x, u, hu_tol=1e-4,
+                   max_iterations=1000):
+    """End-of-iteration bookkeeping of `newton_oc` on the device (ref :184-202): members whose attempt loop has
+    ended take the step (x <- tx, u <- tu), count the iteration and test the exit condition."""
+    Bn = hu.numel()
+    N, nx, nu = tu.shape[-2], tx.shape[-1], tu.shape[-1]
+    with torch.cuda.device(tx.device):
+        L.check(L.lib().ipoc_newton_advance_f64(N, nx, nu, Bn, L.ptr(hu), L.ptr(inner_done), L.ptr(outer_done),
+                                                L.ptr(inner), L.ptr(iteration), L.ptr(advanced), L.ptr(tx), L.ptr(tu),
+                                                L.ptr(x), L.ptr(u), float(hu_tol), int(max_iterations),
+                                                L.stream_ptr()))
+
+
 # ------------------------------------------------------------------ K2 + K3: the Newton step
 def newton_step(fx, fu, ru, Q, R, M, reg):
     """Fused device Newton step on LQ data; `reg` is a device tensor (one value per problem).
@@ -272,15 +285,19 @@ def initial_rollout(ocp: OCP, u, initial_state, parallel_rollout_from=2000):
 def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, barrier_param: float, trace=None,
               stage: int = 0, use_graphs: bool = True, parallel_rollout_from: int = 2000):
     """ref noc/par_interior_point_newton.py:127-225 -> (opt_x, opt_u, iterations).
-    The scalar accept/reject state (rp, r_inc, success) lives on the device; the host reads one
-    small record per attempt to steer the Python loop.  With use_graphs (default) the two loop bodies
-    are CUDA graphs captured once per problem (ipoc_b200/graphed.py); the eager path below is the same
-    sequence of statements."""
+    use_graphs=True (default): the whole loop runs from one CUDA graph with its control flow on the device
+    (graphed.DeviceLoopNewton; the host only watches the exit flag).  With a `trace`, or use_graphs="host",
+    the two loop bodies are separate CUDA graphs and the host reads one small record per attempt to steer
+    the loop (graphed.GraphedNewton).  use_graphs=False: the eager path below, the same sequence of statements."""
     dev = controls.device
     u = L.dev_f64(controls)
     x = initial_rollout(ocp, u, initial_state, parallel_rollout_from)   # :133
     if use_graphs:
         from . import graphed
+        if trace is None and use_graphs != "host":     # whole loop on the device (no per-attempt host read)
+            loop = graphed.get_device_loop(ocp, u.shape[0], x.shape[1], u.shape[1], dev, x, u, barrier_param)
+            if loop:
+                return loop.run(x, u, barrier_param)
         g = graphed.get(ocp, u.shape[0], x.shape[1], u.shape[1], dev, x, u, barrier_param)
         if g:
             return _newton_oc_graphed(g, x, u, barrier_param, trace, stage)

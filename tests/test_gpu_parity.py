@@ -323,6 +323,9 @@ def test_full_solve_matches_reference(golden, name):
     u, its = noc.par_interior_point_optimal_control(ocp, T(g["u0"]), T(g["x0"]))
     assert its == int(g["refp_iterations"])
     assert relerr(N_(u), g["refp_opt_u"]) < 1e-9
+    # the default above is the device-resident loop; the host-steered graphs must give the same iterate
+    u3, its3 = noc.par_interior_point_optimal_control(ocp, T(g["u0"]), T(g["x0"]), use_graphs="host")
+    assert its3 == its and relerr(N_(u3), N_(u)) < 1e-12
     if N <= 100:   # the eager (graph-free) driver is the same sequence of statements
         u2, its2 = noc.par_interior_point_optimal_control(ocp, T(g["u0"]), T(g["x0"]), use_graphs=False)
         assert its2 == its and relerr(N_(u2), N_(u)) < 1e-12
