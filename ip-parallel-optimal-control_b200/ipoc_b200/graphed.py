@@ -154,8 +154,7 @@ class DeviceLoopNewton:
         noc.newton_advance(self.hu, self.inner_done, self.outer_done, self.inner, self.iteration, self.adv,
                            self.tx, self.tu, self.x, self.u)                               # :184-202
         cost, fx, fu, cu, ru, Q, R, M = noc.eval_iteration(self.ocp, self.x[0], self.u[0], self.bp)   # :142-149
-        hu, cu_norm, _ = noc.reductions(ru=ru, cu=cu)                                      # :158, :116
-        self.hu.copy_(hu)
+        _, cu_norm, _ = noc.reductions(ru=ru, cu=cu, hu_out=self.hu)                       # :158, :116
         noc.attempt_begin(self.outer_done, self.rp, cu_norm, self.act, self.reg)           # :117
         dx, du, _, _, pred, bwd_feas = noc.newton_step(fx, fu, ru, Q, R, M, self.reg)      # :153
         noc.trial_point(self.x, dx.unsqueeze(0), self.u, du.unsqueeze(0), self.cx, self.cu)   # :156-157

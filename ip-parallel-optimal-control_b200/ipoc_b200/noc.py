@@ -112,7 +112,19 @@ def noc_to_lqt(ru, Q, R, M, A, B) -> LQT:
 
 
 # ------------------------------------------------------------------ K4 / A8
-def reductions(ru=None, cu=None, cons=None, rp=None, reg_out=None):
+_ones_cache = {}
+
+
+def _ones_i32(n, dev):
+    """Read-only all-ones int32 vector (the `feasible` result when no constraints were passed), cached."""
+    key = (n, str(dev))
+    t = _ones_cache.get(key)
+    if t is None:
+        t = _ones_cache[key] = torch.ones(n, dtype=torch.int32, device=dev)
+    return t
+
+
+def reductions(ru=None, cu=None, cons=None, rp=None, reg_out=None, hu_out=None):
     """(max|ru|, ||cu||_F, all(cons<=0)) per problem — ref :158, :116, :45-47.  Inputs (N,·) or (B,N,·).
     With `rp` and `reg_out` (device, one per problem) also writes reg_out = rp * ||cu||_F (:117)."""
     ref = next(t for t in (ru, cu, cons) if t is not None)
@@ -124,9 +136,15 @@ def reductions(ru=None, cu=None, cons=None, rp=None, reg_out=None):
     Bn, N = ref.shape[0], ref.shape[1]
     nu = (ru if ru is not None else cu).shape[2] if (ru is not None or cu is not None) else 1
     nc = cons.shape[2] if cons is not None else 1
-    hu = torch.zeros(Bn, dtype=torch.float64, device=dev)
-    cn = torch.zeros(Bn, dtype=torch.float64, device=dev)
-    fe = torch.ones(Bn, dtype=torch.int32, device=dev)
+    # outputs the kernel computes are left uninitialised (every fill is a launch on the critical path of a solve);
+    # the others get their neutral values
+    o = dict(dtype=torch.float64, device=dev)
+    if hu_out is not None:                      # caller-owned result buffer (device-resident loops)
+        hu = hu_out
+    else:
+        hu = torch.empty(Bn, **o) if ru is not None else torch.zeros(Bn, **o)
+    cn = torch.empty(Bn, **o) if cu is not None else torch.zeros(Bn, **o)
+    fe = torch.empty(Bn, dtype=torch.int32, device=dev) if cons is not None else _ones_i32(Bn, dev)
     ws, nbytes = L.workspace(L.WS_REDUCTIONS, N, max(nu, nc), nu, Bn, dev)
     with torch.cuda.device(dev):
         L.check(L.lib().ipoc_reductions_f64(N, nu, nc, Bn, L.ptr(ru), L.ptr(cu), L.ptr(cons), L.ptr(hu), L.ptr(cn),
