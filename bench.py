@@ -456,6 +456,37 @@ def run_ours(args):
             except Exception as e:
                 batched_solves.append({"problem": prob_, "error": repr(e)[:200]})
 
+    # ---- BASELINE config 5 on N > 1 GPUs: the batch of independent OCPs is split over the ranks
+    #      (sharded.shard_batch, no data-path collective); solves/s = all problems / max-over-ranks time.
+    if world > 1 and not args.no_solve:
+        from ipoc_b200 import problems as _pbw, batched as _btw, sharded as _shw
+        batched_solves = []
+        for prob_, per_rank in (("pendulum", 2048), ("cartpole", 512)):
+            try:
+                Nb, Bt = 1000, per_rank * world
+                ocp_ = _pbw.make_pendulum(1.0 / Nb) if prob_ == "pendulum" else _pbw.make_cartpole(1.0 / Nb)
+                x0b = (_pbw.pendulum_x0 if prob_ == "pendulum" else _pbw.cartpole_x0)(device=dev)
+                rng_ = np.random.default_rng(1)                      # same global batch on every rank
+                x0_all = 0.1 * rng_.standard_normal((Bt, x0b.numel()))
+                u0_all = 0.1 * rng_.standard_normal((Bt, Nb, 1))
+                lo, hi = _shw.shard_batch(Bt, rank, world)
+                x0s_ = x0b[None] + torch.as_tensor(x0_all[lo:hi], device=dev)
+                u0s_ = torch.as_tensor(u0_all[lo:hi], device=dev)
+                _btw.par_interior_point_optimal_control_batched(ocp_, u0s_[:64], x0s_[:64])   # warm-up (lazy inits)
+                barrier()
+                t0 = time.perf_counter()
+                ub_, itb_ = _btw.par_interior_point_optimal_control_batched(ocp_, u0s_, x0s_)
+                torch.cuda.synchronize(dev)
+                dtb = allmax(time.perf_counter() - t0)
+                its_sum = torch.tensor([float(itb_.double().sum())], dtype=torch.float64, device=dev)
+                dist.all_reduce(its_sum)
+                if rank == 0:
+                    batched_solves.append({"problem": prob_, "N": Nb, "batch": Bt, "batch_per_gpu": per_rank,
+                                           "n_gpus": world, "solves_per_s": Bt / dtb, "seconds": dtb,
+                                           "iterations_mean": float(its_sum[0]) / Bt, "scaling": "weak"})
+            except Exception as e:
+                batched_solves.append({"problem": prob_, "error": repr(e)[:200]})
+
     # ---- BASELINE config 3 as written (ref examples/linear_mpc_parallel.py:67-81): 5000 receding-horizon steps,
     #      each = par_bwd_pass + par_fwd_pass on the T = 5 double-integrator LQT; the whole loop is timed, like the
     #      reference does (after one untimed run).  CPU side: the oracle's par passes on a 300-step sample.
