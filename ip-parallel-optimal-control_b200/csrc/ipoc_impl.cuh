@@ -113,12 +113,15 @@ IPOC_DEV void st_vec(double* __restrict__ p, const double* src) {
 template <class Op>
 constexpr size_t scan_scratch_bytes() { return 2 * sizeof(typename Op::Elem) * 32; }
 
+// `used` = number of leading lanes that hold real aggregates (the rest are identities, forward scans
+// only): rounds with delta >= used would only copy, so they are skipped — a top scan over 8 warp totals
+// (N = 1000) takes 3 combine rounds instead of 5.  Must be the same in every warp of a CTA (buffer parity).
 template <class Op>
-IPOC_DEV double* warp_scan_mem(double* ws, int lane, bool reverse) {
+IPOC_DEV double* warp_scan_mem(double* ws, int lane, bool reverse, int used = 32) {
     constexpr int ESZ = sizeof(typename Op::Elem) / sizeof(double);
     int cur = 0;
 #pragma unroll 1
-    for (int delta = 1; delta < 32; delta <<= 1) {
+    for (int delta = 1; delta < used; delta <<= 1) {
         const double* src = ws + cur * (ESZ * 32);
         double* dst = ws + (cur ^ 1) * (ESZ * 32) + lane;
         const int partner = reverse ? lane + delta : lane - delta;
@@ -255,14 +258,16 @@ k_top(const double* __restrict__ agg, size_t astride, int n, int batch,
         for (int c = 0; c < ESZ; ++c) ws[c * 32 + lane] = id.r[c];
     }
     __syncwarp();
-    const double* inc = warp_scan_mem<Op>(ws, lane, false);   // this warp's inclusive aggregates
+    // this warp's inclusive aggregates; with fewer than 32 aggregates in the whole CTA the late rounds are skipped
+    const int used = (n + q - 1) / q;
+    const double* inc = warp_scan_mem<Op>(ws, lane, false, used < 32 ? used : 32);
     const int inc_off = (int)(inc - ws);                      // same buffer parity in every warp
     __syncthreads();
     if (w == 0 && lane == 0) {
         if (total != nullptr) {
             // composition of all warp totals (time-sharded reduce phase)
 #pragma unroll
-            for (int c = 0; c < ESZ; ++c) s_tot[c] = s_scan[inc_off + c * 32 + 31];
+            for (int c = 0; c < ESZ; ++c) s_tot[c] = s_scan[inc_off + c * 32 + (used < 32 ? used - 1 : 31)];
             for (int ww = 1; ww < nw; ++ww)
                 Op::compose_mm(s_tot, 1, s_tot, 1, s_scan + (size_t)ww * WSZ + inc_off + 31, 32);
 #pragma unroll
