@@ -54,3 +54,25 @@ def test_segment_bounds_cover_horizon():
         b = sharded.segment_bounds(N, P)
         assert b[0][0] == 0 and b[-1][1] == N and all(b[i][1] == b[i + 1][0] for i in range(P - 1))
         assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` needs no GPU: it times the oracle port on the host and prints ONE JSON line
+    with the keys the driver reads (metric/unit/config equal to the CUDA arm's, impl, cpu_baseline, e2e)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "ip_newton_step_throughput_cartpole_N1e4"
+    assert d["unit"] == "newton_steps/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["steps"] == 1 and d["n_gpus"] == 1 and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert abs(d["e2e"]["value"] - d["value"]) < 1e-9 * d["value"]
