@@ -287,7 +287,7 @@ def eval_trial(ocp: OCP, tx, tu, bp):
     return ocp.total_cost(tx, tu, bp).reshape(1), traj_feas              # :161 (masked to inf by A8)
 
 
-def initial_rollout(ocp: OCP, u, initial_state, parallel_rollout_from=2000):
+def initial_rollout(ocp: OCP, u, initial_state, parallel_rollout_from=256):
     """states of the nominal rollout (ref :133): device kernel for the built-in plants, the parallel
     Newton-on-the-rollout scan for long horizons, else the serial host loop."""
     plant = plants.plant_of(ocp)
@@ -301,7 +301,7 @@ def initial_rollout(ocp: OCP, u, initial_state, parallel_rollout_from=2000):
 
 # ------------------------------------------------------------------ driver loops
 def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, barrier_param: float, trace=None,
-              stage: int = 0, use_graphs: bool = True, parallel_rollout_from: int = 2000):
+              stage: int = 0, use_graphs: bool = True, parallel_rollout_from: int = 256):
     """ref noc/par_interior_point_newton.py:127-225 -> (opt_x, opt_u, iterations).
     use_graphs=True (default): the whole loop runs from one CUDA graph with its control flow on the device
     (graphed.DeviceLoopNewton; the host only watches the exit flag).  With a `trace`, or use_graphs="host",
