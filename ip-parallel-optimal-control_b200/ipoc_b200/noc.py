@@ -303,16 +303,21 @@ def initial_rollout(ocp: OCP, u, initial_state, parallel_rollout_from=256):
 def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, barrier_param: float, trace=None,
               stage: int = 0, use_graphs: bool = True, parallel_rollout_from: int = 256):
     """ref noc/par_interior_point_newton.py:127-225 -> (opt_x, opt_u, iterations).
-    use_graphs=True (default): the whole loop runs from one CUDA graph with its control flow on the device
-    (graphed.DeviceLoopNewton; the host only watches the exit flag).  With a `trace`, or use_graphs="host",
-    the two loop bodies are separate CUDA graphs and the host reads one small record per attempt to steer
-    the loop (graphed.GraphedNewton).  use_graphs=False: the eager path below, the same sequence of statements."""
+    use_graphs=True (default): for the built-in plants the whole loop runs from one CUDA graph with its
+    control flow on the device (graphed.DeviceLoopNewton; the host only watches the exit flag; "device"
+    forces this for any OCP).  For user OCPs, with a `trace`, or with use_graphs="host", the two loop bodies
+    are separate CUDA graphs and the host reads one small record per attempt to steer the loop
+    (graphed.GraphedNewton).  use_graphs=False: the eager path below, the same sequence of statements."""
     dev = controls.device
     u = L.dev_f64(controls)
     x = initial_rollout(ocp, u, initial_state, parallel_rollout_from)   # :133
     if use_graphs:
         from . import graphed
-        if trace is None and use_graphs != "host":     # whole loop on the device (no per-attempt host read)
+        # Whole loop on the device (no per-attempt host read) where re-evaluating the iterate after a rejected
+        # attempt is cheap — the built-in plants (7 kernels).  With host-framework autodiff that evaluation is
+        # hundreds of kernels, so user OCPs keep the host-steered graphs, which evaluate once per iteration
+        # (measured: cartpole N=1e4 through autodiff 0.41 s host-steered vs 0.52 s device-resident).
+        if trace is None and use_graphs != "host" and (plants.plant_of(ocp) is not None or use_graphs == "device"):
             loop = graphed.get_device_loop(ocp, u.shape[0], x.shape[1], u.shape[1], dev, x, u, barrier_param)
             if loop:
                 return loop.run(x, u, barrier_param)

@@ -541,6 +541,8 @@ def test_user_defined_ocp_matches_oracle_driver():
     uo, ito = noc_np.par_interior_point_optimal_control(Evaluator(ocp), u0, x0)
     ug, itg = noc.par_interior_point_optimal_control(ocp, T(u0), T(x0))
     assert itg == ito and relerr(N_(ug), uo) < 1e-8
+    ud, itd = noc.par_interior_point_optimal_control(ocp, T(u0), T(x0), use_graphs="device")   # device-resident loop
+    assert itd == ito and relerr(N_(ud), N_(ug)) < 1e-12
 
 
 def test_graph_capture_failure_falls_back_to_eager():
