@@ -119,14 +119,68 @@ def newton_step_fixture(name, ocp, x0, u, bp, reg_param, warm_iters=0):
     print(f"{name}: N={u.shape[0]} |par-seq| step diff {err:.3e} pred {float(pred):.6e} dV {float(dV):.6e}")
 
 
-def solve_fixture(name, ocp, x0, u0):
+def big_step_fixture(name, ocp, x0, u, bp, reg_param, warm_iters=0):
+    """Compact fixture of ONE Newton step at a BASELINE-size horizon (config 2: cartpole N = 1e4).  The 130
+    doubles per step of `Derivatives` are NOT stored (10 MB): a test re-derives them from (states, controls)
+    and is then held against the reference's costates, LQ parameters (ru, Q diagonal-free summary: full Q, R, M
+    are 21 doubles per step and are kept), the in-tree sequential step and the reference par_Newton outputs."""
+    x0 = jnp.array(x0)
+    u = jnp.array(u)
+    states = rollout(ocp.dynamics, u, x0)
+    for _ in range(warm_iters):   # accepted reference Newton iterations -> an interior iterate, indefinite Q
+        d = refpar.compute_derivatives(ocp, states, u, bp)
+        lam = refcos.par_costates(ocp, states[-1], d)
+        ru, Q, R, M = refpar.compute_lqr_params(lam, d)
+        rp = 1.0
+        while True:
+            dx, du, pred, feas, _ = refpar.par_Newton(states, d, rp, ru, Q, R, M)
+            tx, tu = states + dx, u + du
+            ok = bool(refpar.check_traj_feasibility(ocp, tx, tu))
+            if ok and bool(feas) and float(ocp.total_cost(tx, tu, bp)) < float(ocp.total_cost(states, u, bp)):
+                states, u = tx, tu
+                break
+            rp *= 4.0
+    d = refpar.compute_derivatives(ocp, states, u, bp)
+    lam_par = refcos.par_costates(ocp, states[-1], d)
+    ru, Q, R, M = refpar.compute_lqr_params(lam_par, d)
+    reg = reg_param * jnp.linalg.norm(d.cu)
+    Q0 = Q[0]
+    fc = lambda xx: 0.5 * xx @ Q0 @ xx
+    t = time.time()
+    K, k, dV, convex = refseq.bwd_pass(fc, states[-1], LinearizedOCP(ru, Q, R, M), d, reg)
+    du_seq, dx_seq = refseq.fwd_pass(K, k, d)
+    t1 = time.time() - t
+    dx, du, pred, feas, _ = refpar.par_Newton(states, d, reg_param, ru, Q, R, M)
+    tx, tu = states + dx, u + du
+    eig = np.linalg.eigvalsh(0.5 * (A(Q) + A(Q).transpose(0, 2, 1)))
+    out = dict(
+        bp=bp, reg_param=reg_param, states=A(states), controls=A(u), x0=A(x0),
+        ref_costates_par=A(lam_par), ref_ru=A(ru), ref_Q=A(Q), ref_R=A(R), ref_M=A(M), ref_reg=A(reg),
+        ref_cu_norm=A(jnp.linalg.norm(d.cu)),
+        ref_seq_du=A(du_seq), ref_seq_dx=A(dx_seq), ref_seq_dV=A(dV), ref_seq_convex=A(convex),
+        refp_dx=A(dx), refp_du=A(du), refp_pred=A(pred), refp_feasible=A(feas),
+        ref_cost=A(ocp.total_cost(states, u, bp)),
+        ref_new_feasible=A(refpar.check_traj_feasibility(ocp, tx, tu)),
+        ref_new_cost=A(ocp.total_cost(tx, tu, bp)),
+        ref_Q_min_eig=float(eig.min()), ref_Q_indefinite_steps=int((eig.min(axis=1) < 0).sum()),
+    )
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    err = max(float(abs(dx - dx_seq).max()), float(abs(du - du_seq).max()))
+    print(f"{name}: N={u.shape[0]} |par-seq| step diff {err:.3e} pred {float(pred):.6e} dV {float(dV):.6e} "
+          f"min eig(Q) {eig.min():.3e} ({out['ref_Q_indefinite_steps']} indefinite steps) seq step {t1:.1f}s", flush=True)
+
+
+def solve_fixture(name, ocp, x0, u0, with_seq=True):
     x0 = jnp.array(x0)
     u0 = jnp.array(u0)
     t = time.time()
     u_par, it_par = refpar.par_interior_point_optimal_control(ocp, u0, x0)
     t1 = time.time() - t
     t = time.time()
-    u_seq, it_seq = refseq.seq_interior_point_optimal_control(ocp, u0, x0)
+    if with_seq:
+        u_seq, it_seq = refseq.seq_interior_point_optimal_control(ocp, u0, x0)
+    else:   # the sequential twin's Python-level scan is too slow through the shim at this size
+        u_seq, it_seq = jnp.array(np.full(A(u_par).shape, np.nan)), -1
     t2 = time.time() - t
     xs = rollout(ocp.dynamics, u_par, x0)
     np.savez_compressed(
@@ -136,7 +190,7 @@ def solve_fixture(name, ocp, x0, u0):
         refp_final_cost0=A(ocp.total_cost(xs, u_par, 0.0)) if name.startswith("solve_linear") else np.nan,
     )
     print(f"{name}: par its {int(it_par)} ({t1:.1f}s)  seq its {int(it_seq)} ({t2:.1f}s)  "
-          f"|u_par-u_seq| {float(abs(u_par - u_seq).max()):.3e}")
+          f"|u_par-u_seq| {float(abs(u_par - u_seq).max()):.3e}", flush=True)
 
 
 def main():
@@ -176,6 +230,20 @@ def main():
     if "config1" in which:
         # BASELINE.json config 1: pendulum N=500, Ts=1/500
         solve_fixture("solve_pendulum_N500", pendulum_ocp(500), pen_x0, 0.1 * rng(1).standard_normal((500, 1)))
+
+
+    if "config2" in which:
+        # BASELINE.json config 2 (cartpole N = 1e4, Ts = 1e-4): the first Newton step (bp 0.1, rp 1) and a warm
+        # interior iterate; full solves at N = 1000 (config 5's horizon) and N = 1e4
+        u1e4 = 0.1 * rng(1).standard_normal((10000, 1))
+        big_step_fixture("step_cartpole_N10000", cartpole_ocp(10000), car_x0, u1e4, 0.1, 1.0)
+        big_step_fixture("step_cartpole_N10000_warm", cartpole_ocp(10000), car_x0, u1e4, 0.1, 0.6, warm_iters=2)
+    if "config2solve1000" in which or "config2" in which:
+        solve_fixture("solve_cartpole_N1000", cartpole_ocp(1000), car_x0, 0.1 * rng(1).standard_normal((1000, 1)),
+                      with_seq=False)
+    if "config2solve" in which:
+        solve_fixture("solve_cartpole_N10000", cartpole_ocp(10000), car_x0, 0.1 * rng(1).standard_normal((10000, 1)),
+                      with_seq=False)
 
 
 if __name__ == "__main__":

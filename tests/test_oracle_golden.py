@@ -115,3 +115,51 @@ def test_full_solve_matches_reference_driver(golden, name, tol_u):
     u, its = noc_np.par_interior_point_optimal_control(Evaluator(ocp), g["u0"], g["x0"])
     assert its == int(g["refp_iterations"])
     assert relerr(u, g["refp_opt_u"]) < tol_u
+
+
+# ---------------------------------------------------------------------- BASELINE-size fixtures (round 2)
+@pytest.mark.parametrize("name", ["step_cartpole_N10000", "step_cartpole_N10000_warm"])
+def test_config2_oracle_vs_reference(golden, name):
+    """Cartpole N = 1e4 (BASELINE config 2): oracle derivatives -> costates -> LQ parameters -> par_Newton against
+    what the reference's own source produced; the C serial oracles (long double / double) against the
+    reference's in-tree sequential step."""
+    import ipoc_b200.problems as P
+    from oracle.autodiff import Evaluator
+    from oracle import serial_ld
+    g = golden(name)
+    N = g["controls"].shape[0]
+    ev = Evaluator(P.make_cartpole(1.0 / N))
+    d = ev.derivatives(g["states"], g["controls"], float(g["bp"]))
+    lam = noc_np.par_costates(ev.final_cost_grad(g["states"][-1]), d)
+    assert relerr(lam, g["ref_costates_par"]) < 1e-12
+    ru, Q, R, M = noc_np.compute_lqr_params(lam, d)
+    for mine, key in ((ru, "ref_ru"), (Q, "ref_Q"), (R, "ref_R"), (M, "ref_M")):
+        assert relerr(mine, g[key]) < 1e-12
+    dx, du, pred, feas, _ = noc_np.par_Newton(4, d, float(g["reg_param"]), g["ref_ru"], g["ref_Q"], g["ref_R"],
+                                              g["ref_M"])
+    assert relerr(dx, g["refp_dx"]) < 1e-11 and relerr(du, g["refp_du"]) < 1e-11
+    assert relerr(dx, g["ref_seq_dx"]) < 1e-9 and relerr(du, g["ref_seq_du"]) < 1e-9
+    assert abs(pred - float(g["ref_seq_dV"])) <= 1e-10 * abs(float(g["ref_seq_dV"]))
+    assert bool(feas) == bool(g["ref_seq_convex"])
+    for prec, tol in (("ld", 1e-10), ("f64", 1e-10)):
+        dxs, dus, _, _, dV, cvx = serial_ld.seq_newton(d.fx, d.fu, g["ref_ru"], g["ref_Q"], g["ref_R"], g["ref_M"],
+                                                       float(g["ref_reg"]), precision=prec)
+        assert relerr(dxs, g["ref_seq_dx"]) < tol and relerr(dus, g["ref_seq_du"]) < tol
+        assert abs(dV - float(g["ref_seq_dV"])) <= tol * abs(dV) and cvx == bool(g["ref_seq_convex"])
+
+
+@pytest.mark.parametrize("name", STEP_FIXTURES)
+def test_serial_c_oracles_match_reference_sequential_step(golden, name):
+    """oracle/serial_ld.c (both precisions) is pinned by `ref_seq_*`: the reference's in-tree sequential Newton
+    step and sequential costates executed from their source."""
+    from oracle import serial_ld
+    g = golden(name)
+    d = derivs_from_golden(g)
+    for prec in ("ld", "f64"):
+        dx, du, K, k, dV, cvx = serial_ld.seq_newton(d.fx, d.fu, g["ref_ru"], g["ref_Q"], g["ref_R"], g["ref_M"],
+                                                     float(g["ref_reg"]), precision=prec)
+        assert relerr(dx, g["ref_seq_dx"]) < 1e-13 and relerr(du, g["ref_seq_du"]) < 1e-13
+        assert relerr(K, g["ref_seq_K"]) < 1e-13 and relerr(k, g["ref_seq_k"]) < 1e-13
+        assert abs(dV - float(g["ref_seq_dV"])) <= 1e-13 * abs(dV) and cvx == bool(g["ref_seq_convex"])
+        lam = serial_ld.seq_costates(d.fx, d.cx, g["ref_lamT"], precision=prec)
+        assert relerr(lam, g["ref_costates_seq"]) < 1e-13
