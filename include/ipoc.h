@@ -15,11 +15,17 @@
  *     no host reads) and is therefore CUDA-graph capturable.  The caller owns all buffers
  *     including the workspace (`ipoc_workspace_bytes`).  The library keeps no mutable state
  *     apart from the optional tuning knobs below.
+ *   - WORKSPACE CONTROL BLOCK: the first IPOC_WS_CONTROL_BYTES of a scan workspace (every kind except
+ *     IPOC_WS_REDUCTIONS) hold the arrival counters of the in-kernel scan levels.  They must be ZERO when
+ *     the workspace is first used — call ipoc_workspace_init once after allocating (or cudaMemset) — and
+ *     every call leaves them zero again (each counter wraps to 0 on its last arrival), so replays of
+ *     captured graphs and calls with other problem sizes on the same workspace need nothing.  A
+ *     workspace must not be used by two calls at the same time.
  *   - Return value: 0 on success, a negative IPOC_E* code otherwise.  Numerical failure (NaN,
  *     non-positive-definite G) is DATA (`feasible = 0`), never an error — it is an ordinary
  *     branch of the algorithm (ref noc/par_interior_point_newton.py:166).
  *   - There is no CPU fallback: unsupported (nx, nu) -> IPOC_EUNSUPPORTED_DIM.
- *     Supported: nx in {1..8} as instantiated (see ipoc_supported), nu in {1, 2}.
+ *     Supported: nx in {1..8}, nu in {1..min(nx, 4)} (see ipoc_supported).
  */
 #ifndef IPOC_H
 #define IPOC_H
@@ -48,8 +54,14 @@ enum { /* `kind` of ipoc_workspace_bytes */
     IPOC_WS_LQT_BWD = 1,
     IPOC_WS_LQT_FWD = 2,
     IPOC_WS_AFFINE_SCAN = 3,
-    IPOC_WS_REDUCTIONS = 4
+    IPOC_WS_REDUCTIONS = 4,
+    IPOC_WS_COSTATES = 5,       /* ipoc_costates_f64 */
+    IPOC_WS_NEWTON_ATTEMPT = 6  /* ipoc_newton_attempt_f64: pass max(nu, nc) in place of nu when cons is given */
 };
+
+#define IPOC_WS_CONTROL_BYTES 65536
+/* Zero the control block of a freshly allocated workspace (stream-ordered; once per allocation). */
+int ipoc_workspace_init(void* ws, size_t ws_bytes, ipoc_stream_t stream);
 
 const char* ipoc_strerror(int code);
 int ipoc_version(void);
@@ -66,6 +78,13 @@ void ipoc_set_tuning(int leaf_chunk, int mid_fanin, int top_max);
  * 1 = follow those lines operation by operation (X^-1 M by pivoted LU, s, r, then fold back).
  * The two differ by rounding of order eps*cond(Q); both are tested against the oracle. */
 void ipoc_set_literal_lqt(int on);
+
+/* Scan organisation knob (tests / experiments): by default the levels above the warp scans are completed
+ * inside the leaf kernels by their last-arriving warps ("hierarchical" plans: no top / mid kernels, no
+ * spin-waiting).  enabled = 0 selects the separate level kernels; group_warps (<= 32, 0 = 32) and
+ * serial_top (<= 32, 0 = 8) shape the hierarchy.  ipoc_set_tuning with a non-zero mid_fanin or top_max
+ * also selects the separate level kernels. */
+void ipoc_set_hier(int enabled, int group_warps, int serial_top);
 
 /* ---- K2 + K3: one Newton step ----------------------------------------------------------
  * Replaces `par_Newton` (ref noc/par_interior_point_newton.py:107-124) from the regularisation
@@ -124,6 +143,40 @@ int ipoc_lqt_fwd_f64(int N, int nx, int nu, int batch,
 int ipoc_affine_scan_f64(int reverse, int transpose, int N, int nx, int batch,
                          const double* F, const double* c, const double* seed, double* out,
                          void* ws, size_t ws_bytes, ipoc_stream_t stream);
+
+/* ---- K1 + ||cu||: `par_costates` with the norm of ref :116 as a side job --------------------------------
+ * lam = costates (ref noc/costates.py:34-40: reverse scan of lam_k = cx_k + fx_k' lam_{k+1}, lam_N = lamT)
+ * and, if cu (N,nu) is given, cu_norm (batch) = ||cu||_F (ref noc/par_interior_point_newton.py:116) folded
+ * into the up-sweep: per-warp partial sums, fixed-order fold by the warp that completes the scan.
+ * Workspace: ipoc_workspace_bytes(IPOC_WS_COSTATES, N, nx, nu, batch). */
+int ipoc_costates_f64(int N, int nx, int nu, int batch,
+                      const double* fx, const double* cx, const double* lamT, const double* cu,
+                      double* lam, double* cu_norm,
+                      void* ws, size_t ws_bytes, ipoc_stream_t stream);
+
+/* ---- K2 + K3 + the glue of one accept/reject attempt, fused (ref :151-175) --------------------------------
+ * ipoc_newton_step_f64 with reg = rp * cu_norm formed in the kernel (:117) and, each optional (NULL = off),
+ *   hu            = max|ru| (:158), folded into the up-sweep;
+ *   tx, tu        = x + dx, u + du (:156-157), written by K3's leaf kernel next to dx, du;
+ *   traj_feasible = all(cons <= 0) of a GIVEN array cons (batch,N,nc) (:45-47 — when the constraints depend on
+ *                   the trial point the caller evaluates them afterwards and passes traj_feas_in instead);
+ *   accept        : rho = (new_cost - cost)/pred, success, rp_out / r_inc update (:159-173, the rule of
+ *                   ipoc_accept_update_f64) by the warp that completes K3.  rp_out may alias rp.
+ * Five launches in all for one problem; plans that cannot carry a side job (one sequence per lane, explicitly
+ * tuned level kernels) run the stand-alone kernels for it, with identical results.
+ * Workspace: ipoc_workspace_bytes(IPOC_WS_NEWTON_ATTEMPT, N, nx, max(nu, nc), batch). */
+int ipoc_newton_attempt_f64(int N, int nx, int nu, int nc, int batch,
+                            const double* fx, const double* fu, const double* ru,
+                            const double* Q, const double* R, const double* M,
+                            const double* rp, const double* cu_norm,
+                            double* dx, double* du, double* Kx, double* d, double* pred, int32_t* feasible,
+                            double* hu,
+                            const double* x, const double* u, double* tx, double* tu,
+                            const double* cons, int32_t* traj_feasible,
+                            const double* cost, const double* new_cost, const int32_t* traj_feas_in,
+                            const int32_t* active, double* rp_out, double* r_inc, int32_t* success,
+                            double* gain_ratio,
+                            void* ws, size_t ws_bytes, ipoc_stream_t stream);
 
 /* ---- K4: reductions of the accept/reject test ---------------------------------------------
  * (ref noc/par_interior_point_newton.py:45-47 `all(cons <= 0)`, :116 `norm(d.cu)`, :158
@@ -190,6 +243,22 @@ int ipoc_newton_advance_f64(int N, int nx, int nu, int batch, const double* hu, 
                             uint8_t* outer_done, int64_t* inner, int64_t* iteration, int32_t* advanced,
                             const double* tx, const double* tu, double* x, double* u, double hu_tol,
                             int max_iterations, ipoc_stream_t stream);
+
+/* ---- device-resident loops, one launch for everything after the trial cost (ref :159-202) ----------------
+ * For every member with active != 0: the accept rule of ipoc_accept_update_f64; inner += 1 (:174); if the attempt
+ * loop ends (success or inner > max_attempts, :180-181) the Newton iteration ends with it: advanced = 1 (the
+ * caller's next ipoc_masked_copy_f64 takes the step x <- tx, :184), iteration += 1 (:194), inner = 0, and
+ * outer_done = 1, active = 0 if hu < hu_tol or iteration > max_iterations (:199-202; hu = max|ru| of the iterate
+ * BEFORE the step).  Members with active == 0 are left untouched (advanced = 0): the `select` semantics of a
+ * vmapped lax.while_loop.  Replaces accept_update + attempt_commit + the flag half of newton_advance. */
+int ipoc_attempt_finish_f64(int batch, const double* cost, const double* new_cost, const int32_t* traj_feasible,
+                            const double* pred, const int32_t* bwd_feasible, const double* hu, int32_t* active,
+                            double* rp, double* r_inc, int32_t* success, double* gain_ratio, int64_t* inner,
+                            int64_t* iteration, uint8_t* outer_done, int32_t* advanced, double hu_tol,
+                            int max_attempts, int max_iterations, ipoc_stream_t stream);
+/* dst_x <- src_x ((N+1)*nx per member), dst_u <- src_u (N*nu) for the members with mask != 0. */
+int ipoc_masked_copy_f64(int N, int nx, int nu, int batch, const int32_t* mask, const double* src_x,
+                         const double* src_u, double* dst_x, double* dst_u, ipoc_stream_t stream);
 
 /* ---- time-sharded (multi-GPU) split-phase variants -----------------------------------------
  * A horizon of P*N steps is cut into P contiguous segments, one per rank (no reference
@@ -281,6 +350,14 @@ int ipoc_plant_cost_f64(int plant, int N, int batch, double Ts, double bound, co
                         ipoc_stream_t stream);
 int ipoc_plant_rollout_f64(int plant, int N, int batch, double Ts, const double* x0, const double* u,
                            double* x, ipoc_stream_t stream);
+/* ipoc_plant_cost_f64 of the trial point (tx, tu) followed, in the same launch, by ipoc_attempt_finish_f64 with
+ * the cost / feasibility just computed (members with active == 0 are skipped altogether). */
+int ipoc_plant_attempt_finish_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
+                                  const double* tx, const double* tu, double* new_cost, int32_t* traj_feasible,
+                                  const double* cost, const double* pred, const int32_t* bwd_feasible, const double* hu,
+                                  int32_t* active, double* rp, double* r_inc, int32_t* success, double* gain_ratio,
+                                  int64_t* inner, int64_t* iteration, uint8_t* outer_done, int32_t* advanced,
+                                  double hu_tol, int max_attempts, int max_iterations, ipoc_stream_t stream);
 
 /* Number of kernels the library has launched since load (for launch accounting in bench.py). */
 unsigned long long ipoc_launch_count(void);

@@ -6,6 +6,7 @@
 #include <string.h>
 #include "../../include/ipoc.h"
 #include "ipoc_dispatch.h"
+#include "ipoc_accept.cuh"
 
 namespace ipoc {
 
@@ -15,7 +16,10 @@ struct Tuning {
 unsigned long long g_launches = 0;
 Tuning g_tune = {0, 0, 0};
 int g_literal_lqt = 0;
-
+struct HierTuning {
+    int enabled, group_warps, serial_top;
+};
+HierTuning g_hier = {1, 0, 0};
 // ---- per-launch profiler: one CUDA event after every kernel launch, on the launching stream ----
 constexpr int kMaxProf = 256;
 struct Prof {
@@ -296,24 +300,13 @@ static __global__ void k_accept_update(int batch, const double* __restrict__ cos
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     if (active != nullptr && !active[b]) return;
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    const double nc = traj_feasible[b] ? new_cost[b] : inf;
-    const double rho = (nc - cost[b]) / pred[b];
-    const bool ok = (rho > 0.0) && (bwd_feasible[b] != 0);
-    double r = rp[b], ri = r_inc[b];
-    if (ok) {
-        const double tq = 2.0 * rho - 1.0;
-        r = r * fmax(1.0 / 3.0, 1.0 - tq * tq * tq);
-        ri = 2.0;
-    } else {
-        r = r * ri;
-        ri = 2.0 * ri;
-    }
-    r = fmin(fmax(r, 1e-16), 1e16);
-    rp[b] = r;
-    r_inc[b] = ri;
-    success[b] = ok ? 1 : 0;
-    if (gain_ratio != nullptr) gain_ratio[b] = rho;
+    accept_rule_core(AcceptIO{cost, pred, bwd_feasible, rp, r_inc, success, gain_ratio}, b, new_cost[b], traj_feasible[b]);
+}
+
+static __global__ void k_attempt_finish(int batch, FinishIO f, const double* __restrict__ new_cost,
+                                        const int32_t* __restrict__ traj_feasible) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) attempt_finish_rule(f, b, new_cost[b], traj_feasible[b]);
 }
 
 // ---- attempt-loop glue (see include/ipoc.h) ---------------------------------------------------
@@ -399,7 +392,6 @@ static inline long long copy_chunks(long long per, int batch) {
 // =================================================================== C ABI
 using namespace ipoc;
 
-#define IPOC_FOR_NX(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 
 extern "C" {
 
@@ -419,8 +411,8 @@ const char* ipoc_strerror(int code) {
 int ipoc_version(void) { return 100; }
 
 int ipoc_supported(int nx, int nu) {
-#define X(a) if (nx == a) return nx_supported<a>(nu);
-    IPOC_FOR_NX(X)
+#define X(a, b) if (nx == a && nu == b) return 1;
+    IPOC_FOR_PAIRS(X)
 #undef X
     return 0;
 }
@@ -435,6 +427,18 @@ unsigned long long ipoc_launch_count(void) { return g_launches; }
 
 void ipoc_set_literal_lqt(int on) { g_literal_lqt = on ? 1 : 0; }
 
+int ipoc_workspace_init(void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    if (ws == nullptr) return IPOC_EINVAL;
+    const size_t n = ws_bytes < (size_t)IPOC_WS_CONTROL_BYTES ? ws_bytes : (size_t)IPOC_WS_CONTROL_BYTES;
+    return cudaMemsetAsync(ws, 0, n, (cudaStream_t)stream) == cudaSuccess ? IPOC_OK : IPOC_ECUDA;
+}
+
+void ipoc_set_hier(int enabled, int group_warps, int serial_top) {
+    g_hier.enabled = enabled ? 1 : 0;
+    g_hier.group_warps = group_warps;
+    g_hier.serial_top = serial_top;
+}
+
 int ipoc_carry_doubles(int kind, int nx) {
     if (nx < 1 || nx > 8) return 0;
     const int sy = nx * (nx + 1) / 2;
@@ -445,6 +449,11 @@ size_t ipoc_workspace_bytes(int kind, int N, int nx, int nu, int batch) {
     if (N < 1 || batch < 1) return 0;
     if (kind == IPOC_WS_REDUCTIONS)   // here `nx` carries max(nu, nc)
         return (size_t)batch * reduce_blocks(N, nx > nu ? nx : nu, batch) * 3 * sizeof(double) + 256;
+    if (kind == IPOC_WS_COSTATES || kind == IPOC_WS_NEWTON_ATTEMPT) {   // scan + room for the stand-alone reductions
+        const size_t a = ipoc_workspace_bytes(kind == IPOC_WS_COSTATES ? IPOC_WS_AFFINE_SCAN : IPOC_WS_NEWTON_STEP, N, nx,
+                                              nu, batch);
+        return a == 0 ? 0 : a + ipoc_workspace_bytes(IPOC_WS_REDUCTIONS, N, nu, nu, batch);
+    }
     // the sharded entry points use the same formula with batch = 1 and forced chunking; take the max
 #define X(a) if (nx == a) { size_t s1 = nx_ws_bytes<a>(kind, N, batch, false); \
                             size_t s2 = batch == 1 ? nx_ws_bytes<a>(kind, N, 1, true) : 0; return s1 > s2 ? s1 : s2; }
@@ -463,8 +472,8 @@ int ipoc_newton_step_f64(int N, int nx, int nu, int batch, const double* fx, con
     CHECK_ARGS(N >= 1 && batch >= 1 && fx && fu && ru && Q && R && M && reg && dx && du && Kx && d && pred && feasible && ws);
     CHECK_ALIGN(fx); CHECK_ALIGN(fu); CHECK_ALIGN(ru); CHECK_ALIGN(Q); CHECK_ALIGN(R); CHECK_ALIGN(M);
     CHECK_ALIGN(dx); CHECK_ALIGN(du); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(ws);
-#define X(a) if (nx == a) return nx_newton_step<a>(nu, N, batch, fx, fu, ru, Q, R, M, reg, dx, du, Kx, d, pred, feasible, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_NX(X)
+#define X(a, b) if (nx == a && nu == b) return nxu_newton_step<a, b>(N, batch, fx, fu, ru, Q, R, M, reg, dx, du, Kx, d, pred, feasible, ws, ws_bytes, (cudaStream_t)stream, nullptr);
+    IPOC_FOR_PAIRS(X)
 #undef X
     return IPOC_EUNSUPPORTED_DIM;
 }
@@ -477,8 +486,8 @@ int ipoc_lqt_bwd_f64(int N, int nx, int nu, int batch, const double* A, const do
     CHECK_ARGS((S == nullptr) == (v == nullptr));
     CHECK_ALIGN(A); CHECK_ALIGN(B); CHECK_ALIGN(c); CHECK_ALIGN(Xm); CHECK_ALIGN(U); CHECK_ALIGN(M); CHECK_ALIGN(q);
     CHECK_ALIGN(p); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(ws);
-#define X(a) if (nx == a) return nx_lqt_bwd<a>(nu, N, batch, A, B, c, Xm, U, M, q, p, ST, vT, Kx, d, S, v, pred, feasible, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_NX(X)
+#define X(a, b) if (nx == a && nu == b) return nxu_lqt_bwd<a, b>(N, batch, A, B, c, Xm, U, M, q, p, ST, vT, Kx, d, S, v, pred, feasible, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_PAIRS(X)
 #undef X
     return IPOC_EUNSUPPORTED_DIM;
 }
@@ -489,8 +498,8 @@ int ipoc_lqt_fwd_f64(int N, int nx, int nu, int batch, const double* A, const do
     CHECK_ARGS(N >= 1 && batch >= 1 && A && B && Kx && d && u && x && ws);
     CHECK_ALIGN(A); CHECK_ALIGN(B); CHECK_ALIGN(c); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(u); CHECK_ALIGN(x);
     CHECK_ALIGN(ws);
-#define X(a) if (nx == a) return nx_lqt_fwd<a>(nu, N, batch, A, B, c, Kx, d, x0, u, x, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_NX(X)
+#define X(a, b) if (nx == a && nu == b) return nxu_lqt_fwd<a, b>(N, batch, A, B, c, Kx, d, x0, u, x, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_PAIRS(X)
 #undef X
     return IPOC_EUNSUPPORTED_DIM;
 }
@@ -499,7 +508,7 @@ int ipoc_affine_scan_f64(int reverse, int transpose, int N, int nx, int batch, c
                          const double* seed, double* out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
     CHECK_ARGS(N >= 1 && batch >= 1 && F && c && out && ws);
     CHECK_ALIGN(F); CHECK_ALIGN(c); CHECK_ALIGN(out); CHECK_ALIGN(ws);
-#define X(a) if (nx == a) return nx_affine_scan<a>(reverse, transpose, N, batch, F, c, seed, out, ws, ws_bytes, (cudaStream_t)stream);
+#define X(a) if (nx == a) return nx_affine_scan<a>(reverse, transpose, N, batch, F, c, seed, out, ws, ws_bytes, (cudaStream_t)stream, nullptr, 0, nullptr, nullptr);
     IPOC_FOR_NX(X)
 #undef X
     return IPOC_EUNSUPPORTED_DIM;
@@ -603,12 +612,37 @@ int ipoc_newton_advance_f64(int N, int nx, int nu, int batch, const double* hu, 
     return IPOC_OK;
 }
 
+int ipoc_attempt_finish_f64(int batch, const double* cost, const double* new_cost, const int32_t* traj_feasible,
+                            const double* pred, const int32_t* bwd_feasible, const double* hu, int32_t* active,
+                            double* rp, double* r_inc, int32_t* success, double* gain_ratio, int64_t* inner,
+                            int64_t* iteration, uint8_t* outer_done, int32_t* advanced, double hu_tol,
+                            int max_attempts, int max_iterations, ipoc_stream_t stream) {
+    CHECK_ARGS(batch >= 1 && cost && new_cost && traj_feasible && pred && bwd_feasible && hu && active && rp && r_inc && success && inner && iteration && outer_done && advanced);
+    cudaStream_t st_ = (cudaStream_t)stream;
+    const FinishIO f{AcceptIO{cost, pred, bwd_feasible, rp, r_inc, success, gain_ratio}, hu, active, (long long*)inner,
+                     (long long*)iteration, outer_done, advanced, hu_tol, max_attempts, max_iterations};
+    k_attempt_finish<<<(batch + 127) / 128, 128, 0, st_>>>(batch, f, new_cost, traj_feasible);
+    IPOC_API_LAUNCH_CHECK(st_);
+    return IPOC_OK;
+}
+
+int ipoc_masked_copy_f64(int N, int nx, int nu, int batch, const int32_t* mask, const double* sx, const double* su,
+                         double* dx_, double* du_, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && nx >= 1 && nu >= 1 && batch >= 1 && mask && sx && su && dx_ && du_);
+    cudaStream_t st_ = (cudaStream_t)stream;
+    const long long per_x = (long long)(N + 1) * nx, per_u = (long long)N * nu;
+    const long long chunks = copy_chunks(per_x + per_u, batch);
+    k_masked_copy2<<<(unsigned)(chunks * batch), kCommitThreads, 0, st_>>>(per_x, per_u, (int)chunks, mask, sx, su, dx_, du_);
+    IPOC_API_LAUNCH_CHECK(st_);
+    return IPOC_OK;
+}
+
 int ipoc_newton_bwd_reduce_f64(int N, int nx, int nu, const double* fx, const double* fu, const double* ru,
                                const double* Q, const double* R, const double* M, const double* reg,
                                double* carry_out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
     CHECK_ARGS(N >= 1 && fx && fu && ru && Q && R && M && reg && carry_out && ws);
-#define X(a) if (nx == a) return nx_newton_bwd_reduce<a>(nu, N, fx, fu, ru, Q, R, M, reg, carry_out, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_NX(X)
+#define X(a, b) if (nx == a && nu == b) return nxu_newton_bwd_reduce<a, b>(N, fx, fu, ru, Q, R, M, reg, carry_out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_PAIRS(X)
 #undef X
     return IPOC_EUNSUPPORTED_DIM;
 }
@@ -619,8 +653,8 @@ int ipoc_newton_bwd_apply_f64(int N, int nx, int nu, int rank, int nranks, const
                               int32_t* feasible, double* fwd_carry_out, void* ws, size_t ws_bytes,
                               ipoc_stream_t stream) {
     CHECK_ARGS(N >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && carries && ST && Kx && d && pred && feasible && fwd_carry_out && ws);
-#define X(a) if (nx == a) return nx_newton_bwd_apply<a>(nu, N, rank, nranks, fx, fu, ru, Q, R, M, reg, carries, ST, Kx, d, pred, feasible, fwd_carry_out, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_NX(X)
+#define X(a, b) if (nx == a && nu == b) return nxu_newton_bwd_apply<a, b>(N, rank, nranks, fx, fu, ru, Q, R, M, reg, carries, ST, Kx, d, pred, feasible, fwd_carry_out, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_PAIRS(X)
 #undef X
     return IPOC_EUNSUPPORTED_DIM;
 }
@@ -629,8 +663,8 @@ int ipoc_newton_fwd_apply_f64(int N, int nx, int nu, int rank, int nranks, const
                               const double* Kx, const double* d, const double* fwd_carries, double* dx, double* du,
                               void* ws, size_t ws_bytes, ipoc_stream_t stream) {
     CHECK_ARGS(N >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && fx && fu && Kx && d && fwd_carries && dx && du && ws);
-#define X(a) if (nx == a) return nx_newton_fwd_apply<a>(nu, N, rank, nranks, fx, fu, Kx, d, fwd_carries, dx, du, ws, ws_bytes, (cudaStream_t)stream);
-    IPOC_FOR_NX(X)
+#define X(a, b) if (nx == a && nu == b) return nxu_newton_fwd_apply<a, b>(N, rank, nranks, fx, fu, Kx, d, fwd_carries, dx, du, ws, ws_bytes, (cudaStream_t)stream);
+    IPOC_FOR_PAIRS(X)
 #undef X
     return IPOC_EUNSUPPORTED_DIM;
 }
@@ -652,6 +686,77 @@ int ipoc_affine_apply_f64(int reverse, int transpose, int N, int nx, int rank, i
     IPOC_FOR_NX(X)
 #undef X
     return IPOC_EUNSUPPORTED_DIM;
+}
+
+// ---- fused entry points: the same phases with their neighbouring reductions / glue as side jobs ----------
+int ipoc_costates_f64(int N, int nx, int nu, int batch, const double* fx, const double* cx, const double* lamT,
+                      const double* cu, double* lam, double* cu_norm, void* ws, size_t ws_bytes,
+                      ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && nu >= 1 && fx && cx && lam && ws && ((cu == nullptr) == (cu_norm == nullptr)));
+    CHECK_ALIGN(fx); CHECK_ALIGN(cx); CHECK_ALIGN(lam); CHECK_ALIGN(ws);
+    cudaStream_t st_ = (cudaStream_t)stream;
+    int handled = 0, rc = IPOC_EUNSUPPORTED_DIM;
+    const size_t scan_bytes = ipoc_workspace_bytes(IPOC_WS_AFFINE_SCAN, N, nx, nu, batch);
+    if (scan_bytes == 0) return IPOC_EUNSUPPORTED_DIM;
+    if (ws_bytes < scan_bytes) return IPOC_EWORKSPACE;
+#define X(a) if (nx == a) rc = nx_affine_scan<a>(1, 1, N, batch, fx, cx, lamT, lam, ws, ws_bytes, st_, cu, nu, cu_norm, &handled);
+    IPOC_FOR_NX(X)
+#undef X
+    if (rc != IPOC_OK) return rc;
+    if (cu != nullptr && !(handled & IPOC_X_NORM)) {   // plan without in-kernel completion: the stand-alone reduction
+        const size_t red = ipoc_workspace_bytes(IPOC_WS_REDUCTIONS, N, nu, nu, batch);
+        if (ws_bytes < scan_bytes + red) return IPOC_EWORKSPACE;
+        return ipoc_reductions_f64(N, nu, 1, batch, nullptr, cu, nullptr, nullptr, cu_norm, nullptr, nullptr, nullptr,
+                                   (char*)ws + scan_bytes, ws_bytes - scan_bytes, stream);
+    }
+    return IPOC_OK;
+}
+
+int ipoc_newton_attempt_f64(int N, int nx, int nu, int nc, int batch, const double* fx, const double* fu,
+                            const double* ru, const double* Q, const double* R, const double* M, const double* rp,
+                            const double* cu_norm, double* dx, double* du, double* Kx, double* d, double* pred,
+                            int32_t* feasible, double* hu, const double* x, const double* u, double* tx, double* tu,
+                            const double* cons, int32_t* traj_feasible, const double* cost, const double* new_cost,
+                            const int32_t* traj_feas_in, const int32_t* active, double* rp_out, double* r_inc,
+                            int32_t* success, double* gain_ratio, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
+    CHECK_ARGS(N >= 1 && batch >= 1 && fx && fu && ru && Q && R && M && rp && dx && du && Kx && d && pred && feasible && ws);
+    CHECK_ARGS((tx == nullptr) == (tu == nullptr) && (tx == nullptr || (x && u)));
+    CHECK_ARGS(cons == nullptr || (traj_feasible != nullptr && nc >= 1));
+    CHECK_ARGS(rp_out == nullptr || (cost && new_cost && r_inc && success && (cons || traj_feas_in)));
+    CHECK_ALIGN(fx); CHECK_ALIGN(fu); CHECK_ALIGN(ru); CHECK_ALIGN(Q); CHECK_ALIGN(R); CHECK_ALIGN(M);
+    CHECK_ALIGN(dx); CHECK_ALIGN(du); CHECK_ALIGN(Kx); CHECK_ALIGN(d); CHECK_ALIGN(ws);
+    CHECK_ALIGN(x); CHECK_ALIGN(u); CHECK_ALIGN(tx); CHECK_ALIGN(tu);
+    cudaStream_t st_ = (cudaStream_t)stream;
+    const size_t step_bytes = ipoc_workspace_bytes(IPOC_WS_NEWTON_STEP, N, nx, nu, batch);
+    if (step_bytes == 0) return IPOC_EUNSUPPORTED_DIM;
+    if (ws_bytes < step_bytes) return IPOC_EWORKSPACE;
+    AttemptExtras xt{};
+    xt.reg_scale = cu_norm;
+    xt.hu = hu;
+    xt.x = x; xt.u = u; xt.tx = tx; xt.tu = tu;
+    xt.cons = cons; xt.nc = nc; xt.traj_feasible = traj_feasible;
+    xt.cost = cost; xt.new_cost = new_cost; xt.traj_feas_in = traj_feas_in; xt.active = active;
+    xt.rp = rp_out; xt.r_inc = r_inc; xt.success = success; xt.gain = gain_ratio;
+    int rc = IPOC_EUNSUPPORTED_DIM;
+#define X(a, b) if (nx == a && nu == b) rc = nxu_newton_step<a, b>(N, batch, fx, fu, ru, Q, R, M, rp, dx, du, Kx, d, pred, feasible, ws, step_bytes, st_, &xt);
+    IPOC_FOR_PAIRS(X)
+#undef X
+    if (rc != IPOC_OK) return rc;
+    // whatever the scan plan could not carry as a side job runs as the stand-alone kernels (same results)
+    char* rws = (char*)ws + step_bytes;
+    const size_t rbytes = ws_bytes - step_bytes;
+    if (hu != nullptr && !(xt.handled & IPOC_X_HU))
+        if (int r2 = ipoc_reductions_f64(N, nu, 1, batch, ru, nullptr, nullptr, hu, nullptr, nullptr, nullptr, nullptr, rws,
+                                         rbytes, stream)) return r2;
+    if (tx != nullptr && !(xt.handled & IPOC_X_TRIAL))
+        if (int r2 = ipoc_trial_point_f64(N, nx, nu, batch, x, dx, u, du, tx, tu, stream)) return r2;
+    if (cons != nullptr && !(xt.handled & IPOC_X_CONS))
+        if (int r2 = ipoc_reductions_f64(N, nu, nc, batch, nullptr, nullptr, cons, nullptr, nullptr, traj_feasible, nullptr,
+                                         nullptr, rws, rbytes, stream)) return r2;
+    if (rp_out != nullptr && !(xt.handled & IPOC_X_ACCEPT))
+        if (int r2 = ipoc_accept_update_f64(batch, cost, new_cost, cons != nullptr ? traj_feasible : traj_feas_in, pred,
+                                            feasible, active, rp_out, r_inc, success, gain_ratio, stream)) return r2;
+    return IPOC_OK;
 }
 
 size_t ipoc_newton_step_host_scratch_bytes(int N, int nx, int nu, int batch) {
@@ -687,6 +792,7 @@ int ipoc_newton_step_host_f64(int N, int nx, int nu, int batch, const double* fx
     const size_t wsb = ipoc_workspace_bytes(IPOC_WS_NEWTON_STEP, N, nx, nu, batch);
     void* ws = bp.take<char>(wsb);
     if (bp.off > dws_bytes) return IPOC_EWORKSPACE;
+    if (cudaMemsetAsync(ws, 0, IPOC_WS_CONTROL_BYTES, st) != cudaSuccess) return IPOC_ECUDA;   // control block of a fresh carve
     const size_t D = sizeof(double);
     bool ok = true;
     ok &= cudaMemcpyAsync(dfx, fx, T * nx * nx * D, cudaMemcpyHostToDevice, st) == cudaSuccess;

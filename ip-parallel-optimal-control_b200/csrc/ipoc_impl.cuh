@@ -32,6 +32,7 @@
 #include "ipoc_math.cuh"
 #include "../../include/ipoc.h"
 #include "ipoc_dispatch.h"
+#include "ipoc_accept.cuh"
 
 namespace ipoc {
 
@@ -42,6 +43,12 @@ struct Tuning {
 extern unsigned long long g_launches;
 extern Tuning g_tune;
 extern int g_literal_lqt;   // 0: q = 0, p = ru (default); 1: literal noc_to_lqt arithmetic
+struct HierTuning {
+    int enabled;      // 1 (default): levels above the warps are completed inside the leaf kernels (last arriver)
+    int group_warps;  // warps per group (0 = 32)
+    int serial_top;   // up to this many groups the top is a serial chain of `apply` (0 = 8)
+};
+extern HierTuning g_hier;
 void prof_mark(const char* name, cudaStream_t st);   // no-op unless profiling is armed
 
 constexpr int kLeafThreads = 128;
@@ -68,6 +75,13 @@ IPOC_DEV void soa_load(T& t, const double* __restrict__ base, size_t stride, siz
     constexpr int SZ = sizeof(T) / sizeof(double);
 #pragma unroll
     for (int c = 0; c < SZ; ++c) t.r[c] = base[(size_t)c * stride + idx];
+}
+// same, through L2 (data another SM may have written during this kernel)
+template <class T>
+IPOC_DEV void soa_load_cg(T& t, const double* base, size_t stride, size_t idx) {
+    constexpr int SZ = sizeof(T) / sizeof(double);
+#pragma unroll
+    for (int c = 0; c < SZ; ++c) t.r[c] = __ldcg(base + (size_t)c * stride + idx);
 }
 template <class T>
 IPOC_DEV void soa_store(const T& t, double* __restrict__ base, size_t stride, size_t idx) {
@@ -139,11 +153,11 @@ IPOC_DEV double* warp_scan_mem(double* ws, int lane, bool reverse, int used = 32
 // Register-resident variant for the leaf kernels (many warps per SM, code stays hot): the combine
 // is inlined, both operands are read from one shared buffer, the result stays in registers.
 template <class Op>
-IPOC_DEV void warp_scan(typename Op::Elem& a, double* ws, int lane, bool reverse) {
+IPOC_DEV void warp_scan(typename Op::Elem& a, double* ws, int lane, bool reverse, int used = 32) {
     constexpr int ESZ = sizeof(typename Op::Elem) / sizeof(double);
     using View = typename Op::View;
 #pragma unroll 1
-    for (int delta = 1; delta < 32; delta <<= 1) {
+    for (int delta = 1; delta < used; delta <<= 1) {
 #pragma unroll
         for (int c = 0; c < ESZ; ++c) ws[c * 32 + lane] = a.r[c];
         __syncwarp();
@@ -190,30 +204,52 @@ k_mid_down(const double* __restrict__ agg, size_t astride, int n_in,
     }
 }
 
-// Side job a top kernel can do for its sequence (saves a launch): fixed-order reduction of the
-// per-warp pred / feasibility partials of K2 -> pred = -1/2 sum d'Gd, feasible = AND (G > 0).
-struct PredJob {
-    const double* pred_part;
+// fixed-order folds of per-warp partials, done by the warp that completes a sequence
+struct SideJobs {
+    int n;                        // partials per sequence (= nW)
+    const double* pred_part;      // K2 down-sweep: sum d'Gd, AND (G > 0)       -> pred, feasible
     const int* feas_part;
-    int n;
     double* pred;
     int32_t* feasible;
+    const double* sq_part;        // K1 up-sweep: sum cu^2                      -> ||cu||_F
+    double* cu_norm;
+    const double* mx_part;        // K2 up-sweep: max|ru| (NaN-propagating)     -> hu
+    double* hu;
 };
-IPOC_DEV void pred_reduce(const PredJob& pj, int b, int lane) {   // one full warp; fixed order
-    double acc = 0.0;
-    int f = 1;
-    for (int j = lane; j < pj.n; j += 32) {
-        acc += pj.pred_part[(size_t)b * pj.n + j];
-        f &= pj.feas_part[(size_t)b * pj.n + j];
-    }
+IPOC_DEV double nan_max_d(double a, double c) {
+    return (a != a || c != c) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(a, c);
+}
+IPOC_DEV void side_finish(const SideJobs& sj, int b, int lane) {   // one full warp
+    if (sj.pred != nullptr) {
+        double acc = 0.0;
+        int f = 1;
+        for (int j = lane; j < sj.n; j += 32) {
+            acc += __ldcg(sj.pred_part + (size_t)b * sj.n + j);
+            f &= __ldcg(sj.feas_part + (size_t)b * sj.n + j);
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        f &= __shfl_xor_sync(0xffffffffu, f, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            f &= __shfl_xor_sync(0xffffffffu, f, o);
+        }
+        if (lane == 0) {
+            sj.pred[b] = -0.5 * acc;
+            sj.feasible[b] = f;
+        }
     }
-    if (lane == 0) {
-        pj.pred[b] = -0.5 * acc;
-        pj.feasible[b] = f;
+    if (sj.cu_norm != nullptr) {
+        double acc = 0.0;
+        for (int j = lane; j < sj.n; j += 32) acc += __ldcg(sj.sq_part + (size_t)b * sj.n + j);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) sj.cu_norm[b] = sqrt(acc);
+    }
+    if (sj.hu != nullptr) {
+        double m = 0.0;
+        for (int j = lane; j < sj.n; j += 32) m = nan_max_d(m, __ldcg(sj.mx_part + (size_t)b * sj.n + j));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = nan_max_d(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) sj.hu[b] = m;
     }
 }
 
@@ -227,7 +263,7 @@ template <class Op>
 __global__ void __launch_bounds__(kTopThreads)
 k_top(const double* __restrict__ agg, size_t astride, int n, int batch,
       const double* __restrict__ seed, double* __restrict__ vals, size_t vstride,
-      double* __restrict__ total, int reduce_only, PredJob pj) {
+      double* __restrict__ total, int reduce_only, SideJobs sj) {
     using Val = typename Op::Val;
     constexpr int ESZ = sizeof(typename Op::Elem) / sizeof(double);
     constexpr int VSZ = sizeof(Val) / sizeof(double);
@@ -243,7 +279,7 @@ k_top(const double* __restrict__ agg, size_t astride, int n, int batch,
     const size_t base = (size_t)b * n;
     const int j0 = t * q, j1 = min(n, j0 + q);
     double* ws = s_scan + (size_t)w * WSZ;
-    if (pj.pred != nullptr && w == nw - 1) pred_reduce(pj, b, lane);
+    if (w == nw - 1) side_finish(sj, b, lane);   // side jobs of the sequence (saves a launch each)
 
     // thread-level fold of its q aggregates, accumulated in place in the scan scratch
     if (j0 < n) {
@@ -318,6 +354,175 @@ __global__ void k_chain_seed(const double* __restrict__ carries, int first, int 
     for (int i = 0, r = first; i < count; ++i, r += step) Op::apply_mm(v, carries + (size_t)r * ESZ, 1);
 #pragma unroll
     for (int c = 0; c < VSZ; ++c) seed_out[c] = v.r[c];
+}
+
+
+// ------------------------------------------------------------------ levels inside the leaf kernels
+// "Last arriver works" completion of a hierarchical scan, WITHOUT spin-waiting (a launch can never hang
+// and stays graph-capturable): the warps of a sequence are grouped by `gw` consecutive warps in scan
+// order.  A warp that has stored its total arrives on its group's counter; the last arriver of a group
+// scans the group's (<= 32) warp totals in place of a mid-level kernel and arrives on the sequence's
+// counter; the last group scans the group totals in place of the single-CTA top kernel and finishes the
+// side jobs (fixed-order folds of per-warp partials).  Group scans of early groups overlap with the leaf
+// work of later ones.  The seeded way down needs no kernel of its own either: every warp of the
+// down-sweep re-derives the value entering it with at most two `apply`s (hier_enter).
+//
+// Arrival counters are 32-bit words of the workspace's CONTROL BLOCK (its first kCtrlBytes): the caller
+// zero-fills it once (ipoc_workspace_init) and every launch leaves it zero again — the count is an atomic
+// increment that wraps to 0 on the last arrival — so replays of captured graphs and calls with other plans
+// on the same workspace always find zeros.  One acq_rel atomic per warp: its release side publishes what the
+// warp's lanes wrote before the __syncwarp (cumulativity), its acquire side orders the last arriver's reads.
+constexpr int kCtrlBytes = 64 * 1024;
+constexpr int kCtrlRegionWords = 4096;     // three regions: backward/primary scan, forward scan, tail job
+IPOC_DEV bool warp_arrive_last(unsigned* w, unsigned expected, int lane) {
+    __syncwarp();
+    unsigned old = 0;
+    if (lane == 0)
+        asm volatile("atom.acq_rel.gpu.global.inc.u32 %0, [%1], %2;" : "=r"(old) : "l"(w), "r"(expected - 1u) : "memory");
+    old = __shfl_sync(0xffffffffu, old, 0);
+    __syncwarp();
+    return old == expected - 1u;
+}
+
+struct Hier {
+    unsigned* cnt;             // NULL = levels run as separate kernels
+    int gw, ngroups, serial_top;
+    double* incl1;             // in-group inclusive aggregates of the warp totals, index b*nW + s   (stride s1)
+    size_t s1;
+    double* agg2;              // group totals, index b*ngroups + g                                  (stride s2)
+    double* incl2;             // inclusive aggregates over the groups (split-phase / wide tops)     (stride s2)
+    size_t s2;
+    double* val2;              // value entering each group, index b*ngroups + g                     (stride s2)
+    const double* seed;        // SoA, stride batch; NULL = reduce only (time-sharded phase 1)
+    double* total;             // composition of the whole sequence, SoA stride batch; may be NULL
+};
+
+// Called by every warp of a leaf kernel after it has stored its total at agg0[b*nW + s] (s = index of
+// the warp in scan order).  `scr` = the warp's shared scratch, 2 x ESZ x 32 doubles.
+template <class Op>
+IPOC_DEV void hier_finish(const Hier& h, int nW, int batch, const double* agg0, size_t a0stride, int b, int s, int lane,
+                          double* scr, const SideJobs& sj) {
+    using Val = typename Op::Val;
+    constexpr int ESZ = sizeof(typename Op::Elem) / sizeof(double);
+    const int grp = s / h.gw;
+    const int g0 = grp * h.gw;
+    const int gsize = min(h.gw, nW - g0);
+    if (gsize > 1 && !warp_arrive_last(h.cnt + (size_t)b * h.ngroups + grp, (unsigned)gsize, lane)) return;
+    // ---- level 2: inclusive scan of this group's warp totals
+    {
+        typename Op::Elem id;
+        Op::identity(id);
+#pragma unroll
+        for (int c = 0; c < ESZ; ++c)
+            scr[c * 32 + lane] = (lane < gsize) ? __ldcg(agg0 + (size_t)c * a0stride + (size_t)b * nW + g0 + lane) : id.r[c];
+        __syncwarp();
+        const double* inc = warp_scan_mem<Op>(scr, lane, false, gsize);
+        if (lane < gsize) {
+#pragma unroll
+            for (int c = 0; c < ESZ; ++c) h.incl1[(size_t)c * h.s1 + (size_t)b * nW + g0 + lane] = inc[c * 32 + lane];
+        }
+        if (lane == gsize - 1) {
+#pragma unroll
+            for (int c = 0; c < ESZ; ++c) h.agg2[(size_t)c * h.s2 + (size_t)b * h.ngroups + grp] = inc[c * 32 + lane];
+        }
+        __syncwarp();
+    }
+    if (h.ngroups > 1)
+        if (!warp_arrive_last(h.cnt + (size_t)batch * h.ngroups + b, (unsigned)h.ngroups, lane)) return;
+    // ---- level 3: this warp completes the sequence
+    const size_t gb = (size_t)b * h.ngroups;
+    const bool wide = h.ngroups > h.serial_top || h.total != nullptr || h.seed == nullptr;
+    if (!wide) {
+        // few groups: values travel through a short serial chain of `apply` (about half a combine each);
+        // every lane does the same arithmetic, lane 0 stores.  All loads (group totals and seed through L2:
+        // other SMs wrote them) are issued before the side jobs' folds so that their round trips overlap.
+        double tot[ESZ];
+        if (lane < h.ngroups) {
+#pragma unroll
+            for (int c = 0; c < ESZ; ++c) tot[c] = __ldcg(h.agg2 + (size_t)c * h.s2 + gb + lane);
+        }
+        Val v;
+        soa_load_cg(v, h.seed, (size_t)batch, (size_t)b);
+        side_finish(sj, b, lane);
+        if (lane < h.ngroups) {
+#pragma unroll
+            for (int c = 0; c < ESZ; ++c) scr[c * 32 + lane] = tot[c];
+        }
+        __syncwarp();
+        for (int g = 0; g < h.ngroups; ++g) {
+            if (lane == 0) soa_store(v, h.val2, h.s2, gb + g);
+            if (g + 1 < h.ngroups) Op::apply_mm(v, scr + g, 32);
+        }
+        return;
+    }
+    side_finish(sj, b, lane);
+    // many groups (or the composition of everything is wanted): fold q consecutive group totals per lane,
+    // scan the lanes, then walk the q groups again with the value entering the lane
+    const int q = (h.ngroups + 31) / 32;
+    const int j0 = lane * q, j1 = min(h.ngroups, j0 + q);
+    if (j0 < h.ngroups) {
+#pragma unroll
+        for (int c = 0; c < ESZ; ++c) scr[c * 32 + lane] = __ldcg(h.agg2 + (size_t)c * h.s2 + gb + j0);
+        for (int j = j0 + 1; j < j1; ++j) Op::compose_mm(scr + lane, 32, scr + lane, 32, h.agg2 + gb + j, (int)h.s2);
+    } else {
+        typename Op::Elem id;
+        Op::identity(id);
+#pragma unroll
+        for (int c = 0; c < ESZ; ++c) scr[c * 32 + lane] = id.r[c];
+    }
+    __syncwarp();
+    const int used = (h.ngroups + q - 1) / q;
+    const double* inc = warp_scan_mem<Op>(scr, lane, false, used);
+    if (q == 1 && h.incl2 != nullptr && lane < h.ngroups) {
+#pragma unroll
+        for (int c = 0; c < ESZ; ++c) h.incl2[(size_t)c * h.s2 + gb + lane] = inc[c * 32 + lane];
+    }
+    if (h.total != nullptr && lane == used - 1) {
+#pragma unroll
+        for (int c = 0; c < ESZ; ++c) h.total[(size_t)c * batch + b] = inc[c * 32 + lane];
+    }
+    if (h.seed == nullptr) return;
+    Val v;
+    soa_load_cg(v, h.seed, (size_t)batch, (size_t)b);
+    if (lane > 0 && lane < used) Op::apply_mm(v, inc + lane - 1, 32);
+    if (j0 < h.ngroups) {
+        for (int j = j0; j < j1; ++j) {
+            soa_store(v, h.val2, h.s2, gb + j);
+            if (j + 1 < j1) Op::apply_mm(v, h.agg2 + gb + j, (int)h.s2);
+        }
+    }
+}
+
+// Way down: the value entering warp s of sequence b (every lane computes the same thing).
+//   chain (time-sharded phase 2): the seed of the whole horizon is first pushed through the gathered
+//   aggregates of the other ranks (rank-major AoS), then through this rank's inclusive group aggregates.
+struct HierIn {
+    int on;                    // 0 = values come from the legacy level kernels / the seed
+    int gw, ngroups;
+    const double* incl1;
+    size_t s1;
+    const double* val2;        // NULL in chain mode
+    const double* incl2;
+    size_t s2;
+    const double* carries;     // chain mode: gathered rank aggregates [r * ESZ + c]
+    int chain_first, chain_step, chain_count;
+    const double* seed0;       // chain mode: packed Val of the horizon's end (device, VSZ doubles); NULL = zeros
+};
+template <class Op>
+IPOC_DEV void hier_enter(typename Op::Val& v, const HierIn& h, int nW, int b, int s) {
+    constexpr int ESZ = sizeof(typename Op::Elem) / sizeof(double);
+    constexpr int VSZ = sizeof(typename Op::Val) / sizeof(double);
+    const int grp = s / h.gw, r = s - grp * h.gw;
+    if (h.val2 != nullptr) {
+        soa_load(v, h.val2, h.s2, (size_t)b * h.ngroups + grp);
+    } else {
+#pragma unroll
+        for (int c = 0; c < VSZ; ++c) v.r[c] = (h.seed0 != nullptr) ? h.seed0[c] : 0.0;
+        for (int i = 0, rk = h.chain_first; i < h.chain_count; ++i, rk += h.chain_step)
+            Op::apply_mm(v, h.carries + (size_t)rk * ESZ, 1);
+        if (grp > 0) Op::apply_mm(v, h.incl2 + (size_t)b * h.ngroups + grp - 1, (int)h.s2);
+    }
+    if (r > 0) Op::apply_mm(v, h.incl1 + (size_t)b * nW + s - 1, (int)h.s1);
 }
 
 // ------------------------------------------------------------------ leaf geometry
@@ -485,6 +690,7 @@ IPOC_DEV void staged_walk(const Ld& ld, const WarpSmem& w, int T, int len, int l
 template <int NX, int NU, bool LITERAL = false>
 struct NewtonLoader {
     const double *fx, *fu, *ru, *Q, *R, *M, *reg;
+    const double* reg_scale;   // optional second device scalar per problem: reg_eff = reg * reg_scale (rp * ||cu||, ref :117)
     static constexpr int O_FX = 0, O_FU = O_FX + arr_bytes(NX * NX), O_Q = O_FU + arr_bytes(NX * NU),
                          O_R = O_Q + arr_bytes(NX * NX), O_M = O_R + arr_bytes(NU * NU),
                          O_RU = O_M + arr_bytes(NX * NU), STAGE_BYTES = O_RU + arr_bytes(NU);
@@ -498,7 +704,16 @@ struct NewtonLoader {
     }
     // per-lane constant fetched ONCE before the walk (a global load inside the step loop would expose
     // its full latency every step: 16 % of the stall samples in profiles/r01)
-    IPOC_DEV double aux(int b) const { return __ldg(reg + b); }
+    IPOC_DEV double aux(int b) const { return reg_scale != nullptr ? __ldg(reg + b) * __ldg(reg_scale + b) : __ldg(reg + b); }
+    // max |ru| of the staged step (side job of the up-sweep: ref :158)
+    IPOC_DEV double ru_absmax(const char* st, int lane) const {
+        double ruv[NU];
+        read_row<NU>(ruv, st + O_RU, lane);
+        double m = 0.0;
+#pragma unroll
+        for (int a = 0; a < NU; ++a) m = nan_max_d(m, fabs(ruv[a]));
+        return m;
+    }
     IPOC_DEV void read(StepLQ<NX, NU>& s, const char* st, int lane, double rg) const {
         double Qf[NX][NX], Rf[NU][NU], ruv[NU];
         read_row<NX * NX>(&s.A[0][0], st + O_FX, lane);
@@ -596,6 +811,7 @@ struct LqtLoader {
         issue_rows<NU>(st + O_P, p, m, j, lane);
     }
     IPOC_DEV double aux(int) const { return 0.0; }
+    IPOC_DEV double ru_absmax(const char*, int) const { return 0.0; }
     IPOC_DEV void read(StepLQ<NX, NU>& s, const char* st, int lane, double) const {
         double Xf[NX][NX], Uf[NU][NU];
         read_row<NX * NX>(&s.A[0][0], st + O_A, lane);
@@ -702,29 +918,44 @@ __global__ void k_ric_seed(SeedJob sj) {
 template <int NX, int NU, class Loader>
 __global__ void __launch_bounds__(kLeafThreads, IPOC_RIC_MINB)
 k_ric_leaf_up(Loader ld, Geom g, double* __restrict__ incl, size_t istride, double* __restrict__ agg1,
-              size_t a1stride, SeedJob sj) {
+              size_t a1stride, SeedJob sj, Hier h, SideJobs side, double* __restrict__ mx_part) {
     extern __shared__ __align__(16) char smem[];
-    if (sj.ST != nullptr && blockIdx.x == 0)
-        for (int b = threadIdx.x; b < sj.batch; b += blockDim.x) make_ric_seed<NX>(sj, b);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     if (wg >= total_warps(g)) return;
     const Lane L = lane_info(g, wg, lane);
     const WarpSmem w = warp_smem(smem, g, wib, wg);
+    // seeds of a sequence are written by its first warp, i.e. before that warp's arrival on the sequence's
+    // counters: whoever completes the levels in this kernel, and every later kernel, sees them
+    if (sj.ST != nullptr && L.wi == 0 && lane == 0) make_ric_seed<NX>(sj, L.b);
     RicElem<NX> a;
     RicOp<NX>::identity(a);
     StepElem<NX, NU> e;   // formed in the fetch phase: smaller than the raw step, lives across the copy issue
     const double aux = ld.aux(L.b);
+    double mx = 0.0;
     staged_walk<IPOC_NS_RIC_UP>(ld, w, g.T0, L.len, lane, true,
                 [&](const char* st) {
                     StepLQ<NX, NU> s;
                     ld.read(s, st, lane, aux);
+                    if (mx_part != nullptr) mx = nan_max_d(mx, ld.ru_absmax(st, lane));
                     make_step_elem(e, s);
                 },
                 [&](int) { ric_prepend_step(a, e); });
     warp_scan<RicOp<NX>>(a, reinterpret_cast<double*>(w.stage0), lane, true);
     soa_store(a, incl, istride, (size_t)L.slot);
-    if (lane == 0) soa_store(a, agg1, a1stride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
+    const int sidx = g.nW - 1 - L.wi;   // index of this warp in scan order (end of the horizon first)
+    if (lane == 0) soa_store(a, agg1, a1stride, (size_t)L.b * g.nW + sidx);
+    if (mx_part != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = nan_max_d(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) mx_part[(size_t)L.b * g.nW + sidx] = mx;
+    }
+    if (h.cnt != nullptr) {
+        __syncwarp();
+        hier_finish<RicOp<NX>>(h, g.nW, g.batch, agg1, a1stride, L.b, sidx, lane, reinterpret_cast<double*>(w.stage0), side);
+    } else if (g.nW == 1 && side.hu != nullptr && lane == 0) {
+        side.hu[L.b] = mx;   // one warp per sequence: nothing to fold
+    }
 }
 
 // Down-sweep: seeded Riccati recursion over the chunk, gains out, pred/feasibility partials, and
@@ -739,11 +970,14 @@ k_ric_leaf_down(Loader ld, Geom g, const double* __restrict__ incl, size_t istri
                 double* __restrict__ S_out, double* __restrict__ v_out,
                 double* __restrict__ pred_part, int* __restrict__ feas_part,
                 double* __restrict__ pred, int32_t* __restrict__ feasible,
-                double* __restrict__ fincl, size_t fistride, double* __restrict__ fagg1, size_t fa1stride) {
+                double* __restrict__ fincl, size_t fistride, double* __restrict__ fagg1, size_t fa1stride,
+                HierIn hin, Hier hf, SideJobs side) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
-    if (wg >= total_warps(g)) return;
+    // the grid runs over the warps in the REVERSE order of the up-sweep: the first CTAs re-read what the
+    // up-sweep fetched last, i.e. what is still in L2
+    const long long wg = total_warps(g) - 1 - ((long long)blockIdx.x * (blockDim.x >> 5) + wib);
+    if (wg < 0) return;
     const Lane L = lane_info(g, wg, lane);
     const WarpSmem w = warp_smem(smem, g, wib, wg);
     const int N = g.N;
@@ -751,7 +985,8 @@ k_ric_leaf_down(Loader ld, Geom g, const double* __restrict__ incl, size_t istri
     if (g.per_lane) {
         soa_load(val, wvals, wvstride, (size_t)L.b);
     } else {
-        soa_load(val, wvals, wvstride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
+        if (hin.on) hier_enter<RicOp<NX>>(val, hin, g.nW, L.b, g.nW - 1 - L.wi);
+        else soa_load(val, wvals, wvstride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
         if (lane < 31) {   // exclusive prefix (scan order) = inclusive aggregate of the next lane
             RicElem<NX> ex;
             soa_load(ex, incl, istride, (size_t)L.slot + 1);
@@ -818,12 +1053,43 @@ k_ric_leaf_down(Loader ld, Geom g, const double* __restrict__ incl, size_t istri
         warp_scan<AffOp<NX>>(fa, reinterpret_cast<double*>(w.stage0), lane, false);
         soa_store(fa, fincl, fistride, (size_t)L.slot);
         if (lane == 31) soa_store(fa, fagg1, fa1stride, (size_t)L.b * g.nW + L.wi);
+        if (hf.cnt != nullptr) {   // K3's levels (and the pred / feasibility fold) completed by the last arrivers
+            __syncwarp();
+            hier_finish<AffOp<NX>>(hf, g.nW, g.batch, fagg1, fa1stride, L.b, L.wi, lane, reinterpret_cast<double*>(w.stage0),
+                                   side);
+        }
     }
 }
 
 // pred / feasible finalisation as a stand-alone launch (only when no K3 top scan follows that could
 // carry it as a side job).
-static __global__ void __launch_bounds__(32) k_finalize_pred(PredJob pj) { pred_reduce(pj, blockIdx.x, threadIdx.x); }
+static __global__ void __launch_bounds__(32) k_finalize_pred(SideJobs sj) { side_finish(sj, blockIdx.x, threadIdx.x); }
+
+// Tail of an accept/reject attempt as a side job of K3's leaf kernel (saves three launches per attempt):
+//   trial point   tx = x + dx, tu = u + du                                  (ref :156-157)
+//   constraints   traj_feasible = all(cons <= 0) of a GIVEN constraint array (ref :45-47)
+//   accept        gain ratio, success, rp / r_inc update                    (ref :159-173) by the last arriver
+struct TailJob {
+    unsigned* cnt;             // NULL = no last-arriver work (the trial point alone needs none)
+    const double *x, *u;       // trial point (all four NULL = off)
+    double *tx, *tu;
+    const int32_t* trial_mask; // members whose trial point is written (NULL = all): frozen members keep theirs
+    const double* cons;        // (batch, N, nc); NULL = off
+    int nc;
+    int* cons_part;            // per-warp AND
+    int32_t* traj_feasible;
+    const double *cost, *new_cost;   // accept (rp == NULL = off)
+    const int32_t* traj_feas_in;     // used when cons == NULL
+    const double* pred;
+    const int32_t *bwd_feasible, *active;
+    double *rp, *r_inc;
+    int32_t* success;
+    double* gain;
+};
+IPOC_DEV void accept_rule(const TailJob& t, int b, int traj_ok) {   // same arithmetic as k_accept_update
+    if (t.active != nullptr && !t.active[b]) return;
+    accept_rule_core(AcceptIO{t.cost, t.pred, t.bwd_feasible, t.rp, t.r_inc, t.success, t.gain}, b, t.new_cost[b], traj_ok);
+}
 
 // ------------------------------------------------------------------ K3 leaves
 template <int NX, int NU>
@@ -847,7 +1113,7 @@ template <int NX, int NU>
 __global__ void __launch_bounds__(kLeafThreads)
 k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, size_t fistride,
                 const double* __restrict__ xw, size_t xwstride,
-                double* __restrict__ x_out, double* __restrict__ u_out) {
+                double* __restrict__ x_out, double* __restrict__ u_out, HierIn hin, TailJob tail) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -859,7 +1125,8 @@ k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, 
     if (g.per_lane) {
         soa_load(xv, xw, xwstride, (size_t)L.b);
     } else {
-        soa_load(xv, xw, xwstride, (size_t)L.b * g.nW + L.wi);
+        if (hin.on) hier_enter<AffOp<NX>>(xv, hin, g.nW, L.b, L.wi);
+        else soa_load(xv, xw, xwstride, (size_t)L.b * g.nW + L.wi);
         if (lane > 0) {
             AffElem<NX> ex;
             soa_load(ex, fincl, fistride, (size_t)L.slot - 1);
@@ -869,6 +1136,12 @@ k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, 
     double x[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = xv.r[i];
+    double xnom[NX], unom[NU];   // nominal trajectory rows of the trial-point side job, one step ahead
+    const bool do_trial = tail.tx != nullptr && (tail.trial_mask == nullptr || tail.trial_mask[L.b] != 0);
+    if (do_trial && L.len > 0) {
+        ld_vec<NX>(xnom, tail.x + ((size_t)L.b * (N + 1) + L.k0) * NX);
+        ld_vec<NU>(unom, tail.u + (size_t)L.t0 * NU);
+    }
     double Am[NX][NX], Bm[NX][NU], Km[NU][NX], dv[NU], cv[NX];
     staged_walk<IPOC_NS_LIGHT>(ld, w, g.T0, L.len, lane, false,
                 [&](const char* st) { read_fwd_step<NX, NU>(ld, st, lane, Am, Bm, Km, dv, cv); }, [&](int j) {
@@ -881,8 +1154,22 @@ k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, 
             u[a] = v;
         }
         const size_t t = (size_t)(L.t0 + j);
-        st_vec<NX>(x_out + ((size_t)L.b * (N + 1) + L.k0 + j) * NX, x);
+        const size_t xrow = ((size_t)L.b * (N + 1) + L.k0 + j) * NX;
+        st_vec<NX>(x_out + xrow, x);
         st_vec<NU>(u_out + t * NU, u);
+        if (do_trial) {   // trial point (ref :156-157); the nominal rows were prefetched one step ahead
+            double tv[NX], tw[NU];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) tv[i] = xnom[i] + x[i];
+#pragma unroll
+            for (int a = 0; a < NU; ++a) tw[a] = unom[a] + u[a];
+            st_vec<NX>(tail.tx + xrow, tv);
+            st_vec<NU>(tail.tu + t * NU, tw);
+            if (j + 1 < L.len) {
+                ld_vec<NX>(xnom, tail.x + xrow + NX);
+                ld_vec<NU>(unom, tail.u + (t + 1) * NU);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
             double v = cv[i];
@@ -895,7 +1182,40 @@ k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, 
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = xn[i];
     });
-    if (L.len > 0 && L.k0 + L.len == N) st_vec<NX>(x_out + ((size_t)L.b * (N + 1) + N) * NX, x);
+    if (L.len > 0 && L.k0 + L.len == N) {
+        const size_t xrow = ((size_t)L.b * (N + 1) + N) * NX;
+        st_vec<NX>(x_out + xrow, x);
+        if (do_trial) {
+            double tv[NX];
+            ld_vec<NX>(tv, tail.x + xrow);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) tv[i] += x[i];
+            st_vec<NX>(tail.tx + xrow, tv);
+        }
+    }
+    if (tail.cnt == nullptr || g.per_lane) return;
+    // ---- constraint feasibility of a given array + accept / regularisation update by the last arriver
+    int ok = 1;
+    if (tail.cons != nullptr) {
+        const double* cp = tail.cons + (size_t)L.t0 * tail.nc;
+        const int n = L.len * tail.nc;
+        for (int i = 0; i < n; ++i) ok &= (__ldg(cp + i) <= 0.0) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+        if (lane == 0) tail.cons_part[wg] = ok;
+    }
+    if (g.nW > 1)
+        if (!warp_arrive_last(tail.cnt + L.b, (unsigned)g.nW, lane)) return;
+    int traj_ok = 1;
+    if (tail.cons != nullptr) {
+        for (int jw = lane; jw < g.nW; jw += 32) traj_ok &= __ldcg(tail.cons_part + (size_t)L.b * g.nW + jw);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) traj_ok &= __shfl_xor_sync(0xffffffffu, traj_ok, o);
+        if (lane == 0) tail.traj_feasible[L.b] = traj_ok;
+    } else if (tail.traj_feas_in != nullptr) {
+        traj_ok = tail.traj_feas_in[L.b];
+    }
+    if (tail.rp != nullptr && lane == 0) accept_rule(tail, L.b, traj_ok);
 }
 
 // K3 leaf up (only for the stand-alone par_fwd_pass API; the Newton step gets these aggregates
@@ -903,7 +1223,7 @@ k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, 
 template <int NX, int NU>
 __global__ void __launch_bounds__(kLeafThreads)
 k_fwd_leaf_up(FwdLoader<NX, NU> ld, Geom g, double* __restrict__ fincl, size_t fistride,
-              double* __restrict__ fagg1, size_t fa1stride) {
+              double* __restrict__ fagg1, size_t fa1stride, Hier h) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -935,13 +1255,19 @@ k_fwd_leaf_up(FwdLoader<NX, NU> ld, Geom g, double* __restrict__ fincl, size_t f
     warp_scan<AffOp<NX>>(fa, reinterpret_cast<double*>(w.stage0), lane, false);
     soa_store(fa, fincl, fistride, (size_t)L.slot);
     if (lane == 31) soa_store(fa, fagg1, fa1stride, (size_t)L.b * g.nW + L.wi);
+    if (h.cnt != nullptr) {
+        __syncwarp();
+        hier_finish<AffOp<NX>>(h, g.nW, g.batch, fagg1, fa1stride, L.b, L.wi, lane, reinterpret_cast<double*>(w.stage0),
+                               SideJobs{});
+    }
 }
 
 // ------------------------------------------------------------------ K1 (generic affine scan) leaves
 template <int NX>
 __global__ void __launch_bounds__(kLeafThreads)
 k_aff_leaf_up(AffLoader<NX> ld, int reverse, int transpose, Geom g, double* __restrict__ incl, size_t istride,
-              double* __restrict__ agg1, size_t a1stride) {
+              double* __restrict__ agg1, size_t a1stride, Hier h, SideJobs side, const double* __restrict__ sq_src,
+              int sq_width, double* __restrict__ sq_part) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -956,21 +1282,36 @@ k_aff_leaf_up(AffLoader<NX> ld, int reverse, int transpose, Geom g, double* __re
                                [&](int) { AffOp<NX>::compose(a, a, se); });
     warp_scan<AffOp<NX>>(a, reinterpret_cast<double*>(w.stage0), lane, reverse != 0);
     soa_store(a, incl, istride, (size_t)L.slot);
-    if (reverse) {
-        if (lane == 0) soa_store(a, agg1, a1stride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
-    } else {
-        if (lane == 31) soa_store(a, agg1, a1stride, (size_t)L.b * g.nW + L.wi);
+    const int sidx = reverse ? g.nW - 1 - L.wi : L.wi;   // index of this warp in scan order
+    if (lane == (reverse ? 0 : 31)) soa_store(a, agg1, a1stride, (size_t)L.b * g.nW + sidx);
+    if (sq_part != nullptr) {   // side job: sum of squares of this warp's rows of `sq_src` (||cu||_F, ref :116)
+        const double* cp = sq_src + (size_t)L.t0 * sq_width;
+        const int n = L.len * sq_width;
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double v = __ldg(cp + i);
+            acc += v * v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) sq_part[(size_t)L.b * g.nW + sidx] = acc;
+        if (h.cnt == nullptr && g.nW == 1 && lane == 0) side.cu_norm[L.b] = sqrt(acc);
+    }
+    if (h.cnt != nullptr) {
+        __syncwarp();
+        hier_finish<AffOp<NX>>(h, g.nW, g.batch, agg1, a1stride, L.b, sidx, lane, reinterpret_cast<double*>(w.stage0), side);
     }
 }
 
 template <int NX>
 __global__ void __launch_bounds__(kLeafThreads)
 k_aff_leaf_down(AffLoader<NX> ld, int reverse, int transpose, Geom g, const double* __restrict__ incl,
-                size_t istride, const double* __restrict__ wvals, size_t wvstride, double* __restrict__ out) {
+                size_t istride, const double* __restrict__ wvals, size_t wvstride, double* __restrict__ out, HierIn hin) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
-    if (wg >= total_warps(g)) return;
+    // reverse grid order relative to the up-sweep: start with what it left in L2
+    const long long wg = total_warps(g) - 1 - ((long long)blockIdx.x * (blockDim.x >> 5) + wib);
+    if (wg < 0) return;
     const Lane L = lane_info(g, wg, lane);
     const WarpSmem w = warp_smem(smem, g, wib, wg);
     const int N = g.N;
@@ -978,14 +1319,16 @@ k_aff_leaf_down(AffLoader<NX> ld, int reverse, int transpose, Geom g, const doub
     if (g.per_lane) {
         soa_load(x, wvals, wvstride, (size_t)L.b);
     } else if (reverse) {
-        soa_load(x, wvals, wvstride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
+        if (hin.on) hier_enter<AffOp<NX>>(x, hin, g.nW, L.b, g.nW - 1 - L.wi);
+        else soa_load(x, wvals, wvstride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
         if (lane < 31) {
             AffElem<NX> ex;
             soa_load(ex, incl, istride, (size_t)L.slot + 1);
             AffOp<NX>::apply(x, ex, x);
         }
     } else {
-        soa_load(x, wvals, wvstride, (size_t)L.b * g.nW + L.wi);
+        if (hin.on) hier_enter<AffOp<NX>>(x, hin, g.nW, L.b, L.wi);
+        else soa_load(x, wvals, wvstride, (size_t)L.b * g.nW + L.wi);
         if (lane > 0) {
             AffElem<NX> ex;
             soa_load(ex, incl, istride, (size_t)L.slot - 1);
@@ -1030,6 +1373,9 @@ struct Plan {
     int n[MAXLEV];     // aggregates per sequence at level l (n[0] = nW)
     int T[MAXLEV];     // fan-in from level l to l+1
     long long warps, slots;
+    int hier;          // 1: the levels CAN be completed inside the leaf kernels (last arriver), no level kernels
+    int hier_ric;      // 1: ... also those of the Riccati up-sweep (pays only for long horizons, see make_plan)
+    int gw, ngroups, serial_top;
 };
 
 // force_scan: time-sharded mode always wants the segment total, hence at least one level.
@@ -1076,6 +1422,18 @@ static Plan make_plan(int N, int batch, bool force_scan = false, int target_thre
             p.n[p.nlev] = (p.n[p.nlev - 1] + mid - 1) / mid;
             p.nlev++;
         }
+        // default: no level kernels at all.  The legacy multi-kernel levels remain for explicitly tuned
+        // mid/top shapes (tests) and for more groups than one warp can fold (N beyond ~1e8).
+        p.gw = (g_hier.group_warps > 0 && g_hier.group_warps <= 32) ? g_hier.group_warps : 32;
+        p.ngroups = (g.nW + p.gw - 1) / p.gw;
+        p.serial_top = (g_hier.serial_top > 0) ? (g_hier.serial_top > 32 ? 32 : g_hier.serial_top) : 8;
+        p.hier = (g_hier.enabled && g_tune.mid_fanin <= 0 && g_tune.top_max <= 0 && p.ngroups <= 32 * 16 &&
+                  (long long)batch * (p.ngroups + 1) <= kCtrlRegionWords) ? 1 : 0;
+        // Measured (profiles/r02_variants*.log, cartpole nx = 4): for the cheap affine operator the in-kernel
+        // levels win at every size (K1 -6 us at N = 1e4); for the Riccati operator a single-CTA top kernel is
+        // faster until the group scans can hide behind the streaming of later groups (N = 1e5: +13 us,
+        // N = 1e6: -8 us), i.e. from about two dozen groups.  enabled = 2 forces them everywhere (tests).
+        p.hier_ric = (p.hier && (g_hier.enabled == 2 || p.ngroups >= 24)) ? 1 : 0;
     }
     return p;
 }
@@ -1099,9 +1457,14 @@ struct ScanWs {   // workspace of one hierarchical scan
     double* val[MAXLEV];   // val[0] = value entering each warp
     double* seed;
     double* total;
+    // hier mode
+    double *incl1, *agg2, *incl2, *val2;
+    unsigned* cnt;             // control-block region: [batch*ngroups] group counters, [batch] sequence counters
+    double* part;              // per-warp partials of a side job (batch*nW)
+    int* ipart;
 };
 
-static void carve_scan(Bump& bp, const Plan& p, int esz, int vsz, ScanWs& w) {
+static void carve_scan(Bump& bp, const Plan& p, int esz, int vsz, ScanWs& w, int ctrl_region = 0) {
     w.incl = bp.take<double>((size_t)esz * p.slots);
     for (int l = 0; l < p.nlev; ++l) {
         w.agg[l] = bp.take<double>((size_t)esz * p.g.batch * p.n[l]);
@@ -1113,6 +1476,63 @@ static void carve_scan(Bump& bp, const Plan& p, int esz, int vsz, ScanWs& w) {
     }
     w.seed = bp.take<double>((size_t)vsz * p.g.batch);
     w.total = bp.take<double>((size_t)esz * p.g.batch);
+    w.incl1 = w.agg2 = w.incl2 = w.val2 = w.part = nullptr;
+    w.cnt = nullptr;
+    w.ipart = nullptr;
+    if (p.nlev > 0) {   // carved whether or not the plan uses them: the size must not depend on the knobs' history
+        const size_t ng = (size_t)p.g.batch * p.ngroups;
+        w.incl1 = bp.take<double>((size_t)esz * p.g.batch * p.g.nW);
+        w.agg2 = bp.take<double>((size_t)esz * ng);
+        w.incl2 = bp.take<double>((size_t)esz * ng);
+        w.val2 = bp.take<double>((size_t)vsz * ng);
+    }
+    w.cnt = bp.dry ? nullptr : reinterpret_cast<unsigned*>(bp.base) + (size_t)ctrl_region * kCtrlRegionWords;
+    w.part = bp.take<double>((size_t)p.g.batch * p.g.nW);
+    w.ipart = bp.take<int>((size_t)p.g.batch * p.g.nW);
+}
+
+template <class Op>
+static Hier make_hier(const Plan& p, const ScanWs& w, const double* seed, double* total) {
+    Hier h{};
+    if (!p.hier) return h;
+    h.cnt = w.cnt;
+    h.gw = p.gw;
+    h.ngroups = p.ngroups;
+    h.serial_top = p.serial_top;
+    h.incl1 = w.incl1;
+    h.s1 = (size_t)p.g.batch * p.g.nW;
+    h.agg2 = w.agg2;
+    h.incl2 = w.incl2;
+    h.val2 = w.val2;
+    h.s2 = (size_t)p.g.batch * p.ngroups;
+    h.seed = seed;
+    h.total = total;
+    return h;
+}
+static HierIn make_hier_in(const Plan& p, const ScanWs& w) {
+    HierIn h{};
+    if (!p.hier) return h;
+    h.on = 1;
+    h.gw = p.gw;
+    h.ngroups = p.ngroups;
+    h.incl1 = w.incl1;
+    h.s1 = (size_t)p.g.batch * p.g.nW;
+    h.val2 = w.val2;
+    h.incl2 = w.incl2;
+    h.s2 = (size_t)p.g.batch * p.ngroups;
+    return h;
+}
+// time-sharded phase 2: the seed is chained through the other ranks' aggregates inside the down-sweep
+static HierIn make_hier_chain(const Plan& p, const ScanWs& w, const double* carries, int first, int step, int count,
+                              const double* seed0) {
+    HierIn h = make_hier_in(p, w);
+    h.val2 = nullptr;
+    h.carries = carries;
+    h.chain_first = first;
+    h.chain_step = step;
+    h.chain_count = count;
+    h.seed0 = seed0;
+    return h;
 }
 
 struct NewtonWs {
@@ -1125,7 +1545,7 @@ struct NewtonWs {
 template <int NX>
 static void carve_newton(Bump& bp, const Plan& p, NewtonWs& w) {
     carve_scan(bp, p, RicElem<NX>::ESZ, RicVal<NX>::VSZ, w.ric);
-    carve_scan(bp, p, AffElem<NX>::ESZ, NX, w.aff);
+    carve_scan(bp, p, AffElem<NX>::ESZ, NX, w.aff, 1);
     w.pred_part = bp.take<double>((size_t)p.warps);
     w.feas_part = bp.take<int>((size_t)p.warps);
     w.scratch = bp.take<double>(256);
@@ -1225,7 +1645,7 @@ static int top_prepare(int threads) {
 // total aggregate of each sequence is produced (w.total, SoA stride batch).
 template <class Op>
 static int run_levels(const Plan& p, const ScanWs& w, bool want_total, bool reduce_only, cudaStream_t st,
-                      PredJob pj = PredJob{nullptr, nullptr, 0, nullptr, nullptr}) {
+                      SideJobs pj = SideJobs{}) {
     const int L = p.nlev, batch = p.g.batch;
     for (int l = 0; l + 1 < L; ++l) {
         const long long cnt = (long long)batch * p.n[l + 1];
@@ -1265,23 +1685,24 @@ static void leaf_values(const Plan& p, const ScanWs& w, const double*& vals, siz
 
 // ---- K2 (+K3 aggregates) for any loader ---------------------------------------------------
 template <int NX, int NU, class Loader>
-static int run_bwd_up(const Plan& p, const NewtonWs& w, const Loader& ld, cudaStream_t st,
-                      SeedJob sj = SeedJob{nullptr, 0, nullptr, 0, nullptr, nullptr}) {
+static int run_bwd_up(const Plan& p, const NewtonWs& w, const Loader& ld, cudaStream_t st, SeedJob sj, const Hier& h,
+                      const SideJobs& side, double* mx_part) {
     const LeafLaunch ll = leaf_launch(p, Loader::STAGE_BYTES, scan_scratch_bytes<RicOp<NX>>(), IPOC_NS_RIC_UP);
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_ric_leaf_up<NX, NU, Loader>;
     if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.ric.incl, (size_t)p.slots, w.ric.agg[0],
-                                              (size_t)p.g.batch * p.g.nW, sj);
+                                              (size_t)p.g.batch * p.g.nW, sj, h, side, mx_part);
     IPOC_LAUNCH_CHECK_N("k_ric_leaf_up", st);
     return IPOC_OK;
 }
 
+// hin: how the value entering each warp is obtained; hf: in-kernel levels of the forward aggregates (K3)
 template <int NX, int NU, class Loader>
 static int run_bwd_down(const Plan& p, const NewtonWs& w, const Loader& ld, double* Kx, double* d, double* S,
                         double* v, double* pred, int32_t* feasible, bool want_fwd_agg, cudaStream_t st,
-                        bool defer_pred = false) {
+                        bool defer_pred, const HierIn& hin, const Hier& hf) {
     const double* vals;
     size_t vstride;
     leaf_values(p, w.ric, vals, vstride);
@@ -1291,38 +1712,70 @@ static int run_bwd_down(const Plan& p, const NewtonWs& w, const Loader& ld, doub
     auto kern = k_ric_leaf_down<NX, NU, Loader>;
     if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     const bool fwd = want_fwd_agg && !p.g.per_lane;
+    SideJobs side{};
+    const bool fold_here = fwd && hf.cnt != nullptr;   // the warp completing K3's levels also folds pred / feasible
+    if (fold_here) {
+        side.n = p.g.nW;
+        side.pred_part = w.pred_part;
+        side.feas_part = w.feas_part;
+        side.pred = pred;
+        side.feasible = feasible;
+    }
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.ric.incl, (size_t)p.slots, vals, vstride, Kx, d, S, v,
                                               w.pred_part, w.feas_part, pred, feasible, fwd ? w.aff.incl : nullptr,
                                               (size_t)p.slots, fwd ? w.aff.agg[0] : nullptr,
-                                              (size_t)p.g.batch * p.g.nW);
+                                              (size_t)p.g.batch * p.g.nW, hin, hf, side);
     IPOC_LAUNCH_CHECK_N("k_ric_leaf_down", st);
-    if (!p.g.per_lane && !defer_pred) {
-        k_finalize_pred<<<p.g.batch, 32, 0, st>>>(PredJob{w.pred_part, w.feas_part, p.g.nW, pred, feasible});
+    if (!p.g.per_lane && !defer_pred && !fold_here) {
+        SideJobs fin{};
+        fin.n = p.g.nW;
+        fin.pred_part = w.pred_part;
+        fin.feas_part = w.feas_part;
+        fin.pred = pred;
+        fin.feasible = feasible;
+        k_finalize_pred<<<p.g.batch, 32, 0, st>>>(fin);
         IPOC_LAUNCH_CHECK_N("k_finalize_pred", st);
     }
     return IPOC_OK;
 }
 
+// Whole backward pass.  `xtra` (may be NULL) carries the max|ru| side job.
 template <int NX, int NU, class Loader>
 static int run_bwd(const Plan& p, const NewtonWs& w, const Loader& ld, double* Kx, double* d, double* S, double* v,
-                   double* pred, int32_t* feasible, bool want_fwd_agg, cudaStream_t st, bool defer_pred, SeedJob sj) {
+                   double* pred, int32_t* feasible, bool want_fwd_agg, cudaStream_t st, bool defer_pred, SeedJob sj,
+                   AttemptExtras* xtra) {
+    Hier hup{}, hf{};
+    HierIn hin{};
     if (p.g.per_lane) {   // no up-sweep to piggy-back on
         k_ric_seed<NX><<<grid_for(sj.batch, 128), 128, 0, st>>>(sj);
         IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
     } else {
-        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st, sj)) return rc;
-        if (p.nlev > 0)
-            if (int rc = run_levels<RicOp<NX>>(p, w.ric, false, false, st)) return rc;
+        SideJobs side{};
+        double* mx_part = nullptr;
+        if (xtra != nullptr && xtra->hu != nullptr) {   // folded by whoever completes the levels (in-kernel or k_top)
+            side.n = p.g.nW;
+            side.mx_part = mx_part = w.ric.part;
+            side.hu = xtra->hu;
+            xtra->handled |= IPOC_X_HU;
+        }
+        if (p.hier_ric) {
+            hup = make_hier<RicOp<NX>>(p, w.ric, w.ric.seed, nullptr);
+            hin = make_hier_in(p, w.ric);
+        }
+        if (p.hier && want_fwd_agg) hf = make_hier<AffOp<NX>>(p, w.aff, w.aff.seed, nullptr);
+        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st, sj, hup, side, mx_part)) return rc;
+        if (p.nlev > 0 && !p.hier_ric)
+            if (int rc = run_levels<RicOp<NX>>(p, w.ric, false, false, st, side)) return rc;
     }
-    return run_bwd_down<NX, NU>(p, w, ld, Kx, d, S, v, pred, feasible, want_fwd_agg, st, defer_pred);
+    return run_bwd_down<NX, NU>(p, w, ld, Kx, d, S, v, pred, feasible, want_fwd_agg, st, defer_pred, hin, hf);
 }
 
 // ---- K3 given in-warp forward aggregates in w.aff.incl / w.aff.agg[0] and the seed in w.aff.seed
 template <int NX, int NU>
 static int run_fwd_down(const Plan& p, const NewtonWs& w, const double* A, const double* B, const double* c,
                         const double* Kx, const double* d, double* x, double* u, bool levels, cudaStream_t st,
-                        PredJob pj = PredJob{nullptr, nullptr, 0, nullptr, nullptr}) {
-    if (levels && p.nlev > 0)
+                        SideJobs pj, const HierIn& hin, const TailJob& tail) {
+    if (levels && p.nlev > 0 && !hin.on)
         if (int rc = run_levels<AffOp<NX>>(p, w.aff, false, false, st, pj)) return rc;
     const double* vals;
     size_t vstride;
@@ -1333,35 +1786,85 @@ static int run_fwd_down(const Plan& p, const NewtonWs& w, const double* A, const
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_fwd_leaf_down<NX, NU>;
     if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
-    kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.aff.incl, (size_t)p.slots, vals, vstride, x, u);
+    kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.aff.incl, (size_t)p.slots, vals, vstride, x, u, hin, tail);
     IPOC_LAUNCH_CHECK_N("k_fwd_leaf_down", st);
     return IPOC_OK;
+}
+
+static TailJob make_tail(const Plan& p, const NewtonWs& w, void* ws, AttemptExtras* x, const double* pred,
+                         const int32_t* bwd_feasible) {
+    TailJob t{};
+    if (x == nullptr) return t;
+    if (x->tx != nullptr) {   // the trial point needs no fold: any plan
+        t.x = x->x;
+        t.u = x->u;
+        t.tx = x->tx;
+        t.tu = x->tu;
+        t.trial_mask = x->active;
+        x->handled |= IPOC_X_TRIAL;
+    }
+    if (p.g.per_lane || (p.g.nW > 1 && p.g.batch > kCtrlRegionWords)) return t;   // folds need one counter per sequence
+    if (x->cons == nullptr && x->rp == nullptr) return t;
+    t.cnt = reinterpret_cast<unsigned*>(ws) + 2 * (size_t)kCtrlRegionWords;
+    if (x->cons != nullptr) {
+        t.cons = x->cons;
+        t.nc = x->nc;
+        t.cons_part = w.aff.ipart;
+        t.traj_feasible = x->traj_feasible;
+        x->handled |= IPOC_X_CONS;
+    }
+    if (x->rp != nullptr) {
+        t.cost = x->cost;
+        t.new_cost = x->new_cost;
+        t.traj_feas_in = x->traj_feas_in;
+        t.pred = pred;
+        t.bwd_feasible = bwd_feasible;
+        t.active = x->active;
+        t.rp = x->rp;
+        t.r_inc = x->r_inc;
+        t.success = x->success;
+        t.gain = x->gain;
+        x->handled |= IPOC_X_ACCEPT;
+    }
+    return t;
 }
 
 template <int NX, int NU>
 static int newton_step_impl(int N, int batch, const double* fx, const double* fu, const double* ru, const double* Q,
                             const double* R, const double* M, const double* reg, double* dx, double* du, double* Kx,
-                            double* d, double* pred, int32_t* feasible, void* ws, size_t ws_bytes, cudaStream_t st) {
+                            double* d, double* pred, int32_t* feasible, void* ws, size_t ws_bytes, cudaStream_t st,
+                            AttemptExtras* xtra) {
     const Plan p = make_plan(N, batch);
-    Bump bp{(char*)ws, 0, ws_bytes, false};
+    Bump bp{(char*)ws, (size_t)kCtrlBytes, ws_bytes, false};
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     // terminal value function: XT = Q[0], HT = I, rT = 0 (ref noc/par_interior_point_newton.py:73-75);
-    // zero initial deviation dx_0 = 0 (:122) — both seeds in one launch
+    // zero initial deviation dx_0 = 0 (:122) — both seeds as a side job of the up-sweep
     const SeedJob sj{Q, (size_t)N * NX * NX, nullptr, batch, w.ric.seed, w.aff.seed};
-    // the pred / feasibility partials are folded by K3's top scan when there is one
-    const bool defer = p.nlev > 0;
+    // legacy levels: the pred / feasibility partials are folded by K3's top scan when there is one
+    const bool defer = p.nlev > 0 && !p.hier;
+    const double* reg_scale = xtra != nullptr ? xtra->reg_scale : nullptr;
     if (g_literal_lqt) {
-        NewtonLoader<NX, NU, true> ld{fx, fu, ru, Q, R, M, reg};
-        if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer, sj)) return rc;
+        NewtonLoader<NX, NU, true> ld{fx, fu, ru, Q, R, M, reg, reg_scale};
+        if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer, sj, xtra))
+            return rc;
     } else {
-        NewtonLoader<NX, NU, false> ld{fx, fu, ru, Q, R, M, reg};
-        if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer, sj)) return rc;
+        NewtonLoader<NX, NU, false> ld{fx, fu, ru, Q, R, M, reg, reg_scale};
+        if (int rc = run_bwd<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, defer, sj, xtra))
+            return rc;
     }
-    PredJob pj{nullptr, nullptr, 0, nullptr, nullptr};
-    if (defer) pj = PredJob{w.pred_part, w.feas_part, p.g.nW, pred, feasible};
-    return run_fwd_down<NX, NU>(p, w, fx, fu, nullptr, Kx, d, dx, du, true, st, pj);
+    SideJobs pj{};
+    if (defer) {
+        pj.n = p.g.nW;
+        pj.pred_part = w.pred_part;
+        pj.feas_part = w.feas_part;
+        pj.pred = pred;
+        pj.feasible = feasible;
+    }
+    const HierIn hin = make_hier_in(p, w.aff);
+    const TailJob tail = make_tail(p, w, ws, xtra, pred, feasible);
+    return run_fwd_down<NX, NU>(p, w, fx, fu, nullptr, Kx, d, dx, du, true, st, pj, hin, tail);
 }
 
 template <int NX, int NU>
@@ -1370,18 +1873,18 @@ static int lqt_bwd_impl(int N, int batch, const double* A, const double* B, cons
                         const double* vT, double* Kx, double* d, double* S, double* v, double* pred,
                         int32_t* feasible, void* ws, size_t ws_bytes, cudaStream_t st) {
     const Plan p = make_plan(N, batch);
-    Bump bp{(char*)ws, 0, ws_bytes, false};
+    Bump bp{(char*)ws, (size_t)kCtrlBytes, ws_bytes, false};
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     const SeedJob sj{ST, (size_t)NX * NX, vT, batch, w.ric.seed, nullptr};
     LqtLoader<NX, NU> ld{A, B, c, X, U, M, q, pp};
-    return run_bwd<NX, NU>(p, w, ld, Kx, d, S, v, pred, feasible, false, st, false, sj);
+    return run_bwd<NX, NU>(p, w, ld, Kx, d, S, v, pred, feasible, false, st, false, sj, nullptr);
 }
 
 template <int NX, int NU>
 static int run_fwd_up(const Plan& p, const NewtonWs& w, const double* A, const double* B, const double* c,
-                      const double* Kx, const double* d, cudaStream_t st) {
+                      const double* Kx, const double* d, cudaStream_t st, const Hier& h) {
     FwdLoader<NX, NU> ld{A, B, c, Kx, d};
     const LeafLaunch ll = leaf_launch(p, FwdLoader<NX, NU>::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>(), IPOC_NS_LIGHT);
     Geom g = p.g;
@@ -1389,7 +1892,7 @@ static int run_fwd_up(const Plan& p, const NewtonWs& w, const double* A, const d
     auto kern = k_fwd_leaf_up<NX, NU>;
     if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, g, w.aff.incl, (size_t)p.slots, w.aff.agg[0],
-                                              (size_t)p.g.batch * p.g.nW);
+                                              (size_t)p.g.batch * p.g.nW, h);
     IPOC_LAUNCH_CHECK_N("k_fwd_leaf_up", st);
     return IPOC_OK;
 }
@@ -1399,34 +1902,44 @@ static int lqt_fwd_impl(int N, int batch, const double* A, const double* B, cons
                         const double* d, const double* x0, double* u, double* x, void* ws, size_t ws_bytes,
                         cudaStream_t st) {
     const Plan p = make_plan(N, batch);
-    Bump bp{(char*)ws, 0, ws_bytes, false};
+    Bump bp{(char*)ws, (size_t)kCtrlBytes, ws_bytes, false};
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(x0, batch, w.aff.seed);
     IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
+    const Hier h = make_hier<AffOp<NX>>(p, w.aff, w.aff.seed, nullptr);
     if (!p.g.per_lane)
-        if (int rc = run_fwd_up<NX, NU>(p, w, A, B, c, Kx, d, st)) return rc;
-    return run_fwd_down<NX, NU>(p, w, A, B, c, Kx, d, x, u, true, st);
+        if (int rc = run_fwd_up<NX, NU>(p, w, A, B, c, Kx, d, st, h)) return rc;
+    return run_fwd_down<NX, NU>(p, w, A, B, c, Kx, d, x, u, true, st, SideJobs{}, make_hier_in(p, w.aff), TailJob{});
 }
 
+// sq_src (batch, N, sq_width) -> side.cu_norm = ||.||_F per problem, folded into the up-sweep (may be NULL)
 template <int NX>
 static int aff_up(const Plan& p, const ScanWs& w, const double* F, const double* c, int reverse, int transpose,
-                  cudaStream_t st) {
+                  cudaStream_t st, const Hier& h, const double* sq_src = nullptr, int sq_width = 0,
+                  double* cu_norm = nullptr) {
     AffLoader<NX> ld{F, c};
     const LeafLaunch ll = leaf_launch(p, AffLoader<NX>::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>(), IPOC_NS_LIGHT);
     Geom g = p.g;
     g.pw_bytes = (int)(ll.smem / ll.wpc);
     auto kern = k_aff_leaf_up<NX>;
     if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
+    SideJobs side{};
+    double* sq_part = nullptr;
+    if (sq_src != nullptr) {
+        side.n = p.g.nW;
+        side.sq_part = sq_part = w.part;
+        side.cu_norm = cu_norm;
+    }
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, reverse, transpose, g, w.incl, (size_t)p.slots, w.agg[0],
-                                              (size_t)p.g.batch * p.g.nW);
+                                              (size_t)p.g.batch * p.g.nW, h, side, sq_src, sq_width, sq_part);
     IPOC_LAUNCH_CHECK_N("k_aff_leaf_up", st);
     return IPOC_OK;
 }
 template <int NX>
 static int aff_down(const Plan& p, const ScanWs& w, const double* F, const double* c, int reverse, int transpose,
-                    double* out, cudaStream_t st) {
+                    double* out, cudaStream_t st, const HierIn& hin) {
     const double* vals;
     size_t vstride;
     leaf_values(p, w, vals, vstride);
@@ -1437,16 +1950,18 @@ static int aff_down(const Plan& p, const ScanWs& w, const double* F, const doubl
     auto kern = k_aff_leaf_down<NX>;
     if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, reverse, transpose, g, w.incl, (size_t)p.slots, vals, vstride,
-                                              out);
+                                              out, hin);
     IPOC_LAUNCH_CHECK_N("k_aff_leaf_down", st);
     return IPOC_OK;
 }
 
+// `sq_src`/`cu_norm`: optional ||cu||_F side job; *handled tells the caller whether the scan took it
 template <int NX>
 static int affine_scan_impl(int reverse, int transpose, int N, int batch, const double* F, const double* c,
-                            const double* seed, double* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                            const double* seed, double* out, void* ws, size_t ws_bytes, cudaStream_t st,
+                            const double* sq_src, int sq_width, double* cu_norm, int* handled) {
     const Plan p = make_plan(N, batch, false, kAffTargetThreads);
-    Bump bp{(char*)ws, 0, ws_bytes, false};
+    Bump bp{(char*)ws, (size_t)kCtrlBytes, ws_bytes, false};
     ScanWs w;
     carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
@@ -1456,33 +1971,54 @@ static int affine_scan_impl(int reverse, int transpose, int N, int batch, const 
         k_aff_seed<NX><<<grid_for(batch, 128), 128, 0, st>>>(seed, batch, w.seed);
         IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
     }
+    HierIn hin{};
     if (!p.g.per_lane) {
-        if (int rc = aff_up<NX>(p, w, F, c, reverse, transpose, st)) return rc;
-        if (p.nlev > 0)
-            if (int rc = run_levels<AffOp<NX>>(p, w, false, false, st)) return rc;
+        const Hier h = make_hier<AffOp<NX>>(p, w, w.seed, nullptr);
+        hin = make_hier_in(p, w);
+        const bool fold = sq_src != nullptr;
+        if (fold && handled != nullptr) *handled |= IPOC_X_NORM;
+        if (int rc = aff_up<NX>(p, w, F, c, reverse, transpose, st, h, fold ? sq_src : nullptr, sq_width, cu_norm))
+            return rc;
+        if (p.nlev > 0 && !p.hier) {
+            SideJobs side{};
+            if (fold) {
+                side.n = p.g.nW;
+                side.sq_part = w.part;
+                side.cu_norm = cu_norm;
+            }
+            if (int rc = run_levels<AffOp<NX>>(p, w, false, false, st, side)) return rc;
+        }
     }
-    return aff_down<NX>(p, w, F, c, reverse, transpose, out, st);
+    return aff_down<NX>(p, w, F, c, reverse, transpose, out, st, hin);
 }
 
 // ---- time-sharded split-phase implementations ----------------------------------------------
 // The reduce phase leaves the in-warp aggregates and the level arrays in the workspace; the apply
-// phase (same workspace, same plan) only runs the seeded way down.
+// phase (same workspace, same plan) only runs the seeded way down.  With the in-kernel levels a phase is
+// ONE launch: the reduce phase ends with the composition of the whole segment (written straight into
+// `carry_out`), the apply phase pushes the horizon's seed through the other ranks' aggregates inside the
+// down-sweep (hier_enter, chain mode).
 template <int NX, int NU>
 static int newton_bwd_reduce_impl(int N, const double* fx, const double* fu, const double* ru, const double* Q,
                                   const double* R, const double* M, const double* reg, double* carry_out, void* ws,
                                   size_t ws_bytes, cudaStream_t st) {
     const Plan p = make_plan(N, 1, true);
-    Bump bp{(char*)ws, 0, ws_bytes, false};
+    Bump bp{(char*)ws, (size_t)kCtrlBytes, ws_bytes, false};
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
+    const bool split_hier = p.hier && p.ngroups <= 32;
+    Hier h{};
+    if (split_hier) h = make_hier<RicOp<NX>>(p, w.ric, nullptr, carry_out);   // batch = 1: SoA == AoS
+    const SeedJob nosj{nullptr, 0, nullptr, 0, nullptr, nullptr};
     if (g_literal_lqt) {
-        NewtonLoader<NX, NU, true> ld{fx, fu, ru, Q, R, M, reg};
-        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st)) return rc;
+        NewtonLoader<NX, NU, true> ld{fx, fu, ru, Q, R, M, reg, nullptr};
+        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st, nosj, h, SideJobs{}, nullptr)) return rc;
     } else {
-        NewtonLoader<NX, NU, false> ld{fx, fu, ru, Q, R, M, reg};
-        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st)) return rc;
+        NewtonLoader<NX, NU, false> ld{fx, fu, ru, Q, R, M, reg, nullptr};
+        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st, nosj, h, SideJobs{}, nullptr)) return rc;
     }
+    if (split_hier) return IPOC_OK;
     if (int rc = run_levels<RicOp<NX>>(p, w.ric, true, true, st)) return rc;
     k_soa_to_aos<<<1, 256, 0, st>>>(w.ric.total, 1, 0, RicElem<NX>::ESZ, carry_out);
     IPOC_LAUNCH_CHECK_N("k_soa_to_aos", st);
@@ -1496,8 +2032,7 @@ static int run_levels_down(const Plan& p, const ScanWs& w, cudaStream_t st) {
     const int tt = top_threads<Op>(p.n[L - 1]);
     if (int rc = top_prepare<Op>(tt)) return rc;
     k_top<Op><<<1, tt, top_smem<Op>(tt), st>>>(w.agg[L - 1], (size_t)p.n[L - 1], p.n[L - 1], 1, w.seed,
-                                               w.val[L - 1], (size_t)p.n[L - 1], nullptr, 0,
-                                               PredJob{nullptr, nullptr, 0, nullptr, nullptr});
+                                               w.val[L - 1], (size_t)p.n[L - 1], nullptr, 0, SideJobs{});
     IPOC_LAUNCH_CHECK_N(Op::tag_top, st);
     for (int l = L - 2; l >= 0; --l) {
         k_mid_down<Op><<<grid_for(p.n[l + 1], kMidThreads), kMidThreads, 0, st>>>(
@@ -1515,7 +2050,7 @@ static int newton_bwd_apply_impl(int N, int rank, int nranks, const double* fx, 
                                  int32_t* feasible, double* fwd_carry_out, void* ws, size_t ws_bytes,
                                  cudaStream_t st) {
     const Plan p = make_plan(N, 1, true);
-    Bump bp{(char*)ws, 0, ws_bytes, false};
+    Bump bp{(char*)ws, (size_t)kCtrlBytes, ws_bytes, false};
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
@@ -1523,16 +2058,27 @@ static int newton_bwd_apply_impl(int N, int rank, int nranks, const double* fx, 
     double* seed0 = w.scratch;   // RicVal packed
     k_ric_seed<NX><<<1, 32, 0, st>>>(SeedJob{ST, (size_t)NX * NX, nullptr, 1, seed0, nullptr});
     IPOC_LAUNCH_CHECK_N("k_ric_seed", st);
-    k_chain_seed<RicOp<NX>><<<1, 32, 0, st>>>(carries, nranks - 1, -1, nranks - 1 - rank, seed0, w.ric.seed);
-    IPOC_LAUNCH_CHECK_N("k_chain_seed_ric", st);
-    if (int rc = run_levels_down<RicOp<NX>>(p, w.ric, st)) return rc;
-    if (g_literal_lqt) {
-        NewtonLoader<NX, NU, true> ld{fx, fu, ru, Q, R, M, reg};
-        if (int rc = run_bwd_down<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st)) return rc;
+    const bool split_hier = p.hier && p.ngroups <= 32;
+    HierIn hin{};
+    Hier hf{};
+    if (split_hier) {
+        hin = make_hier_chain(p, w.ric, carries, nranks - 1, -1, nranks - 1 - rank, seed0);
+        hf = make_hier<AffOp<NX>>(p, w.aff, nullptr, fwd_carry_out);
     } else {
-        NewtonLoader<NX, NU, false> ld{fx, fu, ru, Q, R, M, reg};
-        if (int rc = run_bwd_down<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st)) return rc;
+        k_chain_seed<RicOp<NX>><<<1, 32, 0, st>>>(carries, nranks - 1, -1, nranks - 1 - rank, seed0, w.ric.seed);
+        IPOC_LAUNCH_CHECK_N("k_chain_seed_ric", st);
+        if (int rc = run_levels_down<RicOp<NX>>(p, w.ric, st)) return rc;
     }
+    if (g_literal_lqt) {
+        NewtonLoader<NX, NU, true> ld{fx, fu, ru, Q, R, M, reg, nullptr};
+        if (int rc = run_bwd_down<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, false, hin, hf))
+            return rc;
+    } else {
+        NewtonLoader<NX, NU, false> ld{fx, fu, ru, Q, R, M, reg, nullptr};
+        if (int rc = run_bwd_down<NX, NU>(p, w, ld, Kx, d, nullptr, nullptr, pred, feasible, true, st, false, hin, hf))
+            return rc;
+    }
+    if (split_hier) return IPOC_OK;
     if (int rc = run_levels<AffOp<NX>>(p, w.aff, true, true, st)) return rc;
     k_soa_to_aos<<<1, 256, 0, st>>>(w.aff.total, 1, 0, AffElem<NX>::ESZ, fwd_carry_out);
     IPOC_LAUNCH_CHECK_N("k_soa_to_aos", st);
@@ -1544,28 +2090,37 @@ static int newton_fwd_apply_impl(int N, int rank, int nranks, const double* fx, 
                                  const double* d, const double* fwd_carries, double* dx, double* du, void* ws,
                                  size_t ws_bytes, cudaStream_t st) {
     const Plan p = make_plan(N, 1, true);
-    Bump bp{(char*)ws, 0, ws_bytes, false};
+    Bump bp{(char*)ws, (size_t)kCtrlBytes, ws_bytes, false};
     NewtonWs w;
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
+    const SideJobs nopj{};
+    if (p.hier && p.ngroups <= 32) {   // dx_0 = 0 chained through the earlier ranks' aggregates in the leaf kernel
+        const HierIn hin = make_hier_chain(p, w.aff, fwd_carries, 0, +1, rank, nullptr);
+        return run_fwd_down<NX, NU>(p, w, fx, fu, nullptr, Kx, d, dx, du, false, st, nopj, hin, TailJob{});
+    }
     double* seed0 = w.scratch;
     k_aff_seed<NX><<<1, 32, 0, st>>>(nullptr, 1, seed0);
     IPOC_LAUNCH_CHECK_N("k_aff_seed", st);
     k_chain_seed<AffOp<NX>><<<1, 32, 0, st>>>(fwd_carries, 0, +1, rank, seed0, w.aff.seed);
     IPOC_LAUNCH_CHECK_N("k_chain_seed_aff", st);
     if (int rc = run_levels_down<AffOp<NX>>(p, w.aff, st)) return rc;
-    return run_fwd_down<NX, NU>(p, w, fx, fu, nullptr, Kx, d, dx, du, false, st);
+    return run_fwd_down<NX, NU>(p, w, fx, fu, nullptr, Kx, d, dx, du, false, st, nopj, HierIn{}, TailJob{});
 }
 
 template <int NX>
 static int affine_reduce_impl(int reverse, int transpose, int N, const double* F, const double* c, double* carry_out,
                               void* ws, size_t ws_bytes, cudaStream_t st) {
     const Plan p = make_plan(N, 1, true);
-    Bump bp{(char*)ws, 0, ws_bytes, false};
+    Bump bp{(char*)ws, (size_t)kCtrlBytes, ws_bytes, false};
     ScanWs w;
     carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
-    if (int rc = aff_up<NX>(p, w, F, c, reverse, transpose, st)) return rc;
+    if (p.hier && p.ngroups <= 32) {
+        const Hier h = make_hier<AffOp<NX>>(p, w, nullptr, carry_out);
+        return aff_up<NX>(p, w, F, c, reverse, transpose, st, h);
+    }
+    if (int rc = aff_up<NX>(p, w, F, c, reverse, transpose, st, Hier{})) return rc;
     if (int rc = run_levels<AffOp<NX>>(p, w, true, true, st)) return rc;
     k_soa_to_aos<<<1, 256, 0, st>>>(w.total, 1, 0, AffElem<NX>::ESZ, carry_out);
     IPOC_LAUNCH_CHECK_N("k_soa_to_aos", st);
@@ -1577,25 +2132,30 @@ static int affine_apply_impl(int reverse, int transpose, int N, int rank, int nr
                              const double* c, const double* carries, const double* seed, double* out, void* ws,
                              size_t ws_bytes, cudaStream_t st) {
     const Plan p = make_plan(N, 1, true);
-    Bump bp{(char*)ws, 0, ws_bytes, false};
+    Bump bp{(char*)ws, (size_t)kCtrlBytes, ws_bytes, false};
     ScanWs w;
     carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     using AOp = AffOp<NX>;
+    if (p.hier && p.ngroups <= 32) {
+        const HierIn hin = reverse ? make_hier_chain(p, w, carries, nranks - 1, -1, nranks - 1 - rank, seed)
+                                   : make_hier_chain(p, w, carries, 0, +1, rank, seed);
+        return aff_down<NX>(p, w, F, c, reverse, transpose, out, st, hin);
+    }
     if (reverse)
         k_chain_seed<AOp><<<1, 32, 0, st>>>(carries, nranks - 1, -1, nranks - 1 - rank, seed, w.seed);
     else
         k_chain_seed<AOp><<<1, 32, 0, st>>>(carries, 0, +1, rank, seed, w.seed);
     IPOC_LAUNCH_CHECK_N("k_chain_seed_aff", st);
     if (int rc = run_levels_down<AOp>(p, w, st)) return rc;
-    return aff_down<NX>(p, w, F, c, reverse, transpose, out, st);
+    return aff_down<NX>(p, w, F, c, reverse, transpose, out, st, HierIn{});
 }
 
 template <int NX>
 static size_t ws_bytes_impl(int kind, int N, int batch, bool sharded) {
     const Plan p = make_plan(N, sharded ? 1 : batch, sharded,
                              (kind == IPOC_WS_AFFINE_SCAN && !sharded) ? kAffTargetThreads : kTargetThreads);
-    Bump bp{nullptr, 0, 0, true};
+    Bump bp{nullptr, (size_t)kCtrlBytes, 0, true};
     if (kind == IPOC_WS_AFFINE_SCAN) {
         ScanWs w;
         carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);

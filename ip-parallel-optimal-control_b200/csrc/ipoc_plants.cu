@@ -9,6 +9,7 @@
 #include <stdint.h>
 #include "../../include/ipoc.h"
 #include "ipoc_jet.cuh"
+#include "ipoc_accept.cuh"
 
 namespace ipoc {
 
@@ -257,11 +258,16 @@ k_plant_hamiltonian(PlantParams pp, const double* __restrict__ bp_ptr, int N, in
 template <class P>
 __global__ void __launch_bounds__(1024)
 k_plant_cost(PlantParams pp, const double* __restrict__ bp_ptr, int N, const double* __restrict__ X,
-             const double* __restrict__ U, double* __restrict__ total, int32_t* __restrict__ feasible) {
+             const double* __restrict__ U, double* __restrict__ total, int32_t* __restrict__ feasible, int finish,
+             FinishIO fin) {
     constexpr int NX = P::NX, NU = P::NU;
     __shared__ double s_sum[32];
     __shared__ int s_ok[32];
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (finish && !fin.active[b]) {   // frozen member of a device-resident loop: nothing to evaluate
+        if (t == 0) fin.advanced[b] = 0;
+        return;
+    }
     const double bp = *bp_ptr;
     double acc = 0.0;
     int ok = 1;
@@ -297,8 +303,10 @@ k_plant_cost(PlantParams pp, const double* __restrict__ bp_ptr, int N, const dou
             double xn[NX];
 #pragma unroll
             for (int i = 0; i < NX; ++i) xn[i] = X[((size_t)b * (N + 1) + N) * NX + i];
-            total[b] = P::state_cost(xn) + acc;
+            const double tot = P::state_cost(xn) + acc;
+            total[b] = tot;
             feasible[b] = ok;
+            if (finish) attempt_finish_rule(fin, b, tot, ok);   // accept + loop bookkeeping (ref :159-202)
         }
     }
 }
@@ -365,7 +373,14 @@ static int hamiltonian_impl(PlantParams pp, const double* bp, int N, int batch, 
 template <class P>
 static int cost_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
                      double* total, int32_t* feasible, cudaStream_t st) {
-    k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible);
+    k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, 0, FinishIO{});
+    PLANT_CHECK(st);
+    return IPOC_OK;
+}
+template <class P>
+static int cost_finish_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
+                            double* total, int32_t* feasible, const FinishIO& fin, cudaStream_t st) {
+    k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, 1, fin);
     PLANT_CHECK(st);
     return IPOC_OK;
 }
@@ -433,6 +448,24 @@ int ipoc_plant_cost_f64(int plant, int N, int batch, double Ts, double bound, co
     cudaStream_t st = (cudaStream_t)stream;
     if (plant == IPOC_PLANT_PENDULUM) return cost_impl<Pendulum>(pp, bp, N, batch, x, u, total_cost, feasible, st);
     if (plant == IPOC_PLANT_CARTPOLE) return cost_impl<Cartpole>(pp, bp, N, batch, x, u, total_cost, feasible, st);
+    return IPOC_EINVAL;
+}
+
+int ipoc_plant_attempt_finish_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
+                                  const double* tx, const double* tu, double* new_cost, int32_t* traj_feasible,
+                                  const double* cost, const double* pred, const int32_t* bwd_feasible, const double* hu,
+                                  int32_t* active, double* rp, double* r_inc, int32_t* success, double* gain_ratio,
+                                  int64_t* inner, int64_t* iteration, uint8_t* outer_done, int32_t* advanced,
+                                  double hu_tol, int max_attempts, int max_iterations, ipoc_stream_t stream) {
+    if (N < 1 || batch < 1 || !bp || !tx || !tu || !new_cost || !traj_feasible || !cost || !pred || !bwd_feasible || !hu ||
+        !active || !rp || !r_inc || !success || !inner || !iteration || !outer_done || !advanced)
+        return IPOC_EINVAL;
+    const PlantParams pp{Ts, bound};
+    cudaStream_t st = (cudaStream_t)stream;
+    const FinishIO fin{AcceptIO{cost, pred, bwd_feasible, rp, r_inc, success, gain_ratio}, hu, active, (long long*)inner,
+                       (long long*)iteration, outer_done, advanced, hu_tol, max_attempts, max_iterations};
+    if (plant == IPOC_PLANT_PENDULUM) return cost_finish_impl<Pendulum>(pp, bp, N, batch, tx, tu, new_cost, traj_feasible, fin, st);
+    if (plant == IPOC_PLANT_CARTPOLE) return cost_finish_impl<Cartpole>(pp, bp, N, batch, tx, tu, new_cost, traj_feasible, fin, st);
     return IPOC_EINVAL;
 }
 

@@ -19,6 +19,10 @@ _SIGS = {
     "ipoc_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "ipoc_set_tuning": (None, [_I, _I, _I]),
     "ipoc_set_literal_lqt": (None, [_I]),
+    "ipoc_set_hier": (None, [_I, _I, _I]),
+    "ipoc_workspace_init": (_I, [_P, _SZ, _P]),
+    "ipoc_costates_f64": (_I, [_I] * 4 + [_P] * 6 + [_P, _SZ, _P]),
+    "ipoc_newton_attempt_f64": (_I, [_I] * 5 + [_P] * 29 + [_P, _SZ, _P]),
     "ipoc_launch_count": (ctypes.c_ulonglong, []),
     "ipoc_carry_doubles": (_I, [_I, _I]),
     "ipoc_newton_step_f64": (_I, [_I] * 4 + [_P] * 13 + [_P, _SZ, _P]),
@@ -31,6 +35,10 @@ _SIGS = {
     "ipoc_trial_point_f64": (_I, [_I] * 4 + [_P] * 6 + [_P]),
     "ipoc_attempt_commit_f64": (_I, [_I] * 4 + [_P] * 8 + [_I, _P]),
     "ipoc_newton_advance_f64": (_I, [_I] * 4 + [_P] * 10 + [ctypes.c_double, _I, _P]),
+    "ipoc_attempt_finish_f64": (_I, [_I] + [_P] * 15 + [ctypes.c_double, _I, _I, _P]),
+    "ipoc_masked_copy_f64": (_I, [_I] * 4 + [_P] * 5 + [_P]),
+    "ipoc_plant_attempt_finish_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 18
+                                      + [ctypes.c_double, _I, _I, _P]),
     "ipoc_lqr_params_f64": (_I, [_I] * 4 + [_P] * 13 + [_P]),
     "ipoc_newton_bwd_reduce_f64": (_I, [_I] * 3 + [_P] * 8 + [_P, _SZ, _P]),
     "ipoc_newton_bwd_apply_f64": (_I, [_I] * 5 + [_P] * 14 + [_P, _SZ, _P]),
@@ -51,7 +59,7 @@ _SIGS = {
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
-WS_NEWTON_STEP, WS_LQT_BWD, WS_LQT_FWD, WS_AFFINE_SCAN, WS_REDUCTIONS = range(5)
+WS_NEWTON_STEP, WS_LQT_BWD, WS_LQT_FWD, WS_AFFINE_SCAN, WS_REDUCTIONS, WS_COSTATES, WS_NEWTON_ATTEMPT = range(7)
 CARRY_RICCATI, CARRY_AFFINE = 0, 1
 
 _lib = None
@@ -114,22 +122,28 @@ def stream_ptr():
 
 
 _ws_cache = {}
-_ws_retired = []
+_ws_retired = []   # never freed; a buffer is only retired when it at least doubles, so the total stays < 2x the live size
 
 
 def workspace(kind, N, nx, nu, batch, device):
-    """Per-device scratch tensor, grown on demand and reused (the C library owns nothing)."""
+    """Scratch tensor for one C-ABI call, grown on demand and reused (the C library owns nothing).
+
+    One buffer per (device, kind, CURRENT STREAM): calls enqueued on different streams — including a CUDA graph
+    captured on one stream and eager calls on another — never share scratch, which makes this binding as
+    re-entrant as the C ABI itself (a workspace must not be used by two calls at the same time).  Buffers are
+    zero-filled at allocation: the control block of a scan workspace must start zeroed (include/ipoc.h)."""
     need = lib().ipoc_workspace_bytes(kind, N, nx, nu, batch)
     if need == 0:
         raise IpocError(f"unsupported problem size (nx={nx}, nu={nu}): no kernel instantiated, no CPU fallback")
-    key = (torch.device(device).index or 0, kind)
+    dev = torch.device(device)
+    key = (dev.index or 0, kind, torch.cuda.current_stream(dev).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < need:
         if buf is not None:
             # captured CUDA graphs (graphed.py, batched.py, sharded.py) hold the old buffer's address:
             # retire it instead of freeing it, so that replaying them can never touch someone else's memory
             _ws_retired.append(buf)
-        buf = torch.empty(int(need * 2) + 1024, dtype=torch.uint8, device=device)
+        buf = torch.zeros(int(need * 2) + 1024, dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf, need
 
@@ -143,7 +157,9 @@ _tuning = (0, 0, 0)
 
 
 def set_tuning(leaf_chunk=0, mid_fanin=0, top_max=0):
-    """Scan-plan knobs of the library (0 = default); remembered so callers can restore them."""
+    """Scan-plan knobs of the library (0 = default); remembered so callers can restore them.  The knobs
+    (this, ipoc_set_hier, ipoc_set_literal_lqt) are PROCESS-GLOBAL test / experiment switches: do not flip them
+    while another thread is inside the library (a plan must be carved with the knobs it was sized with)."""
     global _tuning
     prev = _tuning
     lib().ipoc_set_tuning(int(leaf_chunk), int(mid_fanin), int(top_max))

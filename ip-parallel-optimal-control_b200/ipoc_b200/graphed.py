@@ -115,70 +115,89 @@ def get(ocp: OCP, N, nx, nu, device, x, u, bp):
 
 class DeviceLoopNewton:
     """The WHOLE `newton_oc` loop (ref noc/par_interior_point_newton.py:137-202) with its control flow on the
-    device: one CUDA graph = one accept/reject attempt preceded by the end-of-iteration
-    bookkeeping of the previous one,
+    device, for one problem or a batch of independent problems: one CUDA graph = one
+    accept/reject attempt of every member,
 
-        advance  : if the attempt loop just ended: x <- tx, u <- tu, iteration += 1, exit test on the pre-step
-                   max|ru|                                                          (ipoc_newton_advance_f64)
-        iterate  : cost, derivatives, K1 costates, LQ parameters, K4 at (x, u)      (same statements as graph A;
-                   recomputed — idempotently — when the previous attempt was rejected)
-        attempt  : reg = rp*||cu||, K2+K3, trial point, its cost / feasibility, A8 accept + regularisation
-                   update, keep / count / inner-exit                                (the glue kernels of batched.py)
+        take step : x <- tx, u <- tu for members whose attempt loop ended in the previous replay (:184)
+                                                                                    (ipoc_masked_copy_f64)
+        iterate   : cost, linearisation, K1 costates (+ ||cu||), LQ parameters at (x, u)   (:142-149; recomputed
+                    — idempotently — when the previous attempt was rejected)
+        attempt   : K2 + K3 with reg = rp*||cu|| (:117, :153), max|ru| (:158) and the trial point (:156-157) as
+                    side jobs of the scan kernels                                   (ipoc_newton_attempt_f64)
+        finish    : trial cost / feasibility, accept rule and rp update (:159-173), attempt counter and inner
+                    exit (:174-182), iteration counter and outer exit on the PRE-step max|ru| (:194-202)
+                                        (ipoc_plant_attempt_finish_f64 / eval_trial + ipoc_attempt_finish_f64)
 
-    and every piece is frozen once `outer_done` is set — exactly the `select` semantics of a `lax.while_loop`
-    — so the host may run ahead: it keeps `depth` replays queued and looks at the exit flag of an OLDER
-    replay (one byte copied to pinned memory behind each replay), i.e. no host round trip sits on the critical
-    path.  Iterates and iteration counts are those of the eager loop (tests)."""
+    Ten launches for the built-in plants.  Every member is frozen once its `outer_done` is set — exactly the
+    `select` semantics of a (vmapped) `lax.while_loop` — so the host may run ahead: it keeps `depth` replays
+    queued and looks at the exit flags of an OLDER replay (copied to pinned memory behind each replay), i.e. no
+    host round trip sits on the critical path.  Iterates and iteration counts are those of the eager loop."""
 
-    def __init__(self, ocp: OCP, N: int, nx: int, nu: int, device):
-        self.ocp, self.N, self.nx, self.nu, self.dev = ocp, N, nx, nu, torch.device(device)
+    def __init__(self, ocp: OCP, N: int, nx: int, nu: int, device, batch: int = 1):
+        self.ocp, self.N, self.nx, self.nu, self.dev, self.B = ocp, N, nx, nu, torch.device(device), batch
+        B = batch
         o = dict(dtype=torch.float64, device=self.dev)
         i32 = dict(dtype=torch.int32, device=self.dev)
-        self.x, self.tx, self.cx = (torch.zeros(1, N + 1, nx, **o) for _ in range(3))
-        self.u, self.tu, self.cu = (torch.zeros(1, N, nu, **o) for _ in range(3))
+        self.x, self.tx = torch.zeros(B, N + 1, nx, **o), torch.zeros(B, N + 1, nx, **o)
+        self.u, self.tu = torch.zeros(B, N, nu, **o), torch.zeros(B, N, nu, **o)
         self.bp = torch.zeros((), **o)
-        self.rp, self.r_inc = torch.ones(1, **o), torch.full((1,), 2.0, **o)
-        self.reg, self.gain, self.hu = torch.zeros(1, **o), torch.zeros(1, **o), torch.ones(1, **o)
-        self.act, self.succ, self.adv = torch.zeros(1, **i32), torch.zeros(1, **i32), torch.zeros(1, **i32)
-        self.inner = torch.zeros(1, dtype=torch.int64, device=self.dev)
-        self.iteration = torch.zeros(1, dtype=torch.int64, device=self.dev)
-        self.inner_done = torch.zeros(1, dtype=torch.bool, device=self.dev)
-        self.outer_done = torch.zeros(1, dtype=torch.bool, device=self.dev)
-        self.depth = 3 if N <= 20000 else 1      # replays kept in flight (a replay is > 1 ms for long horizons)
+        self.rp, self.r_inc = torch.ones(B, **o), torch.full((B,), 2.0, **o)
+        self.gain, self.new_cost = torch.zeros(B, **o), torch.zeros(B, **o)
+        self.act, self.succ, self.adv = torch.ones(B, **i32), torch.zeros(B, **i32), torch.zeros(B, **i32)
+        self.traj_feas = torch.zeros(B, **i32)
+        self.inner = torch.zeros(B, dtype=torch.int64, device=self.dev)
+        self.iteration = torch.zeros(B, dtype=torch.int64, device=self.dev)
+        self.outer_done = torch.zeros(B, dtype=torch.bool, device=self.dev)
+        self.buf = noc.AttemptBuffers(B, N, nx, nu, self.dev)
+        self.depth = 3 if N * B <= 20000 else 1    # replays kept in flight (a replay is > 1 ms for long horizons)
         self.ring = 8
-        self.flags = torch.zeros(self.ring, dtype=torch.bool).pin_memory()
+        self.flags = torch.zeros(self.ring, B, dtype=torch.bool).pin_memory()
         self.events = [torch.cuda.Event() for _ in range(self.ring)]
         self.graph = None
 
     def _step(self):
-        noc.newton_advance(self.hu, self.inner_done, self.outer_done, self.inner, self.iteration, self.adv,
-                           self.tx, self.tu, self.x, self.u)                               # :184-202
-        cost, fx, fu, cu, ru, Q, R, M = noc.eval_iteration(self.ocp, self.x[0], self.u[0], self.bp)   # :142-149
-        _, cu_norm, _ = noc.reductions(ru=ru, cu=cu, hu_out=self.hu)                       # :158, :116
-        noc.attempt_begin(self.outer_done, self.rp, cu_norm, self.act, self.reg)           # :117
-        dx, du, _, _, pred, bwd_feas = noc.newton_step(fx, fu, ru, Q, R, M, self.reg)      # :153
-        noc.trial_point(self.x, dx.unsqueeze(0), self.u, du.unsqueeze(0), self.cx, self.cu)   # :156-157
-        new_cost, traj_feas = noc.eval_trial(self.ocp, self.cx[0], self.cu[0], self.bp)    # :159-163
+        from . import plants
+        lib, p = L.lib(), L.ptr
+        B, N, nx, nu = self.B, self.N, self.nx, self.nu
         with torch.cuda.device(self.dev):
-            L.check(L.lib().ipoc_accept_update_f64(1, L.ptr(cost), L.ptr(new_cost.contiguous()), L.ptr(traj_feas),
-                                                   L.ptr(pred), L.ptr(bwd_feas), L.ptr(self.act), L.ptr(self.rp),
-                                                   L.ptr(self.r_inc), L.ptr(self.succ), L.ptr(self.gain),
-                                                   L.stream_ptr()))                        # :159-173
-        noc.attempt_commit(self.act, self.succ, self.cx, self.cu, self.tx, self.tu, self.inner,
-                           self.inner_done)                                                # :174-182
+            L.check(lib.ipoc_masked_copy_f64(N, nx, nu, B, p(self.adv), p(self.tx), p(self.tu), p(self.x), p(self.u),
+                                             L.stream_ptr()))                               # :184
+        plant = plants.plant_of(self.ocp)
+        if plant is not None:                                                              # :142-149
+            fx, fu, cx, cu, lamT = plants.linearize(plant, self.x, self.u, self.bp)
+            cost, _ = plants.cost(plant, self.x, self.u, self.bp)
+            lam, cu_norm = noc.costates_fused(fx, cx, lamT, cu)                            # :147, :116
+            ru, Q, R, M = plants.hamiltonian(plant, self.x, self.u, lam, self.bp)
+        else:
+            cost, fx, fu, cu, ru, Q, R, M = noc.eval_iteration(self.ocp, self.x, self.u, self.bp)
+            _, cu_norm, _ = noc.reductions(cu=cu)
+        buf = noc.newton_attempt(self.buf, fx, fu, ru, Q, R, M, self.rp, cu_norm, self.x, self.u, self.tx, self.tu,
+                                 self.act)                                                 # :153-158
+        fin = (p(cost.contiguous()), p(buf.pred), p(buf.bwd_feas), p(buf.hu), p(self.act), p(self.rp), p(self.r_inc),
+               p(self.succ), p(self.gain), p(self.inner), p(self.iteration), p(self.outer_done), p(self.adv), 1e-4,
+               500, 1000, L.stream_ptr())                                                  # :159-202
+        with torch.cuda.device(self.dev):
+            if plant is not None:
+                L.check(lib.ipoc_plant_attempt_finish_f64(plant["id"], N, B, plant["Ts"], plant["bound"],
+                                                          p(plants._bp_tensor(self.bp, self.dev)), p(self.tx), p(self.tu),
+                                                          p(self.new_cost), p(self.traj_feas), *fin))
+            else:
+                new_cost, traj_feas = noc.eval_trial(self.ocp, self.tx, self.tu, self.bp)  # :159-163
+                L.check(lib.ipoc_attempt_finish_f64(B, fin[0], p(new_cost.contiguous()), p(traj_feas), *fin[1:]))
 
     def _reset(self, x, u, bp):
-        self.x[0].copy_(x)
-        self.u[0].copy_(u)
+        self.x.copy_(x.reshape(self.x.shape))
+        self.u.copy_(u.reshape(self.u.shape))
         self.tx.copy_(self.x)
         self.tu.copy_(self.u)
         self.bp.fill_(float(bp))
         self.rp.fill_(1.0)                                                                 # :134
         self.r_inc.fill_(2.0)                                                              # :135
-        self.hu.fill_(1.0)
+        self.buf.hu.fill_(1.0)
+        self.act.fill_(1)
+        self.adv.zero_()
         self.inner.zero_()
         self.iteration.zero_()
-        self.inner_done.zero_()
         self.outer_done.zero_()
 
     def capture(self, x, u, bp):
@@ -195,22 +214,38 @@ class DeviceLoopNewton:
             self._step()
         self.graph = g
 
+    def launch(self, r):
+        """Replay number r; its exit flags land in pinned memory behind it."""
+        self.graph.replay()
+        k = r % self.ring
+        self.flags[k].copy_(self.outer_done, non_blocking=True)
+        self.events[k].record()
+
+    def finished(self, r):
+        """Exit flags (B,) bool as of replay r (blocks until that replay is done)."""
+        k = r % self.ring
+        self.events[k].synchronize()
+        return self.flags[k]
+
+    def take_last_step(self):
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().ipoc_masked_copy_f64(self.N, self.nx, self.nu, self.B, L.ptr(self.adv), L.ptr(self.tx),
+                                                 L.ptr(self.tu), L.ptr(self.x), L.ptr(self.u), L.stream_ptr()))
+        self.adv.zero_()
+
     def run(self, x, u, bp):
-        """-> (x, u, iterations) of `newton_oc` started at (x, u)."""
+        """-> (x, u, iterations) of `newton_oc` started at (x, u) (single problem: unbatched results)."""
         self._reset(x, u, bp)
         r = 0
         while True:
-            self.graph.replay()
-            k = r % self.ring
-            self.flags[k:k + 1].copy_(self.outer_done, non_blocking=True)
-            self.events[k].record()
+            self.launch(r)
             r += 1
-            if r >= self.depth:
-                j = (r - self.depth) % self.ring
-                self.events[j].synchronize()
-                if bool(self.flags[j]):
-                    break
-        return self.x[0].clone(), self.u[0].clone(), int(self.iteration)
+            if r >= self.depth and bool(self.finished(r - self.depth).all()):
+                break
+        self.take_last_step()
+        if self.B == 1:
+            return self.x[0].clone(), self.u[0].clone(), int(self.iteration)
+        return self.x.clone(), self.u.clone(), self.iteration.clone()
 
 
 _loop_cache = {}

@@ -103,3 +103,39 @@ class MpcLoop:
             self.xstart.copy_(self.X[k - 1, 1])
             done += k
         return torch.cat(xs), torch.cat(us)
+
+
+def constrained_mpc(ocp, x0, horizon: int = 40, sim_steps: int = 20, u_init=None, use_graphs: bool = True):
+    """Box-constrained receding-horizon MPC of REPEATED interior-point solves — BASELINE config 3 as
+    BASELINE.json words it ("receding-horizon loop of repeated IP solves"; an extension: the reference has no
+    script for it).  Anchors: the loop of ref examples/linear_mpc_parallel.py:67-81 (solve from the current
+    state, apply u[0], move to x[1]) around `par_interior_point_optimal_control` on the OCP of
+    ref examples/linear_demo_cuda.py:19-55 with the dummy constraint `-1` (:30-31) replaced by the box
+    |u| <= u_max (problems.make_linear_demo(control_bound=...)), horizon 40 (:51).  The first solve starts
+    from u = 0.1 N(0,1) (the start of the reference's constrained examples, ref examples/cartpole_runtime.py:102-103)
+    instead of the demo's u = 0 (:54): at u = 0 a symmetric box makes cu = 0, hence reg = rp*||cu|| = 0 (ref
+    noc/par_interior_point_newton.py:116-117) for every rp, the full Newton step is re-tried 501 times and the
+    reference's own algorithm walks out of the feasible set for good.
+
+    Every MPC step: solve the horizon-`horizon` OCP from the current state, warm-started with the previous
+    solution shifted by one step (last control repeated), apply the first control through the OCP's own
+    dynamics.  -> (xs (sim_steps+1, nx), us (sim_steps, nu), iterations per step (list))."""
+    from . import noc
+    dev = x0.device
+    if not x0.is_cuda:
+        raise L.IpocError("constrained_mpc needs CUDA tensors; there is no CPU fallback")
+    x = L.dev_f64(x0)
+    nu = 1 if u_init is None else u_init.shape[-1]
+    if u_init is None:
+        import numpy as np
+        u_init = torch.as_tensor(0.1 * np.random.default_rng(1).standard_normal((horizon, nu)), device=dev)
+    u = L.dev_f64(u_init, dev).clone()
+    xs, us, its = [x.clone()], [], []
+    for _ in range(sim_steps):
+        u_opt, n_it = noc.par_interior_point_optimal_control(ocp, u, x, use_graphs=use_graphs)
+        x = ocp.dynamics(x, u_opt[0]).detach()           # plant = model (linear_mpc_parallel.py:69: x_par[1])
+        xs.append(x.clone())
+        us.append(u_opt[0].clone())
+        its.append(int(n_it))
+        u = torch.cat((u_opt[1:], u_opt[-1:])).contiguous()   # shifted warm start
+    return torch.stack(xs), torch.stack(us), its

@@ -41,7 +41,7 @@ def compute_lqr_params(lagrange_multipliers: torch.Tensor, d: Derivatives):
     """ref noc/par_interior_point_newton.py:31-42 (tensordot contracts the OUTPUT index).
     CUDA tensors go through one streaming kernel (ipoc_lqr_params_f64); the einsum form below is the
     same arithmetic for anything else.  Accepts (N, ...) or (B, N, ...)."""
-    if lagrange_multipliers.is_cuda:
+    if lagrange_multipliers.is_cuda and lagrange_multipliers.shape[-1] <= 8:   # kernel: nx <= 8; else the einsums
         lam = L.dev_f64(lagrange_multipliers)
         t = [L.dev_f64(a) for a in (d.cu, d.cxx, d.cuu, d.cxu, d.fu, d.fxx, d.fuu, d.fxu)]
         batched = lam.dim() == 3
@@ -202,6 +202,50 @@ def newton_advance(hu, inner_done, outer_done, inner, iteration, advanced, tx, t
                                                 L.ptr(inner), L.ptr(iteration), L.ptr(advanced), L.ptr(tx), L.ptr(tu),
                                                 L.ptr(x), L.ptr(u), float(hu_tol), int(max_iterations),
                                                 L.stream_ptr()))
+
+
+def costates_fused(fx, cx, lamT, cu):
+    """K1 with ||cu||_F folded into the up-sweep (ipoc_costates_f64; ref noc/costates.py:34-40 + :116 of the
+    Newton step) -> (lam (B,N+1,nx), cu_norm (B,)).  Batched (B,N,...) tensors."""
+    fx, cx, cu = L.dev_f64(fx), L.dev_f64(cx), L.dev_f64(cu)
+    lamT = L.dev_f64(lamT, fx.device).reshape(fx.shape[0], -1).contiguous()
+    Bn, N, nx, nu = fx.shape[0], fx.shape[1], fx.shape[2], cu.shape[-1]
+    lam = torch.empty(Bn, N + 1, nx, dtype=torch.float64, device=fx.device)
+    cu_norm = torch.empty(Bn, dtype=torch.float64, device=fx.device)
+    ws, nbytes = L.workspace(L.WS_COSTATES, N, nx, nu, Bn, fx.device)
+    with torch.cuda.device(fx.device):
+        L.check(L.lib().ipoc_costates_f64(N, nx, nu, Bn, L.ptr(fx), L.ptr(cx), L.ptr(lamT), L.ptr(cu), L.ptr(lam),
+                                          L.ptr(cu_norm), L.ptr(ws), nbytes, L.stream_ptr()))
+    return lam, cu_norm
+
+
+class AttemptBuffers:
+    """Result buffers + private workspace of `newton_attempt` (allocated once per loop object)."""
+
+    def __init__(self, B, N, nx, nu, dev):
+        o = dict(dtype=torch.float64, device=dev)
+        self.dx, self.du = torch.empty(B, N + 1, nx, **o), torch.empty(B, N, nu, **o)
+        self.Kx, self.d = torch.empty(B, N, nu, nx, **o), torch.empty(B, N, nu, **o)
+        self.pred, self.hu = torch.empty(B, **o), torch.ones(B, **o)
+        self.bwd_feas = torch.empty(B, dtype=torch.int32, device=dev)
+        self.nbytes = L.lib().ipoc_workspace_bytes(L.WS_NEWTON_ATTEMPT, N, nx, nu, B)
+        if self.nbytes == 0:
+            raise L.IpocError(f"unsupported (nx={nx}, nu={nu}): no kernel instantiated and there is no CPU fallback")
+        self.ws = torch.zeros(self.nbytes, dtype=torch.uint8, device=dev)   # control block must start zeroed
+
+
+def newton_attempt(buf: AttemptBuffers, fx, fu, ru, Q, R, M, rp, cu_norm, x=None, u=None, tx=None, tu=None, active=None):
+    """ipoc_newton_attempt_f64: K2 + K3 with reg = rp*||cu|| formed in the kernel (ref :117), max|ru| (:158) folded
+    into the up-sweep and the trial point tx = x + dx, tu = u + du (:156-157; only for members with active != 0)
+    written by K3's leaf kernel.  Three launches.  Results land in `buf`."""
+    Bn, N, nx, nu = fx.shape[0], fx.shape[1], fx.shape[2], fu.shape[-1]
+    p = L.ptr
+    with torch.cuda.device(fx.device):
+        L.check(L.lib().ipoc_newton_attempt_f64(
+            N, nx, nu, 1, Bn, p(fx), p(fu), p(ru), p(Q), p(R), p(M), p(rp), p(cu_norm), p(buf.dx), p(buf.du), p(buf.Kx),
+            p(buf.d), p(buf.pred), p(buf.bwd_feas), p(buf.hu), p(x), p(u), p(tx), p(tu), None, None, None, None, None,
+            p(active), None, None, None, None, p(buf.ws), buf.nbytes, L.stream_ptr()))
+    return buf
 
 
 # ------------------------------------------------------------------ K2 + K3: the Newton step

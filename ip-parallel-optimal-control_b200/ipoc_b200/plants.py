@@ -16,16 +16,25 @@ ENABLED = True
 PLANT_IDS = {"pendulum": 1, "cartpole": 2}
 
 
-def tag(dynamics, name, Ts, bound):
-    dynamics._ipoc_plant = {"name": name, "id": PLANT_IDS[name], "Ts": float(Ts), "bound": float(bound)}
-    return dynamics
+def register(ocp, name, Ts, bound):
+    """Mark an OCP built by `problems.make_pendulum` / `make_cartpole` as a built-in plant.  The kernels of
+    ipoc_plants.cu hard-code the dynamics, stage cost, final cost, goal state, weights AND box constraints, so the
+    descriptor records the identity of ALL five callables: an OCP in which any of them was replaced
+    (`ocp._replace(stage_cost=my_cost)`, `OCP(make_cartpole(Ts).dynamics, my_cons, ...)`) no longer matches and
+    goes through the host framework's autodiff like every user-defined problem."""
+    ocp.dynamics._ipoc_plant = {"name": name, "id": PLANT_IDS[name], "Ts": float(Ts), "bound": float(bound),
+                                "callables": tuple(id(f) for f in ocp)}
+    return ocp
 
 
 def plant_of(ocp):
-    """Plant descriptor of a built-in OCP, or None (also None when the fast path is disabled)."""
+    """Plant descriptor of an UNMODIFIED built-in OCP, or None (also None when the fast path is disabled)."""
     if not ENABLED:
         return None
-    return getattr(ocp.dynamics, "_ipoc_plant", None)
+    d = getattr(ocp.dynamics, "_ipoc_plant", None)
+    if d is None or d["callables"] != tuple(id(f) for f in ocp):
+        return None
+    return d
 
 
 def _bp_tensor(bp, dev):

@@ -69,8 +69,8 @@ def make_pendulum(Ts: float, control_bound: float = 5.0) -> OCP:
         return torch.hstack((velocity, acc))
 
     from . import plants
-    return OCP(plants.tag(euler(ode, Ts), "pendulum", Ts, control_bound), constraints, stage_cost, final_cost,
-               total_cost)
+    return plants.register(OCP(euler(ode, Ts), constraints, stage_cost, final_cost, total_cost), "pendulum", Ts,
+                           control_bound)
 
 
 def pendulum_x0(dtype=torch.float64, device="cpu"):
@@ -112,8 +112,8 @@ def make_cartpole(Ts: float, control_bound: float = 50.0) -> OCP:
         return torch.hstack((cart_velocity, pole_velocity, cart_acc, pole_acc))
 
     from . import plants
-    return OCP(plants.tag(euler(ode, Ts), "cartpole", Ts, control_bound), constraints, stage_cost, final_cost,
-               total_cost)
+    return plants.register(OCP(euler(ode, Ts), constraints, stage_cost, final_cost, total_cost), "cartpole", Ts,
+                           control_bound)
 
 
 def cartpole_x0(dtype=torch.float64, device="cpu"):

@@ -51,8 +51,14 @@ class NewtonPass:
         self.ws_new_bytes = lib.ipoc_workspace_bytes(L.WS_NEWTON_STEP, N, nx, nu, B)
         self.ws_red_bytes = lib.ipoc_workspace_bytes(L.WS_REDUCTIONS, N, max(nu, self.nc), nu, B)
         self.ws_red = torch.empty(self.ws_red_bytes, dtype=torch.uint8, device=dev)
-        self.ws_aff = torch.empty(self.ws_aff_bytes, dtype=torch.uint8, device=dev)
-        self.ws_new = torch.empty(self.ws_new_bytes, dtype=torch.uint8, device=dev)
+        self.ws_aff = torch.zeros(self.ws_aff_bytes, dtype=torch.uint8, device=dev)
+        self.ws_new = torch.zeros(self.ws_new_bytes, dtype=torch.uint8, device=dev)
+        # fused entry points (K1 + ||cu||; K2 + K3 + max|ru| + constraints + accept): their own workspaces
+        self.ws_cos_bytes = lib.ipoc_workspace_bytes(L.WS_COSTATES, N, nx, nu, B)
+        self.ws_att_bytes = lib.ipoc_workspace_bytes(L.WS_NEWTON_ATTEMPT, N, nx, max(nu, self.nc), B)
+        self.ws_cos = torch.zeros(self.ws_cos_bytes, dtype=torch.uint8, device=dev)
+        self.ws_att = torch.zeros(self.ws_att_bytes, dtype=torch.uint8, device=dev)
+        self.fused = True
         self.graph = None
 
     # algorithmic bytes per pass: each phase reads its inputs once, writes outputs once
@@ -91,14 +97,42 @@ class NewtonPass:
                                            p(self.bwd_feas), None, p(self.rp), p(self.r_inc), p(self.success),
                                            p(self.gain), s))
 
-    def run(self):
-        """K1 costates, K4 (max|ru|, ||cu||), reg = rp*||cu||, K2+K3 Newton step, K4 (constraints of
-        the stepped trajectory), A8 accept/update (rp, r_inc evolve on the device from pass to pass; the
-        work per pass does not depend on their values).  Only kernels of libipoc.so are launched."""
+    def costates_fused(self):
+        """K1 with ||cu||_F as a side job of the up-sweep (ipoc_costates_f64): two launches."""
+        p, lib = L.ptr, L.lib()
+        L.check(lib.ipoc_costates_f64(self.N, self.nx, self.nu, self.B, p(self.fx), p(self.cx), p(self.lamT), p(self.cu),
+                                      p(self.lam), p(self.cu_norm), p(self.ws_cos), self.ws_cos_bytes, L.stream_ptr()))
+
+    def attempt_fused(self):
+        """K2 + K3 with reg = rp*||cu|| formed in the kernel, max|ru| folded into the up-sweep, the constraint
+        reduction and the accept / regularisation update folded into K3's leaf kernel
+        (ipoc_newton_attempt_f64): three launches."""
+        p, lib = L.ptr, L.lib()
+        L.check(lib.ipoc_newton_attempt_f64(
+            self.N, self.nx, self.nu, self.nc, self.B, p(self.fx), p(self.fu), p(self.ru), p(self.Q), p(self.R),
+            p(self.M), p(self.rp), p(self.cu_norm), p(self.dx), p(self.du), p(self.Kx), p(self.d), p(self.pred),
+            p(self.bwd_feas), p(self.hu), None, None, None, None,
+            p(self.cons), p(self.traj_feas) if self.cons is not None else None,
+            p(self.cost), p(self.new_cost), p(self.traj_feas), None, p(self.rp), p(self.r_inc), p(self.success),
+            p(self.gain), p(self.ws_att), self.ws_att_bytes, L.stream_ptr()))
+
+    def run_unfused(self):
+        """The same pass as four separate C-ABI calls (round-1 sequence, 11 launches): K1, K4, K2+K3, K4 + A8."""
         self.costates()
         self.reductions_ru_cu()
         self.newton()
         self.feasibility_and_accept()
+
+    def run(self):
+        """K1 costates, K4 (max|ru|, ||cu||), reg = rp*||cu||, K2+K3 Newton step, K4 (constraints of
+        the stepped trajectory), A8 accept/update (rp, r_inc evolve on the device from pass to pass; the
+        work per pass does not depend on their values).  Only kernels of libipoc.so are launched: five with
+        the fused entry points (default), eleven as separate calls (`fused = False`)."""
+        if self.fused:
+            self.costates_fused()
+            self.attempt_fused()
+        else:
+            self.run_unfused()
 
     def capture(self):
         """Capture one pass into a CUDA graph (every C-ABI call is enqueue-only)."""
@@ -143,8 +177,8 @@ class HostNewtonPass:
     and every result comes back into ONE pinned host arena, so a step is a single host->device copy, the
     kernels of `NewtonPass.run()` and a single device->host copy — all three captured into one CUDA graph
     (`capture()`), i.e. one launch per step.  The input arena is ordered by first use
-    (fx, cx, lamT | ru, cu | fu, Q, R, M | cons); `views` exposes the named host views an integrator fills."""
-    IN = ("fx", "cx", "lamT", "ru", "cu", "fu", "Q", "R", "M", "cons")
+    (fx, cx, lamT, cu | ru, fu, Q, R, M, cons); `views` exposes the named host views an integrator fills."""
+    IN = ("fx", "cx", "lamT", "cu", "ru", "fu", "Q", "R", "M", "cons")
     OUT_F64 = ("lam", "dx", "du", "pred", "hu", "cu_norm", "gain", "rp", "r_inc")
     OUT_I32 = ("bwd_feas", "traj_feas", "success")
 
@@ -185,11 +219,10 @@ class HostNewtonPass:
         for k in ("fx", "fu", "cx", "cu", "ru", "Q", "R", "M", "cons"):   # the pass must read the arena itself
             assert getattr(self.inner, k).data_ptr() == dv[k].data_ptr(), k
         off = lambda name, arena_views, base: (arena_views[name].data_ptr() - base.data_ptr()) // 8
-        self.cut_a = off("ru", self.views, self.h_in)        # [fx cx lamT] | [ru cu fu Q R M] | [cons]
-        self.cut_b = off("cons", self.views, self.h_in)
+        self.cut_a = off("ru", self.views, self.h_in)        # [fx cx lamT cu] | [ru fu Q R M cons]
         self.cut_lam = off("dx", self.results, self.h_out)   # [lam] | [dx du scalars]
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self.ev_a, self.ev_b, self.ev_c, self.ev_lam = (torch.cuda.Event() for _ in range(4))
+        self.ev_a, self.ev_b, self.ev_lam = (torch.cuda.Event() for _ in range(3))
         self.h2d_bytes = self.h_in.numel() * 8
         self.d2h_bytes = self.h_out.numel() * 8
         self.graph = None
@@ -197,30 +230,25 @@ class HostNewtonPass:
     def run(self):
         """Copies on a second stream, ordered by first use, so that K1 runs while the inputs of K2 are still
         arriving and the costates go back while K2/K3 compute (PCIe is full duplex):
-           copy stream : H2D [fx cx lamT] | H2D [ru cu fu Q R M] | H2D [cons] ........ D2H [lam]
-           main stream :        wait A -> K1 | wait B -> K4, K2+K3 | wait C -> K4, A8 | D2H [dx du scalars]"""
+           copy stream : H2D [fx cx lamT cu] | H2D [ru fu Q R M cons] ............ D2H [lam]
+           main stream :        wait A -> K1 (+ ||cu||) | wait B -> K2+K3 (+ K4, A8) | D2H [dx du scalars]"""
         main = torch.cuda.current_stream(self.d_in.device)
         cs = self.copy_stream
-        a, b = self.cut_a, self.cut_b
+        a = self.cut_a
         cs.wait_stream(main)
         with torch.cuda.stream(cs):
             self.d_in[:a].copy_(self.h_in[:a], non_blocking=True)
             self.ev_a.record(cs)
-            self.d_in[a:b].copy_(self.h_in[a:b], non_blocking=True)
+            self.d_in[a:].copy_(self.h_in[a:], non_blocking=True)
             self.ev_b.record(cs)
-            self.d_in[b:].copy_(self.h_in[b:], non_blocking=True)
-            self.ev_c.record(cs)
         main.wait_event(self.ev_a)
-        self.inner.costates()
+        self.inner.costates_fused()
         self.ev_lam.record(main)
         with torch.cuda.stream(cs):
             cs.wait_event(self.ev_lam)
             self.h_out[:self.cut_lam].copy_(self.d_out[:self.cut_lam], non_blocking=True)
         main.wait_event(self.ev_b)
-        self.inner.reductions_ru_cu()
-        self.inner.newton()
-        main.wait_event(self.ev_c)
-        self.inner.feasibility_and_accept()
+        self.inner.attempt_fused()
         self.h_out[self.cut_lam:].copy_(self.d_out[self.cut_lam:], non_blocking=True)
         main.wait_stream(cs)
 

@@ -28,7 +28,7 @@ class SegmentNewton:
         self.dev = self.fx.device
         need = L.lib().ipoc_workspace_bytes(L.WS_NEWTON_STEP, self.N, self.nx, self.nu, 1)
         # private workspace: the leaf aggregates of phase 1 are reused by phase 2
-        self.ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        self.ws = torch.zeros(need, dtype=torch.uint8, device=self.dev)   # control block must start zeroed
         self.nbytes = need
         o = dict(dtype=torch.float64, device=self.dev)
         self.Kx = torch.empty(self.N, self.nu, self.nx, **o)
@@ -78,7 +78,7 @@ class SegmentNewton:
         all_gather_into(self.g_fwd, self.g_scal)
         self.graph3.replay()
         na = self.g_fwd.shape[1] - 2
-        return self.dx, self.du, self.g_fwd[:, na].sum(), self.g_fwd[:, na + 1]
+        return self.dx, self.du, self.g_fwd[:, na].sum(), (self.g_fwd[:, na + 1] != 0).all()   # 0-d bool tensor
 
     def bwd_reduce(self, reg):
         self.reg = L.dev_f64(reg, self.dev).reshape(1)
@@ -150,8 +150,11 @@ def dist_all_gather_into(group=None):
     return gather
 
 
-def segment_bounds(N, nranks):
-    """Contiguous, near-equal time segments [lo, hi) per rank."""
+def segment_bounds(N, nranks, allow_empty=False):
+    """Contiguous, near-equal segments [lo, hi) per rank.  Time segments must be non-empty (a rank without steps
+    would reach the C ABI as N = 0); batch shards may be empty."""
+    if nranks < 1 or (N < nranks and not allow_empty):
+        raise ValueError(f"cannot cut a horizon of {N} steps into {nranks} non-empty contiguous segments")
     base, rem = divmod(N, nranks)
     bounds, lo = [], 0
     for r in range(nranks):
@@ -163,7 +166,7 @@ def segment_bounds(N, nranks):
 
 def shard_batch(batch, rank, nranks):
     """[lo, hi) of the independent problems owned by `rank` (no data-path collective needed)."""
-    return segment_bounds(batch, nranks)[rank]
+    return segment_bounds(batch, nranks, allow_empty=True)[rank]
 
 
 def newton_step_virtual_ranks(fx, fu, ru, Q, R, M, reg, nranks):

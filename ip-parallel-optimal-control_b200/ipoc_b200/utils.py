@@ -35,18 +35,18 @@ def euler(ode: Callable, simulation_step: float):   # ref noc/utils.py:50-54
 
 def rollout(dynamics, controls, initial_state):
     """Serial nonlinear rollout, (N,nu),(nx,) -> (N+1,nx) — ref noc/utils.py:57-63.
-    O(N) sequential and outside the Newton step; runs on the CPU in float64 (N tiny
-    host-framework ops per step would be launch-bound on the GPU) and returns on the
-    device of `controls`."""
-    dev = controls.device
-    us = controls.detach().to("cpu", torch.float64)
-    x = initial_state.detach().to("cpu", torch.float64)
+    O(N) sequential, once per barrier stage and outside the Newton step.  The user's `dynamics` is evaluated by
+    the host framework on the device of `controls` (callables that capture CUDA tensors work for every horizon);
+    N tiny host-framework launches per step make this slow, which is why `noc.initial_rollout` switches to the
+    parallel rollout below from a few hundred steps on."""
+    us = controls.detach().to(torch.float64)
+    x = initial_state.detach().to(device=us.device, dtype=torch.float64)
     xs = [x]
     with torch.no_grad():
         for k in range(us.shape[0]):
             x = dynamics(x, us[k])
             xs.append(x)
-    return torch.stack(xs).to(dev)
+    return torch.stack(xs)
 
 
 def rollout_parallel(dynamics, controls, initial_state, x_guess=None, tol=1e-14, max_iter=200):
@@ -79,7 +79,7 @@ def rollout_parallel(dynamics, controls, initial_state, x_guess=None, tol=1e-14,
             err = float((Xn - X).abs().max())
             scale = 1.0 + float(Xn.abs().max())
             X = Xn
-            if not (err == err):   # NaN: diverged
+            if not (err == err) or not bool(torch.isfinite(Xn).all()):   # NaN / overflow: diverged, use the serial loop
                 break
             if err <= tol * scale:
                 X = torch.cat((x0.unsqueeze(0), f(X[:-1], controls)))   # states are exactly f of their predecessor

@@ -196,3 +196,21 @@ def par_interior_point_optimal_control(ev, controls, initial_state, trace=None, 
         total += its                                                   # :239
         stage += 1
     return u, total
+
+
+def constrained_mpc(ev, x0, horizon=40, sim_steps=20, u_init=None):
+    """CPU twin of ipoc_b200.mpc.constrained_mpc (BASELINE config 3, box-constrained extension): the loop of
+    ref examples/linear_mpc_parallel.py:67-81 around par_interior_point_optimal_control
+    (ref noc/par_interior_point_newton.py:228-254) with a shifted warm start.  `ev` = Evaluator of the OCP."""
+    import torch
+    x = np.asarray(x0, dtype=np.float64)
+    u = 0.1 * np.random.default_rng(1).standard_normal((horizon, 1)) if u_init is None else np.array(u_init, dtype=np.float64)
+    xs, us, its = [x.copy()], [], []
+    for _ in range(sim_steps):
+        u_opt, n_it = par_interior_point_optimal_control(ev, u, x)
+        x = ev.ocp.dynamics(torch.as_tensor(x), torch.as_tensor(u_opt[0])).detach().numpy().astype(np.float64)
+        xs.append(x.copy())
+        us.append(u_opt[0].copy())
+        its.append(int(n_it))
+        u = np.concatenate((u_opt[1:], u_opt[-1:]))
+    return np.stack(xs), np.stack(us), its

@@ -30,10 +30,12 @@ def N_(t):
 def _reset_tuning():
     from ipoc_b200 import _lib, plants
     _lib.lib().ipoc_set_tuning(0, 0, 0)
+    _lib.lib().ipoc_set_hier(1, 0, 0)
     _lib.lib().ipoc_set_literal_lqt(0)
     plants.ENABLED = True
     yield
     _lib.lib().ipoc_set_tuning(0, 0, 0)
+    _lib.lib().ipoc_set_hier(1, 0, 0)
     _lib.lib().ipoc_set_literal_lqt(0)
     plants.ENABLED = True
 
@@ -50,12 +52,12 @@ def test_library_loaded_and_supported():
     from ipoc_b200 import _lib
     L = _lib.lib()
     assert L.ipoc_version() >= 100
-    assert L.ipoc_supported(2, 1) and L.ipoc_supported(4, 1) and not L.ipoc_supported(5, 3)
+    assert L.ipoc_supported(2, 1) and L.ipoc_supported(4, 1) and L.ipoc_supported(5, 3) and L.ipoc_supported(8, 4)
+    assert not L.ipoc_supported(3, 4) and not L.ipoc_supported(8, 5) and not L.ipoc_supported(9, 1)   # nu <= min(nx, 4)
     assert b"no CPU fallback" in L.ipoc_strerror(-1)
 
 
-@pytest.mark.parametrize("nx,nu", [(2, 1), (4, 1), (3, 1), (2, 2), (4, 2), (1, 1), (6, 1), (8, 1),
-                                   (3, 2), (5, 1), (5, 2), (6, 2), (6, 3), (7, 1), (7, 2), (8, 2)])
+@pytest.mark.parametrize("nx,nu", [(nx, nu) for nx in range(1, 9) for nu in range(1, min(nx, 4) + 1)])
 @pytest.mark.parametrize("N", [1, 2, 3, 31, 32, 33, 500])
 def test_newton_step_vs_oracle(nx, nu, N):
     from ipoc_b200 import noc
@@ -438,7 +440,7 @@ def test_host_buffer_entry_point_and_error_codes():
     o = dict(dtype=torch.float64, device=DEV)
     outs = [torch.empty(N + 1, nx, **o), torch.empty(N, nu, **o), torch.empty(N, nu, nx, **o), torch.empty(N, nu, **o),
             torch.empty(1, **o), torch.empty(1, dtype=torch.int32, device=DEV)]
-    ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    ws = torch.zeros(1 << 20, dtype=torch.uint8, device=DEV)
     dp = lambda t: ctypes.c_void_p(t.data_ptr())
     regd = T([0.4])
     call = lambda nx_, wsb, fxp: L.ipoc_newton_step_f64(N, nx_, nu, 1, fxp, *(dp(t) for t in dev[1:]), dp(regd),
@@ -749,3 +751,164 @@ def test_config5_batched_subsample_histogram(problem):
         assert int(itb[b]) == it1, (b, int(itb[b]), it1)
         assert relerr(N_(ub[b]), N_(u1)) < 1e-9
     assert np.array_equal(np.bincount(np.array(its1)), np.bincount(N_(itb).astype(np.int64)))
+
+
+# ====================================================================== in-kernel levels (round 2)
+HIER_SHAPES = [(0, 0, 0, 0), (1, 1, 2, 1), (1, 1, 5, 32), (1, 2, 32, 3), (1, 3, 7, 8), (1, 0, 3, 2)]
+
+
+@pytest.mark.parametrize("enabled,leaf_chunk,group_warps,serial_top", HIER_SHAPES)
+@pytest.mark.parametrize("nx,nu,N", [(2, 1, 1000), (4, 1, 10000), (4, 2, 777), (3, 1, 4097)])
+def test_in_kernel_levels_all_shapes(enabled, leaf_chunk, group_warps, serial_top, nx, nu, N):
+    """The levels above the warp scans completed by the last-arriving warps inside the leaf kernels (no top /
+    mid kernels): every grouping (2 ... 32 warps per group; serial value chain or scan over the groups; more than
+    32 groups folded q per lane) and the separate level kernels (enabled = 0) give the oracle's step, costates
+    and forward pass."""
+    from ipoc_b200 import noc, _lib
+    from ipoc_b200.paroc import LQT, par_fwd_pass
+    rng = np.random.default_rng(11 * nx + N)
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu)
+    dxo, duo, Kxo, do, predo, feaso = oracle_newton(fx, fu, ru, Q, R, M, 0.05)
+    _lib.lib().ipoc_set_tuning(leaf_chunk, 0, 0)
+    _lib.lib().ipoc_set_hier(enabled, group_warps, serial_top)
+    for rep in range(2):   # second call: the arrival counters must have been re-armed
+        dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), T([0.05]))
+        assert relerr(N_(dx), dxo) < 1e-10 and relerr(N_(du), duo) < 1e-10
+        assert relerr(N_(Kx), Kxo) < 1e-10 and relerr(N_(d), do) < 1e-10
+        assert abs(float(pred) - predo) <= 1e-10 * abs(predo) and bool(feas[0]) == bool(feaso)
+    # K1 in both directions against a serial loop
+    c = rng.standard_normal((N, nx))
+    seed = rng.standard_normal(nx)
+    lam = N_(noc.affine_scan(T(fx), T(c), T(seed), reverse=True, transpose=True))
+    ref = np.zeros((N + 1, nx))
+    ref[N] = seed
+    for k in range(N - 1, -1, -1):
+        ref[k] = fx[k].T @ ref[k + 1] + c[k]
+    assert relerr(lam, ref) < 1e-11
+    xs = N_(noc.affine_scan(T(fx), T(c), T(seed), reverse=False, transpose=False))
+    ref = np.zeros((N + 1, nx))
+    ref[0] = seed
+    for k in range(N):
+        ref[k + 1] = fx[k] @ ref[k] + c[k]
+    assert relerr(xs, ref) < 1e-11
+    # raw forward pass (its own up-sweep) with x0 != 0
+    lq = noc_np.noc_to_lqt(ru, Q, R, M, fx, fu)
+    x0 = rng.standard_normal(nx)
+    uo, xo = paroc_np.par_fwd_pass(lq, x0, Kxo, do)
+    u, x = par_fwd_pass(LQT(*(T(a) for a in lq)), T(x0), T(Kxo), T(do))
+    assert relerr(N_(u), uo) < 1e-10 and relerr(N_(x), xo) < 1e-10
+
+
+@pytest.mark.parametrize("enabled,leaf_chunk,group_warps,serial_top", HIER_SHAPES)
+def test_in_kernel_levels_batched_and_sharded(enabled, leaf_chunk, group_warps, serial_top):
+    from ipoc_b200 import noc, sharded, _lib
+    rng = np.random.default_rng(5)
+    _lib.lib().ipoc_set_tuning(leaf_chunk if leaf_chunk else 2, 0, 0)
+    _lib.lib().ipoc_set_hier(enabled, group_warps, serial_top)
+    N, nx, nu, B = 700, 4, 1, 5
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu, batch=B)
+    reg = 0.1 + rng.random(B)
+    dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), T(reg))
+    for b in range(B):
+        dxo, duo, Kxo, do, predo, feaso = oracle_newton(fx[b], fu[b], ru[b], Q[b], R[b], M[b], reg[b])
+        assert relerr(N_(dx[b]), dxo) < 1e-10 and relerr(N_(du[b]), duo) < 1e-10
+        assert abs(float(pred[b]) - predo) <= 1e-10 * abs(predo) and bool(feas[b]) == bool(feaso)
+    args = [T(a[0]) for a in (fx, fu, ru, Q, R, M)]
+    for P in (2, 3):
+        dxs, dus, Kxs, ds, preds, feass = sharded.newton_step_virtual_ranks(*args, T(reg[:1]), P)
+        assert relerr(N_(dxs), N_(dx[0])) < 1e-11 and relerr(N_(dus), N_(du[0])) < 1e-11
+        assert abs(float(preds) - float(pred[0])) <= 1e-11 * abs(float(pred[0])) and feass == bool(feas[0])
+
+
+@pytest.mark.parametrize("N,B", [(300, 1), (10000, 1), (1000, 7), (100000, 1), (64, 200)])
+def test_fused_pass_equals_separate_calls(N, B):
+    """ipoc_costates_f64 + ipoc_newton_attempt_f64 (5 launches: ||cu||, max|ru|, reg = rp*||cu||, constraint
+    reduction and accept update as side jobs of the scan kernels) against the same pass as separate C-ABI calls
+    (K1, K4, K2+K3, K4, A8).  Everything but the summation order of ||cu|| is the same arithmetic."""
+    from ipoc_b200 import _lib
+    from ipoc_b200.runner import NewtonPass
+    rng = np.random.default_rng(N + B)
+    nx, nu, nc = 4, 1, 2
+    shape = (B, N) if B > 1 else (N,)
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu, batch=B if B > 1 else None)
+    cx, cu = rng.standard_normal(shape + (nx,)), rng.standard_normal(shape + (nu,))
+    lamT = rng.standard_normal((B, nx))
+    cons = -rng.random(shape + (nc,))
+    if B > 1:
+        cons[1, N // 2, 1] = 0.25          # one member infeasible
+    mk = lambda: NewtonPass(T(fx), T(fu), T(cx), T(cu), T(lamT), T(ru), T(Q), T(R), T(M), T(cons), rp=0.7)
+    a, b = mk(), mk()
+    b.fused = False
+    for p in (a, b):
+        p.new_cost.copy_(T(rng.standard_normal(B)) * 0 + 0.5)
+        p.cost.fill_(1.0)
+    assert mk().launches_per_pass() <= 5 + (B > 1) or B >= 64     # (batch > 1: + the seed transposition of K1)
+    for rep in range(3):      # rp / r_inc evolve from pass to pass on the device
+        a.run()
+        b.run()
+        torch.cuda.synchronize()
+        assert torch.equal(a.lam, b.lam) and torch.equal(a.hu, b.hu)
+        assert float((a.cu_norm - b.cu_norm).abs().max()) <= 1e-14 * float(b.cu_norm.abs().max())
+        assert relerr(N_(a.dx), N_(b.dx)) < 1e-12 and relerr(N_(a.du), N_(b.du)) < 1e-12
+        assert relerr(N_(a.pred), N_(b.pred)) < 1e-12
+        assert torch.equal(a.bwd_feas, b.bwd_feas) and torch.equal(a.traj_feas, b.traj_feas)
+        assert torch.equal(a.success, b.success)
+        assert relerr(N_(a.rp), N_(b.rp)) < 1e-12 and torch.equal(a.r_inc, b.r_inc)
+    if B > 1:
+        assert int(a.traj_feas[1]) == 0 and int(a.traj_feas[0]) == 1
+    # a captured graph of the fused pass replays to the same numbers
+    a2 = mk()
+    a2.new_cost.fill_(0.5)
+    a2.capture()
+    a2.rp.fill_(0.7)          # the warm-up pass of the capture moved them
+    a2.r_inc.fill_(2.0)
+    for rep in range(3):
+        a2.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(a2.dx, a.dx) and torch.equal(a2.rp, a.rp) and torch.equal(a2.success, a.success)
+
+
+def test_trial_point_side_job():
+    """tx = x + dx, tu = u + du written by K3's leaf kernel (ipoc_newton_attempt_f64) == the stand-alone kernel."""
+    from ipoc_b200 import _lib as L
+    rng = np.random.default_rng(9)
+    for N, B in ((257, 1), (5000, 1), (100, 40)):
+        nx, nu = 4, 1
+        fx, fu, ru, Q, R, M = (T(a) for a in random_lq(rng, N, nx, nu, batch=B))
+        x, u = T(rng.standard_normal((B, N + 1, nx))), T(rng.standard_normal((B, N, nu)))
+        o = dict(dtype=torch.float64, device=DEV)
+        dx, du, tx, tu = torch.empty(B, N + 1, nx, **o), torch.empty(B, N, nu, **o), torch.empty(B, N + 1, nx, **o), torch.empty(B, N, nu, **o)
+        Kx, d = torch.empty(B, N, nu, nx, **o), torch.empty(B, N, nu, **o)
+        pred, hu = torch.empty(B, **o), torch.empty(B, **o)
+        feas = torch.empty(B, dtype=torch.int32, device=DEV)
+        rp, cn = T(0.5 + rng.random(B)), T(0.5 + rng.random(B))
+        nbytes = L.lib().ipoc_workspace_bytes(L.WS_NEWTON_ATTEMPT, N, nx, nu, B)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+        L.check(L.lib().ipoc_workspace_init(L.ptr(ws), nbytes, L.stream_ptr()))
+        p = L.ptr
+        L.check(L.lib().ipoc_newton_attempt_f64(N, nx, nu, 1, B, p(fx), p(fu), p(ru), p(Q), p(R), p(M), p(rp), p(cn),
+                                                p(dx), p(du), p(Kx), p(d), p(pred), p(feas), p(hu), p(x), p(u), p(tx),
+                                                p(tu), *([None] * 10), p(ws), nbytes, L.stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(tx, x + dx) and torch.equal(tu, u + du)
+        assert torch.equal(hu, ru.abs().amax(dim=(1, 2)))
+        from ipoc_b200 import noc
+        dx2 = noc.newton_step(fx, fu, ru, Q, R, M, rp * cn)[0]
+        assert torch.equal(dx2, dx)
+
+
+def test_config3_constrained_receding_horizon_mpc():
+    """BASELINE config 3, box-constrained extension (no reference script; anchors in mpc.constrained_mpc): the
+    receding-horizon loop of repeated IP solves against its oracle twin — closed-loop states and controls within
+    1e-9, the same Newton iteration count at every MPC step, the bound active at the start and never violated."""
+    from ipoc_b200 import problems
+    from ipoc_b200.mpc import constrained_mpc
+    from oracle.autodiff import Evaluator
+    ub = 15.0                                 # the unconstrained solution starts at u = -48
+    ocp = problems.make_linear_demo(0.1, control_bound=ub)
+    x0 = np.array([2.0, 1.0])
+    xs_o, us_o, its_o = noc_np.constrained_mpc(Evaluator(ocp), x0, horizon=40, sim_steps=4)
+    xs, us, its = constrained_mpc(ocp, T(x0), horizon=40, sim_steps=4)
+    assert its == its_o and min(its) > 5
+    assert relerr(N_(xs), xs_o) < 1e-9 and relerr(N_(us), us_o) < 1e-9
+    assert float(us.abs().max()) < ub and float(us[0].abs()) > ub - 1e-3       # the box is active, never crossed

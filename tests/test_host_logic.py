@@ -26,7 +26,7 @@ def test_pure_host_entry_points_without_gpu():
     L = _lib.lib()
     assert L.ipoc_version() >= 100
     assert L.ipoc_supported(4, 1) == 1 and L.ipoc_supported(7, 1) == 1 and L.ipoc_supported(9, 1) == 0
-    assert L.ipoc_supported(6, 3) == 1 and L.ipoc_supported(5, 3) == 0
+    assert L.ipoc_supported(6, 3) == 1 and L.ipoc_supported(5, 3) == 1 and L.ipoc_supported(5, 5) == 0 and L.ipoc_supported(3, 4) == 0
     assert L.ipoc_carry_doubles(_lib.CARRY_RICCATI, 4) == 44 and L.ipoc_carry_doubles(_lib.CARRY_AFFINE, 4) == 20
     assert L.ipoc_carry_doubles(_lib.CARRY_RICCATI, 2) == 14
     small = L.ipoc_workspace_bytes(_lib.WS_NEWTON_STEP, 1000, 4, 1, 1)
