@@ -179,6 +179,107 @@ def _tail_graphs(ocp, N, nx, nu, dev):
     return gs or None
 
 
+# ------------------------------------------------------------------ device-resident batched loops
+class _DeviceLadder:
+    """Device-resident Newton + attempt loops (graphed.DeviceLoopNewton with a batch axis) for a LADDER of batch
+    sizes 8, 16, ..., 2^k >= B.  A stage starts in the smallest loop that holds its members; every replay advances
+    ALL members still inside their loops by one accept/reject attempt (finished members are frozen on the device,
+    the `select` of a vmapped `lax.while_loop`), the host looks at the exit flags once per burst and MIGRATES the
+    survivors to the next smaller loop when at most half a loop is still alive — so the long tail of a few hard
+    members (cartpole: iterations_max 340 against a mean of 127) runs in small graphs instead of dragging the whole
+    batch through every attempt, and no eager host-framework op or per-attempt host sync is left on the path."""
+    MIN = 8
+
+    def __init__(self, ocp, N, nx, nu, dev):
+        self.ocp, self.N, self.nx, self.nu, self.dev = ocp, N, nx, nu, dev
+        self.loops = {}
+
+    def loop(self, size, x, u, bp):
+        from .graphed import DeviceLoopNewton
+        lp = self.loops.get(size)
+        if lp is None:
+            lp = DeviceLoopNewton(self.ocp, self.N, self.nx, self.nu, self.dev, batch=size)
+            k = x.shape[0]
+            reps = (size + k - 1) // k
+            lp.capture(x.repeat(reps, 1, 1)[:size], u.repeat(reps, 1, 1)[:size], bp)
+            self.loops[size] = lp
+        return lp
+
+    @staticmethod
+    def _size_for(k):
+        s = _DeviceLadder.MIN
+        while s < k:
+            s *= 2
+        return s
+
+    @staticmethod
+    def _load(lp, k, x, u, tx, tu, rp, rinc, inner, iteration, bp):
+        """Members 0..k-1 <- the given state; the padding slots are frozen copies of member 0."""
+        lp.bp.fill_(float(bp))
+        for dst, src in ((lp.x, x), (lp.u, u), (lp.tx, tx), (lp.tu, tu), (lp.rp, rp), (lp.r_inc, rinc), (lp.inner, inner),
+                         (lp.iteration, iteration)):
+            dst[:k].copy_(src)
+            if k < lp.B:
+                dst[k:].copy_(src[:1].expand((lp.B - k,) + tuple(src.shape[1:])))
+        lp.act.fill_(0)
+        lp.act[:k] = 1
+        lp.outer_done.fill_(True)
+        lp.outer_done[:k] = False
+        lp.adv.zero_()
+        lp.buf.hu.fill_(1.0)
+
+    def run_stage(self, x, u, bp):
+        """`newton_oc` for every member from the iterate (x, u): -> (x, u, iterations (B,) int64)."""
+        B = x.shape[0]
+        dev = self.dev
+        out_x, out_u = x.clone(), u.clone()
+        out_it = torch.zeros(B, dtype=torch.int64, device=dev)
+        ids = torch.arange(B, device=dev)                     # global index of the member in each live slot
+        o = dict(dtype=torch.float64, device=dev)
+        st = dict(x=x, u=u, tx=x.clone(), tu=u.clone(), rp=torch.ones(B, **o), rinc=torch.full((B,), 2.0, **o),
+                  inner=torch.zeros(B, dtype=torch.int64, device=dev),
+                  iteration=torch.zeros(B, dtype=torch.int64, device=dev))
+        while ids.numel() > 0:
+            k = ids.numel()
+            size = self._size_for(k)
+            lp = self.loop(size, st["x"], st["u"], bp)
+            self._load(lp, k, st["x"], st["u"], st["tx"], st["tu"], st["rp"], st["rinc"], st["inner"], st["iteration"], bp)
+            burst = 4 if size * self.N > 2_000_000 else 8
+            while True:
+                for _ in range(burst):
+                    lp.graph.replay()
+                done = lp.outer_done[:k].clone()
+                alive = int(k - int(done.sum()))              # the one host sync per burst
+                if alive == 0 or (size > self.MIN and alive <= size // 2):
+                    break
+            lp.take_last_step()                               # x <- tx for members whose last attempt ended an iteration
+            fin = torch.nonzero(done).reshape(-1)
+            if fin.numel() > 0:
+                g = ids[fin]
+                out_x[g], out_u[g], out_it[g] = lp.x[fin], lp.u[fin], lp.iteration[fin]
+            keep = torch.nonzero(~done).reshape(-1)
+            ids = ids[keep]
+            if keep.numel() > 0:
+                st = dict(x=lp.x[keep], u=lp.u[keep], tx=lp.tx[keep], tu=lp.tu[keep], rp=lp.rp[keep], rinc=lp.r_inc[keep],
+                          inner=lp.inner[keep], iteration=lp.iteration[keep])
+        return out_x, out_u, out_it
+
+
+_ladder_cache = {}
+
+
+def _device_ladder(ocp, N, nx, nu, dev):
+    key = (id(ocp.dynamics), id(ocp.stage_cost), id(ocp.final_cost), id(ocp.constraints), id(ocp.total_cost),
+           N, nx, nu, str(dev), plants.ENABLED)
+    ld = _ladder_cache.get(key)
+    if ld is None:
+        while len(_ladder_cache) >= 2:
+            _ladder_cache.pop(next(iter(_ladder_cache)))
+        ld = _ladder_cache[key] = _DeviceLadder(ocp, N, nx, nu, dev)
+        ld._keepalive = ocp
+    return ld
+
+
 def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param, use_graphs: bool = True):
     """Per-member semantics of ref noc/par_interior_point_newton.py:127-225 for a batch.
     -> (x (B,N+1,nx), u (B,N,nu), iterations (B,) int64)
@@ -194,6 +295,10 @@ def newton_oc_batched(ocp: OCP, controls, initial_states, barrier_param, use_gra
     else:
         x_all = rollout_batched(ocp.dynamics, u_all, initial_states.to(dev))
     B = u_all.shape[0]
+    if use_graphs and plant is not None and use_graphs != "host":
+        # built-in plants: both loops live on the device for every member (graphed.DeviceLoopNewton, batch axis)
+        return _device_ladder(ocp, u_all.shape[1], x_all.shape[-1], u_all.shape[-1], dev).run_stage(x_all, u_all,
+                                                                                                     barrier_param)
     o = dict(dtype=torch.float64, device=dev)
     rp_all = torch.ones(B, **o)                                                    # :134
     rinc_all = torch.full((B,), 2.0, **o)                                          # :135

@@ -111,6 +111,166 @@ class SegmentNewton:
         return self.dx, self.du
 
 
+class SegmentPass:
+    """One rank's share of a WHOLE time-sharded hot-path pass (K1 + K4 + K2 + K3 + K4) on its contiguous segment:
+
+        K1 reduce + local max|ru|, sum cu^2        -> exchange 1: affine carry, the two scalars, lamT
+        K1 apply  (costates of the segment), reg = rp * ||cu|| from the gathered sums (fixed rank order)
+        K2 reduce                                   -> exchange 2: Riccati carry
+        K2 apply  (gains, pred / feasibility partials, K3's segment aggregate)
+                                                    -> exchange 3: forward carry, pred, feasible[, constraints ok]
+        K3 apply  (dx, du of the segment)
+
+    i.e. the three dependent carry exchanges of SURVEY section 8(e), each a (P, len) all-gather of < 0.5 KB per
+    rank.  Every local phase is one or two launches of libipoc.so (the scan levels complete inside the leaf
+    kernels and the seeds are chained through the gathered carries inside the down-sweeps).  `step()` enqueues the
+    whole pass on the current stream; `capture()` records it — collectives included — into ONE CUDA graph."""
+
+    def __init__(self, fx, fu, cx, cu, lamT, ru, Q, R, M, rank, nranks, cons=None, rp=1.0):
+        self.new = SegmentNewton(fx, fu, ru, Q, R, M, rank, nranks)
+        n = self.new
+        self.rank, self.nranks, self.dev, self.N, self.nx, self.nu = rank, nranks, n.dev, n.N, n.nx, n.nu
+        self.cx, self.cu = L.dev_f64(cx), L.dev_f64(cu)
+        self.cons = None if cons is None else L.dev_f64(cons)
+        o = dict(dtype=torch.float64, device=self.dev)
+        self.na = carry_doubles(L.CARRY_AFFINE, self.nx)
+        self.nr = carry_doubles(L.CARRY_RICCATI, self.nx)
+        P = nranks
+        # exchange buffers: row r = rank r's contribution
+        self.x1_mine, self.x1 = torch.zeros(self.na + 2 + self.nx, **o), torch.zeros(P, self.na + 2 + self.nx, **o)
+        self.x2_mine, self.x2 = torch.zeros(self.nr, **o), torch.zeros(P, self.nr, **o)
+        self.x3_mine, self.x3 = torch.zeros(self.na + 3, **o), torch.zeros(P, self.na + 3, **o)
+        self.x1_mine[self.na + 2:].copy_(L.dev_f64(lamT, self.dev).reshape(-1))   # only the last rank's is used
+        self.lam = torch.empty(self.N + 1, self.nx, **o)
+        self.rp = torch.full((1,), float(rp), **o)
+        self.reg = torch.empty(1, **o)
+        self.hu, self.cu_norm = torch.empty(1, **o), torch.empty(1, **o)
+        self.hu_l, self.cn_l = torch.empty(1, **o), torch.empty(1, **o)
+        self.feas_l = torch.ones(1, dtype=torch.int32, device=self.dev)
+        lib = L.lib()
+        self.nb_aff = lib.ipoc_workspace_bytes(L.WS_AFFINE_SCAN, self.N, self.nx, self.nu, 1)
+        self.ws_aff = torch.zeros(self.nb_aff, dtype=torch.uint8, device=self.dev)
+        nc = 1 if self.cons is None else self.cons.shape[-1]
+        self.nc = nc
+        self.nb_red = lib.ipoc_workspace_bytes(L.WS_REDUCTIONS, self.N, max(self.nu, nc), self.nu, 1)
+        self.ws_red = torch.zeros(self.nb_red, dtype=torch.uint8, device=self.dev)
+        self.graph = None
+
+    # ---- local phases (C ABI calls only) -----------------------------------------------------------------
+    def _k1_reduce(self):
+        p, lib, n = L.ptr, L.lib(), self.new
+        with torch.cuda.device(self.dev):
+            L.check(lib.ipoc_affine_reduce_f64(1, 1, self.N, self.nx, p(n.fx), p(self.cx), p(self.x1_mine),
+                                               p(self.ws_aff), self.nb_aff, L.stream_ptr()))
+            L.check(lib.ipoc_reductions_f64(self.N, self.nu, self.nc, 1, p(n.ru), p(self.cu), None, p(self.hu_l),
+                                            p(self.cn_l), None, None, None, p(self.ws_red), self.nb_red,
+                                            L.stream_ptr()))
+        self.x1_mine[self.na:self.na + 1].copy_(self.cn_l * self.cn_l)      # sum of squares travels, not the norm
+        self.x1_mine[self.na + 1:self.na + 2].copy_(self.hu_l)
+
+    def _k1_apply(self):
+        p, lib, n, na = L.ptr, L.lib(), self.new, self.na
+        carries = self.x1[:, :na].contiguous()
+        seed = self.x1[self.nranks - 1, na + 2:].contiguous()               # lamT lives on the last rank
+        with torch.cuda.device(self.dev):
+            L.check(lib.ipoc_affine_apply_f64(1, 1, self.N, self.nx, self.rank, self.nranks, p(n.fx), p(self.cx),
+                                              p(carries), p(seed), p(self.lam), p(self.ws_aff), self.nb_aff,
+                                              L.stream_ptr()))
+        self.cu_norm.copy_(self.x1[:, na].sum().sqrt().reshape(1))          # fixed rank order (ref :116)
+        self.hu.copy_(self.x1[:, na + 1].max().reshape(1))                  # (ref :158)
+        self.reg.copy_(self.rp * self.cu_norm)                              # (ref :117)
+
+    def _k2_reduce(self):
+        self.x2_mine.copy_(self.new.bwd_reduce(self.reg))
+
+    def _k2_apply(self, ST):
+        n, na = self.new, self.na
+        fc = n.bwd_apply(self.x2, ST)
+        self.x3_mine[:na].copy_(fc)
+        self.x3_mine[na:na + 1].copy_(n.pred)
+        self.x3_mine[na + 1:na + 2].copy_(n.feas.to(torch.float64))
+        if self.cons is not None:
+            p, lib = L.ptr, L.lib()
+            with torch.cuda.device(self.dev):
+                L.check(lib.ipoc_reductions_f64(self.N, self.nu, self.nc, 1, None, None, p(self.cons), None, None,
+                                                p(self.feas_l), None, None, p(self.ws_red), self.nb_red,
+                                                L.stream_ptr()))
+        self.x3_mine[na + 2:na + 3].copy_(self.feas_l.to(torch.float64))
+
+    def _k3_apply(self):
+        self.new.fwd_apply(self.x3[:, :self.na].contiguous())
+
+    # ---- the collective pass -------------------------------------------------------------------------------
+    def step(self, all_gather_into, ST):
+        """Enqueue one pass.  `all_gather_into(out (P, len), mine (len))` fills `out` with every rank's `mine`.
+        Results: lam, new.Kx, new.d, new.dx, new.du (segment), hu, cu_norm, and — after `scalars()` — the
+        horizon-wide pred / feasibility flags."""
+        self._k1_reduce()
+        all_gather_into(self.x1, self.x1_mine)          # exchange 1
+        self._k1_apply()
+        self._k2_reduce()
+        all_gather_into(self.x2, self.x2_mine)          # exchange 2
+        self._k2_apply(ST)
+        all_gather_into(self.x3, self.x3_mine)          # exchange 3
+        self._k3_apply()
+
+    def scalars(self):
+        """-> (pred (sum over ranks, fixed order), bwd_feasible (all ranks), traj_feasible (all ranks))."""
+        na = self.na
+        return (self.x3[:, na].sum(), bool((self.x3[:, na + 1] != 0).all()), bool((self.x3[:, na + 2] != 0).all()))
+
+    def capture(self, all_gather_into, ST):
+        """Record the whole pass, its three all-gathers included, into ONE CUDA graph (NCCL collectives are
+        graph-capturable); `replay()` then costs a single launch per pass on every rank."""
+        self.g_ST = L.dev_f64(ST, self.dev).clone()
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):          # warm-up outside the capture (allocator, communicator, lazy inits)
+            for _ in range(2):
+                self.step(all_gather_into, self.g_ST)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step(all_gather_into, self.g_ST)
+        self.graph = g
+        return self
+
+    def replay(self):
+        self.graph.replay()
+
+
+def pass_virtual_ranks(fx, fu, cx, cu, lamT, ru, Q, R, M, nranks, cons=None, rp=1.0):
+    """The time-sharded PASS with `nranks` virtual ranks on one GPU (fake all-gather between the phases) —
+    the single-GPU test of `SegmentPass`.  -> dict of horizon-wide results."""
+    N = fx.shape[0]
+    bounds = segment_bounds(N, nranks)
+    segs = [SegmentPass(fx[lo:hi], fu[lo:hi], cx[lo:hi], cu[lo:hi], lamT, ru[lo:hi], Q[lo:hi], R[lo:hi], M[lo:hi], r,
+                        nranks, None if cons is None else cons[lo:hi], rp) for r, (lo, hi) in enumerate(bounds)]
+    ST = Q[0].contiguous()
+    for s in segs:
+        s._k1_reduce()
+    x1 = torch.stack([s.x1_mine for s in segs])
+    for s in segs:
+        s.x1.copy_(x1)
+        s._k1_apply()
+        s._k2_reduce()
+    x2 = torch.stack([s.x2_mine for s in segs])
+    for s in segs:
+        s.x2.copy_(x2)
+        s._k2_apply(ST)
+    x3 = torch.stack([s.x3_mine for s in segs])
+    for s in segs:
+        s.x3.copy_(x3)
+        s._k3_apply()
+    pred, bwd_feas, traj_feas = segs[0].scalars()
+    return dict(lam=torch.cat([s.lam[:-1] for s in segs[:-1]] + [segs[-1].lam]),
+                dx=torch.cat([s.new.dx[:-1] for s in segs[:-1]] + [segs[-1].new.dx]),
+                du=torch.cat([s.new.du for s in segs]), Kx=torch.cat([s.new.Kx for s in segs]),
+                d=torch.cat([s.new.d for s in segs]), pred=pred, bwd_feasible=bwd_feas, traj_feasible=traj_feas,
+                hu=segs[0].hu.clone(), cu_norm=segs[0].cu_norm.clone())
+
+
 def newton_step_time_sharded(seg: SegmentNewton, reg, ST, all_gather):
     """Collective Newton step.  `all_gather(t)` returns the (P, len) stack of every rank's `t`.
     `ST`: terminal weight (= Q[0] of the global horizon, ref noc/par_interior_point_newton.py:73),
