@@ -421,8 +421,8 @@ def run_ours(args):
                 # (a) Newton step K2 + K3
                 if world > 1:
                     seg = sharded.SegmentNewton(fx_, fu_, ru_, Q_, R_, M_, rank, world)
-                    seg.capture(regs, ST)   # three local phases as CUDA graphs, two NCCL all-gathers between them
-                    fn_a = lambda: seg.step_graphed(gather_into)
+                    seg.capture_one(regs, ST, gather_into)   # 3 local phases + 2 NCCL all-gathers in ONE CUDA graph
+                    fn_a = seg.step_one
                 else:
                     fn_a = lambda: _noc.newton_step(fx_, fu_, ru_, Q_, R_, M_, regs)
                 rec["ms_per_newton_step_K2K3"] = timed(fn_a)
@@ -436,7 +436,7 @@ def run_ours(args):
                 rec["hbm_frac_of_aggregate_peak_pass"] = (ab_["total"] / (rec["ms_per_pass_K1K2K3K4_one_graph"] * 1e-3)
                                                           / 1e9 / (hbm_peak * world))
                 rec["collectives_per_pass"] = 0 if world == 1 else 3
-                rec["launch"] = ("K2+K3: 3 CUDA graphs + 2 NCCL all-gathers; pass: ONE CUDA graph incl. 3 NCCL all-gathers"
+                rec["launch"] = ("K2+K3: ONE CUDA graph incl. 2 NCCL all-gathers; pass: ONE CUDA graph incl. 3 NCCL all-gathers"
                                  if world > 1 else "K2+K3: eager API call; pass: one CUDA graph") + ", max over ranks"
                 if check:      # the sharded results of this rank's slice against the single-device scans
                     ref = _NP(full_[0], full_[1], cx_f, cu_f, lamT_, full_[2], full_[3], full_[4], full_[5], cons_f, rp=0.25)

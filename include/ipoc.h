@@ -85,6 +85,8 @@ void ipoc_set_literal_lqt(int on);
  * serial_top (<= 32, 0 = 8) shape the hierarchy.  ipoc_set_tuning with a non-zero mid_fanin or top_max
  * also selects the separate level kernels. */
 void ipoc_set_hier(int enabled, int group_warps, int serial_top);
+/* Leaf warps per SM the stand-alone affine scans are planned for (0 = default); experiment knob. */
+void ipoc_set_affine_occupancy(int warps_per_sm);
 
 /* ---- K2 + K3: one Newton step ----------------------------------------------------------
  * Replaces `par_Newton` (ref noc/par_interior_point_newton.py:107-124) from the regularisation
@@ -151,7 +153,7 @@ int ipoc_affine_scan_f64(int reverse, int transpose, int N, int nx, int batch,
  * Workspace: ipoc_workspace_bytes(IPOC_WS_COSTATES, N, nx, nu, batch). */
 int ipoc_costates_f64(int N, int nx, int nu, int batch,
                       const double* fx, const double* cx, const double* lamT, const double* cu,
-                      double* lam, double* cu_norm,
+                      double* lam, double* cu_norm, const int32_t* fresh /* may be NULL, see ipoc_plant_* */,
                       void* ws, size_t ws_bytes, ipoc_stream_t stream);
 
 /* ---- K2 + K3 + the glue of one accept/reject attempt, fused (ref :151-175) --------------------------------
@@ -339,15 +341,19 @@ int ipoc_plant_derivatives_f64(int plant, int N, int batch, double Ts, double bo
  * first/second derivatives of the Hamiltonian H = stage_cost + lam[k+1]' f(x,u), so the 130-double
  * `Derivatives` record never has to exist:  linearize (before the costate scan) -> fx, fu, cx, cu, lamT;
  * hamiltonian (after it, lam (batch,N+1,nx)) -> ru, Q, R, M. */
+/* `fresh` (int32 per problem, may be NULL = all): problems whose flag is 0 are skipped and keep their previous
+ * outputs — device-resident loops re-run an attempt on an UNCHANGED iterate after a rejection (ref :177-182) and
+ * must not pay for re-evaluating it. */
 int ipoc_plant_linearize_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
                              const double* x, const double* u, double* fx, double* fu, double* cx, double* cu,
-                             double* lamT, ipoc_stream_t stream);
+                             double* lamT, const int32_t* fresh, ipoc_stream_t stream);
 int ipoc_plant_hamiltonian_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
                                const double* x, const double* u, const double* lam,
-                               double* ru, double* Q, double* R, double* M, ipoc_stream_t stream);
+                               double* ru, double* Q, double* R, double* M, const int32_t* fresh,
+                               ipoc_stream_t stream);
 int ipoc_plant_cost_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
                         const double* x, const double* u, double* total_cost, int32_t* feasible,
-                        ipoc_stream_t stream);
+                        const int32_t* fresh, ipoc_stream_t stream);
 int ipoc_plant_rollout_f64(int plant, int N, int batch, double Ts, const double* x0, const double* u,
                            double* x, ipoc_stream_t stream);
 /* ipoc_plant_cost_f64 of the trial point (tx, tu) followed, in the same launch, by ipoc_attempt_finish_f64 with

@@ -17,9 +17,9 @@ unsigned long long g_launches = 0;
 Tuning g_tune = {0, 0, 0};
 int g_literal_lqt = 0;
 struct HierTuning {
-    int enabled, group_warps, serial_top;
+    int enabled, group_warps, serial_top, aff_warps_per_sm;
 };
-HierTuning g_hier = {1, 0, 0};
+HierTuning g_hier = {1, 0, 0, 0};
 // ---- per-launch profiler: one CUDA event after every kernel launch, on the launching stream ----
 constexpr int kMaxProf = 256;
 struct Prof {
@@ -433,6 +433,8 @@ int ipoc_workspace_init(void* ws, size_t ws_bytes, ipoc_stream_t stream) {
     return cudaMemsetAsync(ws, 0, n, (cudaStream_t)stream) == cudaSuccess ? IPOC_OK : IPOC_ECUDA;
 }
 
+void ipoc_set_affine_occupancy(int warps_per_sm) { g_hier.aff_warps_per_sm = warps_per_sm; }
+
 void ipoc_set_hier(int enabled, int group_warps, int serial_top) {
     g_hier.enabled = enabled ? 1 : 0;
     g_hier.group_warps = group_warps;
@@ -508,7 +510,7 @@ int ipoc_affine_scan_f64(int reverse, int transpose, int N, int nx, int batch, c
                          const double* seed, double* out, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
     CHECK_ARGS(N >= 1 && batch >= 1 && F && c && out && ws);
     CHECK_ALIGN(F); CHECK_ALIGN(c); CHECK_ALIGN(out); CHECK_ALIGN(ws);
-#define X(a) if (nx == a) return nx_affine_scan<a>(reverse, transpose, N, batch, F, c, seed, out, ws, ws_bytes, (cudaStream_t)stream, nullptr, 0, nullptr, nullptr);
+#define X(a) if (nx == a) return nx_affine_scan<a>(reverse, transpose, N, batch, F, c, seed, out, ws, ws_bytes, (cudaStream_t)stream, nullptr, 0, nullptr, nullptr, nullptr);
     IPOC_FOR_NX(X)
 #undef X
     return IPOC_EUNSUPPORTED_DIM;
@@ -690,7 +692,7 @@ int ipoc_affine_apply_f64(int reverse, int transpose, int N, int nx, int rank, i
 
 // ---- fused entry points: the same phases with their neighbouring reductions / glue as side jobs ----------
 int ipoc_costates_f64(int N, int nx, int nu, int batch, const double* fx, const double* cx, const double* lamT,
-                      const double* cu, double* lam, double* cu_norm, void* ws, size_t ws_bytes,
+                      const double* cu, double* lam, double* cu_norm, const int32_t* fresh, void* ws, size_t ws_bytes,
                       ipoc_stream_t stream) {
     CHECK_ARGS(N >= 1 && batch >= 1 && nu >= 1 && fx && cx && lam && ws && ((cu == nullptr) == (cu_norm == nullptr)));
     CHECK_ALIGN(fx); CHECK_ALIGN(cx); CHECK_ALIGN(lam); CHECK_ALIGN(ws);
@@ -699,7 +701,7 @@ int ipoc_costates_f64(int N, int nx, int nu, int batch, const double* fx, const 
     const size_t scan_bytes = ipoc_workspace_bytes(IPOC_WS_AFFINE_SCAN, N, nx, nu, batch);
     if (scan_bytes == 0) return IPOC_EUNSUPPORTED_DIM;
     if (ws_bytes < scan_bytes) return IPOC_EWORKSPACE;
-#define X(a) if (nx == a) rc = nx_affine_scan<a>(1, 1, N, batch, fx, cx, lamT, lam, ws, ws_bytes, st_, cu, nu, cu_norm, &handled);
+#define X(a) if (nx == a) rc = nx_affine_scan<a>(1, 1, N, batch, fx, cx, lamT, lam, ws, ws_bytes, st_, cu, nu, cu_norm, &handled, fresh);
     IPOC_FOR_NX(X)
 #undef X
     if (rc != IPOC_OK) return rc;

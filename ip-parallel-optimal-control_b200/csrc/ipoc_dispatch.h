@@ -38,7 +38,7 @@ template <int NX> size_t nx_ws_bytes(int kind, int N, int batch, bool sharded);
 template <int NX>
 int nx_affine_scan(int reverse, int transpose, int N, int batch, const double* F, const double* c, const double* seed,
                    double* out, void* ws, size_t ws_bytes, cudaStream_t st, const double* sq_src, int sq_width,
-                   double* cu_norm, int* handled);
+                   double* cu_norm, int* handled, const int32_t* fresh);
 template <int NX>
 int nx_affine_reduce(int reverse, int transpose, int N, const double* F, const double* c, double* carry_out, void* ws,
                      size_t ws_bytes, cudaStream_t st);

@@ -47,6 +47,7 @@ struct HierTuning {
     int enabled;      // 1 (default): levels above the warps are completed inside the leaf kernels (last arriver)
     int group_warps;  // warps per group (0 = 32)
     int serial_top;   // up to this many groups the top is a serial chain of `apply` (0 = 8)
+    int aff_warps_per_sm;   // leaf warps per SM the stand-alone affine scans (K1) are planned for (0 = default)
 };
 extern HierTuning g_hier;
 void prof_mark(const char* name, cudaStream_t st);   // no-op unless profiling is armed
@@ -68,6 +69,9 @@ constexpr int kMidThreads = 128;
 constexpr int kTopThreads = 256;
 constexpr int kTargetThreads = 148 * 256;       // K2/K3: 8 warps per SM (register-limited)
 constexpr int kAffTargetThreads = 148 * 256;    // K1: light kernels are bytes-in-flight limited
+static inline int aff_target_threads() {
+    return g_hier.aff_warps_per_sm > 0 ? 148 * 32 * g_hier.aff_warps_per_sm : kAffTargetThreads;
+}
 
 // ------------------------------------------------------------------ SoA helpers
 template <class T>
@@ -219,14 +223,29 @@ struct SideJobs {
 IPOC_DEV double nan_max_d(double a, double c) {
     return (a != a || c != c) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(a, c);
 }
+// The partials come from L2 (other SMs wrote them): loads are issued eight at a time before they are consumed, so
+// a fold over n partials costs n/256 memory round trips instead of n/32; the accumulation order is fixed.
+template <class T, class F>
+IPOC_DEV void fold_partials(const T* p, int n, int lane, F&& consume) {
+    constexpr int U = 8;
+    for (int j0 = lane; j0 < n; j0 += 32 * U) {
+        T v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int j = j0 + 32 * k;
+            if (j < n) v[k] = __ldcg(p + j);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+            if (j0 + 32 * k < n) consume(v[k]);
+    }
+}
 IPOC_DEV void side_finish(const SideJobs& sj, int b, int lane) {   // one full warp
     if (sj.pred != nullptr) {
         double acc = 0.0;
         int f = 1;
-        for (int j = lane; j < sj.n; j += 32) {
-            acc += __ldcg(sj.pred_part + (size_t)b * sj.n + j);
-            f &= __ldcg(sj.feas_part + (size_t)b * sj.n + j);
-        }
+        fold_partials(sj.pred_part + (size_t)b * sj.n, sj.n, lane, [&](double v) { acc += v; });
+        fold_partials(sj.feas_part + (size_t)b * sj.n, sj.n, lane, [&](int v) { f &= v; });
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -239,14 +258,14 @@ IPOC_DEV void side_finish(const SideJobs& sj, int b, int lane) {   // one full w
     }
     if (sj.cu_norm != nullptr) {
         double acc = 0.0;
-        for (int j = lane; j < sj.n; j += 32) acc += __ldcg(sj.sq_part + (size_t)b * sj.n + j);
+        fold_partials(sj.sq_part + (size_t)b * sj.n, sj.n, lane, [&](double v) { acc += v; });
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) sj.cu_norm[b] = sqrt(acc);
     }
     if (sj.hu != nullptr) {
         double m = 0.0;
-        for (int j = lane; j < sj.n; j += 32) m = nan_max_d(m, __ldcg(sj.mx_part + (size_t)b * sj.n + j));
+        fold_partials(sj.mx_part + (size_t)b * sj.n, sj.n, lane, [&](double v) { m = nan_max_d(m, v); });
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = nan_max_d(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (lane == 0) sj.hu[b] = m;
@@ -582,25 +601,73 @@ struct RowMap {
     int S, T0;
 };
 
-// Copy step j of every lane-row r of one input array into the stage: the warp cooperates, `CPR`
-// granules per row, consecutive lanes on consecutive granules of the same row.  32-bit index
-// arithmetic relative to the warp's first row, one wide multiply-add per copy.
+// ---- TMA (bulk async copy) staging -----------------------------------------------------------------------
+// A row whose size is a multiple of 16 bytes travels as ONE `cp.async.bulk` (TMA, SASS: UBLKCP) issued by the
+// lane that owns it — source and destination are 16-byte aligned by construction — and completes on the
+// stage's mbarrier (transaction bytes; SASS: SYNCS).  Rows of 8 bytes (R and ru when nu = 1) cannot be bulk
+// copies (16-byte granularity) and keep the per-granule cp.async path and its wait_group.  Compared with the
+// 16-byte cp.async granules this is one copy instruction per row instead of eight for an nx = 4 matrix row.
+#ifndef IPOC_TMA
+#define IPOC_TMA 0
+#endif
+IPOC_DEV void mbar_init(unsigned mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
+}
+IPOC_DEV void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
+IPOC_DEV void mbar_wait(unsigned mbar, unsigned parity) {
+    unsigned done = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1 << 24)) __trap();   // a lost transaction must fail the launch, never hang the GPU
+    }
+}
 template <int CNT>
-IPOC_DEV void issue_rows(unsigned dst_arr, const double* __restrict__ g, const RowMap& m, int j, int lane) {
+__host__ __device__ constexpr bool row_is_bulk() { return IPOC_TMA != 0 && (CNT * 8) % 16 == 0; }
+template <int CNT>
+__host__ __device__ constexpr int row_bulk_bytes() { return row_is_bulk<CNT>() ? CNT * 8 : 0; }
+
+// Copy step j of every lane-row r of one input array into the stage.  Bulk rows: lane r copies its own row.
+// Other rows: the warp cooperates, `CPR` granules per row, consecutive lanes on consecutive granules of the
+// same row.  32-bit index arithmetic relative to the warp's first row, one wide multiply-add per copy.
+template <int CNT>
+IPOC_DEV void issue_rows(unsigned dst_arr, unsigned mbar, const double* __restrict__ g, const RowMap& m, int j, int lane) {
     constexpr int G = row_gran(CNT), CPR = row_cpr(CNT), PITCH = row_pitch(CNT);
     const char* gbase = reinterpret_cast<const char*>(g + m.tb * CNT);
-#pragma unroll
-    for (int i = 0; i < CPR; ++i) {
-        const int idx = lane + 32 * i;
-        const int r = idx / CPR, part = idx % CPR;
-        const int k = r * m.S + j;
+    if constexpr (row_is_bulk<CNT>()) {
+        const int k = lane * m.S + j;
         if (k < m.remc) {
-            const char* src = gbase + (long long)k * (CNT * 8) + part * G;
-            const unsigned dst = dst_arr + r * PITCH + part * G;
-            if constexpr (G == 16)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
-            else
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
+            const char* src = gbase + (long long)k * (CNT * 8);
+            const unsigned dst = dst_arr + lane * PITCH;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                         "l"(src), "n"(CNT * 8), "r"(mbar)
+                         : "memory");
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const int idx = lane + 32 * i;
+            const int r = idx / CPR, part = idx % CPR;
+            const int k = r * m.S + j;
+            if (k < m.remc) {
+                const char* src = gbase + (long long)k * (CNT * 8) + part * G;
+                const unsigned dst = dst_arr + r * PITCH + part * G;
+                if constexpr (G == 16)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+                else
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
+            }
         }
     }
 }
@@ -625,11 +692,14 @@ struct WarpSmem {
     RowMap map;
     char* stage0;
     unsigned stage0_s;   // the same address in the shared window (computed once, not per copy)
+    unsigned mbar_s;     // kMbarBytes at the end of the warp's area: one mbarrier per stage of the ring
 };
+constexpr int kMbarBytes = 64;   // up to 8 stages
 IPOC_DEV WarpSmem warp_smem(char* smem, const Geom& g, int warp_in_block, long long wg) {
     WarpSmem w;
     w.stage0 = smem + (size_t)warp_in_block * g.pw_bytes;
     w.stage0_s = (unsigned)__cvta_generic_to_shared(w.stage0);
+    w.mbar_s = w.stage0_s + (unsigned)g.pw_bytes - (unsigned)kMbarBytes;
     long long rem;
     if (g.per_lane) {
         w.map.tb = wg * 32 * (long long)g.N;
@@ -657,23 +727,47 @@ IPOC_DEV WarpSmem warp_smem(char* smem, const Geom& g, int warp_in_block, long l
 template <int NS, class Ld, class F1, class F2>
 IPOC_DEV void staged_walk(const Ld& ld, const WarpSmem& w, int T, int len, int lane, bool reverse, F1&& fetch,
                           F2&& compute) {
+    const int bulk_row = ld.bulk_row_bytes();   // bytes per row that travel as bulk copies (0: cp.async only)
+    if (IPOC_TMA) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) mbar_init(w.mbar_s + 8 * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncwarp();
+    }
+    // all copies of step j into ring slot `slot`; lane 0 arms the slot's mbarrier with the bytes of the valid rows
+    auto issue = [&](int slot, int j) {
+        const unsigned mb = w.mbar_s + 8 * slot;
+        if (IPOC_TMA && lane == 0) {
+            const int nvalid = (j < w.map.remc) ? min(32, (w.map.remc - j - 1) / w.map.S + 1) : 0;
+            mbar_expect_tx(mb, (unsigned)(nvalid * bulk_row));
+        }
+        ld.issue(w.stage0_s + slot * Ld::STAGE_BYTES, mb, w.map, j, lane);
+    };
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        if (s < T) ld.issue(w.stage0_s + s * Ld::STAGE_BYTES, w.map, reverse ? T - 1 - s : s, lane);
+        if (s < T) issue(s, reverse ? T - 1 - s : s);
         cp_async_commit();
     }
     int slot = 0;
+    unsigned parity = 0;
     for (int it = 0; it < T; ++it) {
         const int j = reverse ? T - 1 - it : it;
         cp_async_wait<NS - 1>();
+        if (IPOC_TMA) mbar_wait(w.mbar_s + 8 * slot, parity);
         __syncwarp();
         if (j < len) fetch(w.stage0 + slot * Ld::STAGE_BYTES);
         __syncwarp();
-        if (it + NS < T)
-            ld.issue(w.stage0_s + slot * Ld::STAGE_BYTES, w.map, reverse ? j - NS : j + NS, lane);
+        if (it + NS < T) issue(slot, reverse ? j - NS : j + NS);
         cp_async_commit();
         if (j < len) compute(j);
-        slot = (slot + 1 == NS) ? 0 : slot + 1;
+        if (slot + 1 == NS) {
+            slot = 0;
+            parity ^= 1u;
+        } else {
+            ++slot;
+        }
     }
 }
 
@@ -694,13 +788,16 @@ struct NewtonLoader {
     static constexpr int O_FX = 0, O_FU = O_FX + arr_bytes(NX * NX), O_Q = O_FU + arr_bytes(NX * NU),
                          O_R = O_Q + arr_bytes(NX * NX), O_M = O_R + arr_bytes(NU * NU),
                          O_RU = O_M + arr_bytes(NX * NU), STAGE_BYTES = O_RU + arr_bytes(NU);
-    IPOC_DEV void issue(unsigned st, const RowMap& m, int j, int lane) const {
-        issue_rows<NX * NX>(st + O_FX, fx, m, j, lane);
-        issue_rows<NX * NU>(st + O_FU, fu, m, j, lane);
-        issue_rows<NX * NX>(st + O_Q, Q, m, j, lane);
-        issue_rows<NU * NU>(st + O_R, R, m, j, lane);
-        issue_rows<NX * NU>(st + O_M, M, m, j, lane);
-        issue_rows<NU>(st + O_RU, ru, m, j, lane);
+    IPOC_DEV int bulk_row_bytes() const {
+        return 2 * row_bulk_bytes<NX * NX>() + 2 * row_bulk_bytes<NX * NU>() + row_bulk_bytes<NU * NU>() + row_bulk_bytes<NU>();
+    }
+    IPOC_DEV void issue(unsigned st, unsigned mb, const RowMap& m, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_FX, mb, fx, m, j, lane);
+        issue_rows<NX * NU>(st + O_FU, mb, fu, m, j, lane);
+        issue_rows<NX * NX>(st + O_Q, mb, Q, m, j, lane);
+        issue_rows<NU * NU>(st + O_R, mb, R, m, j, lane);
+        issue_rows<NX * NU>(st + O_M, mb, M, m, j, lane);
+        issue_rows<NU>(st + O_RU, mb, ru, m, j, lane);
     }
     // per-lane constant fetched ONCE before the walk (a global load inside the step loop would expose
     // its full latency every step: 16 % of the stall samples in profiles/r01)
@@ -800,15 +897,19 @@ struct LqtLoader {
     static constexpr int O_A = 0, O_B = O_A + arr_bytes(NX * NX), O_C = O_B + arr_bytes(NX * NU),
                          O_X = O_C + arr_bytes(NX), O_U = O_X + arr_bytes(NX * NX), O_M = O_U + arr_bytes(NU * NU),
                          O_Q = O_M + arr_bytes(NX * NU), O_P = O_Q + arr_bytes(NX), STAGE_BYTES = O_P + arr_bytes(NU);
-    IPOC_DEV void issue(unsigned st, const RowMap& m, int j, int lane) const {
-        issue_rows<NX * NX>(st + O_A, A, m, j, lane);
-        issue_rows<NX * NU>(st + O_B, B, m, j, lane);
-        if (c != nullptr) issue_rows<NX>(st + O_C, c, m, j, lane);
-        issue_rows<NX * NX>(st + O_X, X, m, j, lane);
-        issue_rows<NU * NU>(st + O_U, U, m, j, lane);
-        issue_rows<NX * NU>(st + O_M, M, m, j, lane);
-        issue_rows<NX>(st + O_Q, q, m, j, lane);
-        issue_rows<NU>(st + O_P, p, m, j, lane);
+    IPOC_DEV int bulk_row_bytes() const {
+        return 2 * row_bulk_bytes<NX * NX>() + 2 * row_bulk_bytes<NX * NU>() + row_bulk_bytes<NU * NU>() +
+               (c != nullptr ? 2 : 1) * row_bulk_bytes<NX>() + row_bulk_bytes<NU>();
+    }
+    IPOC_DEV void issue(unsigned st, unsigned mb, const RowMap& m, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_A, mb, A, m, j, lane);
+        issue_rows<NX * NU>(st + O_B, mb, B, m, j, lane);
+        if (c != nullptr) issue_rows<NX>(st + O_C, mb, c, m, j, lane);
+        issue_rows<NX * NX>(st + O_X, mb, X, m, j, lane);
+        issue_rows<NU * NU>(st + O_U, mb, U, m, j, lane);
+        issue_rows<NX * NU>(st + O_M, mb, M, m, j, lane);
+        issue_rows<NX>(st + O_Q, mb, q, m, j, lane);
+        issue_rows<NU>(st + O_P, mb, p, m, j, lane);
     }
     IPOC_DEV double aux(int) const { return 0.0; }
     IPOC_DEV double ru_absmax(const char*, int) const { return 0.0; }
@@ -844,12 +945,16 @@ struct FwdLoader {
     const double *A, *B, *c, *Kx, *d;
     static constexpr int O_A = 0, O_B = O_A + arr_bytes(NX * NX), O_C = O_B + arr_bytes(NX * NU),
                          O_K = O_C + arr_bytes(NX), O_D = O_K + arr_bytes(NU * NX), STAGE_BYTES = O_D + arr_bytes(NU);
-    IPOC_DEV void issue(unsigned st, const RowMap& m, int j, int lane) const {
-        issue_rows<NX * NX>(st + O_A, A, m, j, lane);
-        issue_rows<NX * NU>(st + O_B, B, m, j, lane);
-        if (c != nullptr) issue_rows<NX>(st + O_C, c, m, j, lane);
-        issue_rows<NU * NX>(st + O_K, Kx, m, j, lane);
-        issue_rows<NU>(st + O_D, d, m, j, lane);
+    IPOC_DEV int bulk_row_bytes() const {
+        return row_bulk_bytes<NX * NX>() + row_bulk_bytes<NX * NU>() + (c != nullptr ? row_bulk_bytes<NX>() : 0) +
+               row_bulk_bytes<NU * NX>() + row_bulk_bytes<NU>();
+    }
+    IPOC_DEV void issue(unsigned st, unsigned mb, const RowMap& m, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_A, mb, A, m, j, lane);
+        issue_rows<NX * NU>(st + O_B, mb, B, m, j, lane);
+        if (c != nullptr) issue_rows<NX>(st + O_C, mb, c, m, j, lane);
+        issue_rows<NU * NX>(st + O_K, mb, Kx, m, j, lane);
+        issue_rows<NU>(st + O_D, mb, d, m, j, lane);
     }
 };
 
@@ -858,9 +963,10 @@ template <int NX>
 struct AffLoader {
     const double *F, *c;
     static constexpr int O_F = 0, O_C = O_F + arr_bytes(NX * NX), STAGE_BYTES = O_C + arr_bytes(NX);
-    IPOC_DEV void issue(unsigned st, const RowMap& m, int j, int lane) const {
-        issue_rows<NX * NX>(st + O_F, F, m, j, lane);
-        issue_rows<NX>(st + O_C, c, m, j, lane);
+    IPOC_DEV int bulk_row_bytes() const { return row_bulk_bytes<NX * NX>() + row_bulk_bytes<NX>(); }
+    IPOC_DEV void issue(unsigned st, unsigned mb, const RowMap& m, int j, int lane) const {
+        issue_rows<NX * NX>(st + O_F, mb, F, m, j, lane);
+        issue_rows<NX>(st + O_C, mb, c, m, j, lane);
     }
     IPOC_DEV void read(AffElem<NX>& e, const char* st, int lane, int transpose) const {
         double Fm[NX][NX], cv[NX];
@@ -1208,7 +1314,7 @@ k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, 
         if (!warp_arrive_last(tail.cnt + L.b, (unsigned)g.nW, lane)) return;
     int traj_ok = 1;
     if (tail.cons != nullptr) {
-        for (int jw = lane; jw < g.nW; jw += 32) traj_ok &= __ldcg(tail.cons_part + (size_t)L.b * g.nW + jw);
+        fold_partials(tail.cons_part + (size_t)L.b * g.nW, g.nW, lane, [&](int v) { traj_ok &= v; });
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) traj_ok &= __shfl_xor_sync(0xffffffffu, traj_ok, o);
         if (lane == 0) tail.traj_feasible[L.b] = traj_ok;
@@ -1267,12 +1373,15 @@ template <int NX>
 __global__ void __launch_bounds__(kLeafThreads)
 k_aff_leaf_up(AffLoader<NX> ld, int reverse, int transpose, Geom g, double* __restrict__ incl, size_t istride,
               double* __restrict__ agg1, size_t a1stride, Hier h, SideJobs side, const double* __restrict__ sq_src,
-              int sq_width, double* __restrict__ sq_part) {
+              int sq_width, double* __restrict__ sq_part, const int32_t* __restrict__ fresh) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     if (wg >= total_warps(g)) return;
     const Lane L = lane_info(g, wg, lane);
+    // sequences whose inputs did not change since the last scan keep their stored results (no warp of a skipped
+    // sequence arrives anywhere, so its counters stay at zero)
+    if (fresh != nullptr && !g.per_lane && fresh[L.b] == 0) return;
     const WarpSmem w = warp_smem(smem, g, wib, wg);
     AffElem<NX> a;
     AffOp<NX>::identity(a);
@@ -1306,13 +1415,15 @@ k_aff_leaf_up(AffLoader<NX> ld, int reverse, int transpose, Geom g, double* __re
 template <int NX>
 __global__ void __launch_bounds__(kLeafThreads)
 k_aff_leaf_down(AffLoader<NX> ld, int reverse, int transpose, Geom g, const double* __restrict__ incl,
-                size_t istride, const double* __restrict__ wvals, size_t wvstride, double* __restrict__ out, HierIn hin) {
+                size_t istride, const double* __restrict__ wvals, size_t wvstride, double* __restrict__ out, HierIn hin,
+                const int32_t* __restrict__ fresh) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // reverse grid order relative to the up-sweep: start with what it left in L2
     const long long wg = total_warps(g) - 1 - ((long long)blockIdx.x * (blockDim.x >> 5) + wib);
     if (wg < 0) return;
     const Lane L = lane_info(g, wg, lane);
+    if (fresh != nullptr && !g.per_lane && fresh[L.b] == 0) return;
     const WarpSmem w = warp_smem(smem, g, wib, wg);
     const int N = g.N;
     AffVal<NX> x;
@@ -1379,7 +1490,11 @@ struct Plan {
 };
 
 // force_scan: time-sharded mode always wants the segment total, hence at least one level.
-static Plan make_plan(int N, int batch, bool force_scan = false, int target_threads = kTargetThreads) {
+// lat_heuristic: the Riccati plans trade leaf length against the number of warp totals their levels must scan
+// (measured optimum below); the stand-alone affine scans complete their cheap levels inside the leaf kernels and
+// are planned for occupancy alone.
+static Plan make_plan(int N, int batch, bool force_scan = false, int target_threads = kTargetThreads,
+                      bool lat_heuristic = true) {
     Plan p{};
     Geom& g = p.g;
     g.N = N;
@@ -1401,7 +1516,7 @@ static Plan make_plan(int N, int batch, bool force_scan = false, int target_thre
             // chunks of a multiple of 8 steps keep the staged rows sector-aligned (measurably faster)
             const long long t_lat = (long long)(sqrt((double)N) / 256.0 + 0.5) * 8;
             if (t > 4) t = ((t + 7) / 8) * 8;
-            if (t < t_lat) t = t_lat;
+            if (lat_heuristic && t < t_lat) t = t_lat;
             T0 = (int)(t < 4 ? 4 : t);
         }
     }
@@ -1572,7 +1687,7 @@ static LeafLaunch leaf_launch(const Plan& p, int stage_bytes, size_t scratch_byt
     // balance the single wave better.
     size_t body = (size_t)stage_bytes * nstages;   // stage ring; the scan scratch reuses the area after the walk
     if (body < scratch_bytes) body = scratch_bytes;
-    const size_t per_warp = body;
+    const size_t per_warp = body + kMbarBytes;      // + the ring's mbarriers (never overlaid)
     const size_t sm_bytes = 228 * 1024;
     int best_wpc = 1, best_warps = 0;
     for (int wpc = 1; wpc <= kLeafThreads / 32; wpc *= 2) {
@@ -1918,7 +2033,7 @@ static int lqt_fwd_impl(int N, int batch, const double* A, const double* B, cons
 template <int NX>
 static int aff_up(const Plan& p, const ScanWs& w, const double* F, const double* c, int reverse, int transpose,
                   cudaStream_t st, const Hier& h, const double* sq_src = nullptr, int sq_width = 0,
-                  double* cu_norm = nullptr) {
+                  double* cu_norm = nullptr, const int32_t* fresh = nullptr) {
     AffLoader<NX> ld{F, c};
     const LeafLaunch ll = leaf_launch(p, AffLoader<NX>::STAGE_BYTES, scan_scratch_bytes<AffOp<NX>>(), IPOC_NS_LIGHT);
     Geom g = p.g;
@@ -1933,13 +2048,13 @@ static int aff_up(const Plan& p, const ScanWs& w, const double* F, const double*
         side.cu_norm = cu_norm;
     }
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, reverse, transpose, g, w.incl, (size_t)p.slots, w.agg[0],
-                                              (size_t)p.g.batch * p.g.nW, h, side, sq_src, sq_width, sq_part);
+                                              (size_t)p.g.batch * p.g.nW, h, side, sq_src, sq_width, sq_part, fresh);
     IPOC_LAUNCH_CHECK_N("k_aff_leaf_up", st);
     return IPOC_OK;
 }
 template <int NX>
 static int aff_down(const Plan& p, const ScanWs& w, const double* F, const double* c, int reverse, int transpose,
-                    double* out, cudaStream_t st, const HierIn& hin) {
+                    double* out, cudaStream_t st, const HierIn& hin, const int32_t* fresh = nullptr) {
     const double* vals;
     size_t vstride;
     leaf_values(p, w, vals, vstride);
@@ -1950,7 +2065,7 @@ static int aff_down(const Plan& p, const ScanWs& w, const double* F, const doubl
     auto kern = k_aff_leaf_down<NX>;
     if (int rc = set_smem(kern, ll.smem, ll.threads)) return rc;
     kern<<<ll.grid, ll.threads, ll.smem, st>>>(ld, reverse, transpose, g, w.incl, (size_t)p.slots, vals, vstride,
-                                              out, hin);
+                                              out, hin, fresh);
     IPOC_LAUNCH_CHECK_N("k_aff_leaf_down", st);
     return IPOC_OK;
 }
@@ -1959,8 +2074,8 @@ static int aff_down(const Plan& p, const ScanWs& w, const double* F, const doubl
 template <int NX>
 static int affine_scan_impl(int reverse, int transpose, int N, int batch, const double* F, const double* c,
                             const double* seed, double* out, void* ws, size_t ws_bytes, cudaStream_t st,
-                            const double* sq_src, int sq_width, double* cu_norm, int* handled) {
-    const Plan p = make_plan(N, batch, false, kAffTargetThreads);
+                            const double* sq_src, int sq_width, double* cu_norm, int* handled, const int32_t* fresh) {
+    const Plan p = make_plan(N, batch, false, aff_target_threads(), g_hier.aff_warps_per_sm <= 0);
     Bump bp{(char*)ws, (size_t)kCtrlBytes, ws_bytes, false};
     ScanWs w;
     carve_scan(bp, p, AffElem<NX>::ESZ, NX, w);
@@ -1977,7 +2092,8 @@ static int affine_scan_impl(int reverse, int transpose, int N, int batch, const 
         hin = make_hier_in(p, w);
         const bool fold = sq_src != nullptr;
         if (fold && handled != nullptr) *handled |= IPOC_X_NORM;
-        if (int rc = aff_up<NX>(p, w, F, c, reverse, transpose, st, h, fold ? sq_src : nullptr, sq_width, cu_norm))
+        if (p.g.per_lane || (p.nlev > 0 && !p.hier)) fresh = nullptr;   // masks are carried by the in-kernel plans only
+        if (int rc = aff_up<NX>(p, w, F, c, reverse, transpose, st, h, fold ? sq_src : nullptr, sq_width, cu_norm, fresh))
             return rc;
         if (p.nlev > 0 && !p.hier) {
             SideJobs side{};
@@ -1989,7 +2105,7 @@ static int affine_scan_impl(int reverse, int transpose, int N, int batch, const 
             if (int rc = run_levels<AffOp<NX>>(p, w, false, false, st, side)) return rc;
         }
     }
-    return aff_down<NX>(p, w, F, c, reverse, transpose, out, st, hin);
+    return aff_down<NX>(p, w, F, c, reverse, transpose, out, st, hin, p.g.per_lane ? nullptr : fresh);
 }
 
 // ---- time-sharded split-phase implementations ----------------------------------------------
@@ -2153,8 +2269,9 @@ static int affine_apply_impl(int reverse, int transpose, int N, int rank, int nr
 
 template <int NX>
 static size_t ws_bytes_impl(int kind, int N, int batch, bool sharded) {
-    const Plan p = make_plan(N, sharded ? 1 : batch, sharded,
-                             (kind == IPOC_WS_AFFINE_SCAN && !sharded) ? kAffTargetThreads : kTargetThreads);
+    const bool aff = kind == IPOC_WS_AFFINE_SCAN && !sharded;
+    const Plan p = make_plan(N, sharded ? 1 : batch, sharded, aff ? aff_target_threads() : kTargetThreads,
+                             !(aff && g_hier.aff_warps_per_sm > 0));
     Bump bp{nullptr, (size_t)kCtrlBytes, 0, true};
     if (kind == IPOC_WS_AFFINE_SCAN) {
         ScanWs w;

@@ -63,9 +63,9 @@ template <> size_t nx_ws_bytes<NXc>(int kind, int N, int batch, bool sharded) {
 template <>
 int nx_affine_scan<NXc>(int reverse, int transpose, int N, int batch, const double* F, const double* c,
                         const double* seed, double* out, void* ws, size_t ws_bytes, cudaStream_t st,
-                        const double* sq_src, int sq_width, double* cu_norm, int* handled) {
+                        const double* sq_src, int sq_width, double* cu_norm, int* handled, const int32_t* fresh) {
     return affine_scan_impl<NXc>(reverse, transpose, N, batch, F, c, seed, out, ws, ws_bytes, st, sq_src, sq_width, cu_norm,
-                                 handled);
+                                 handled, fresh);
 }
 template <>
 int nx_affine_reduce<NXc>(int reverse, int transpose, int N, const double* F, const double* c, double* carry_out,

@@ -164,12 +164,13 @@ __global__ void __launch_bounds__(128)
 k_plant_linearize(PlantParams pp, const double* __restrict__ bp_ptr, int N, int batch,
                   const double* __restrict__ X, const double* __restrict__ U, double* __restrict__ fx,
                   double* __restrict__ fu, double* __restrict__ cx, double* __restrict__ cu,
-                  double* __restrict__ lamT) {
+                  double* __restrict__ lamT, const int32_t* __restrict__ fresh) {
     constexpr int NX = P::NX, NU = P::NU, NV = NX + NU;
     using J = Jet<NV>;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)batch * N) return;
     const int b = (int)(g / N), k = (int)(g % N);
+    if (fresh != nullptr && fresh[b] == 0) return;   // iterate unchanged since the last evaluation: outputs still valid
     const double bp = *bp_ptr;
     const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
     J x[NX], u[NU];
@@ -213,12 +214,13 @@ __global__ void __launch_bounds__(128)
 k_plant_hamiltonian(PlantParams pp, const double* __restrict__ bp_ptr, int N, int batch,
                     const double* __restrict__ X, const double* __restrict__ U, const double* __restrict__ lam,
                     double* __restrict__ ru, double* __restrict__ Q, double* __restrict__ R,
-                    double* __restrict__ M) {
+                    double* __restrict__ M, const int32_t* __restrict__ fresh) {
     constexpr int NX = P::NX, NU = P::NU, NV = NX + NU;
     using J = Jet<NV>;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)batch * N) return;
     const int b = (int)(g / N), k = (int)(g % N);
+    if (fresh != nullptr && fresh[b] == 0) return;
     const double bp = *bp_ptr;
     const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
     const double* lp = lam + ((size_t)b * (N + 1) + k + 1) * NX;
@@ -259,11 +261,12 @@ template <class P>
 __global__ void __launch_bounds__(1024)
 k_plant_cost(PlantParams pp, const double* __restrict__ bp_ptr, int N, const double* __restrict__ X,
              const double* __restrict__ U, double* __restrict__ total, int32_t* __restrict__ feasible, int finish,
-             FinishIO fin) {
+             FinishIO fin, const int32_t* __restrict__ fresh) {
     constexpr int NX = P::NX, NU = P::NU;
     __shared__ double s_sum[32];
     __shared__ int s_ok[32];
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (fresh != nullptr && fresh[b] == 0) return;
     if (finish && !fin.active[b]) {   // frozen member of a device-resident loop: nothing to evaluate
         if (t == 0) fin.advanced[b] = 0;
         return;
@@ -356,31 +359,33 @@ static int derivs_impl(PlantParams pp, const double* bp, int N, int batch, const
 }
 template <class P>
 static int linearize_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
-                          double* fx, double* fu, double* cx, double* cu, double* lamT, cudaStream_t st) {
+                          double* fx, double* fu, double* cx, double* cu, double* lamT, const int32_t* fresh,
+                          cudaStream_t st) {
     const long long n = (long long)N * batch;
-    k_plant_linearize<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pp, bp, N, batch, X, U, fx, fu, cx, cu, lamT);
+    k_plant_linearize<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pp, bp, N, batch, X, U, fx, fu, cx, cu, lamT, fresh);
     PLANT_CHECK(st);
     return IPOC_OK;
 }
 template <class P>
 static int hamiltonian_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
-                            const double* lam, double* ru, double* Q, double* R, double* M, cudaStream_t st) {
+                            const double* lam, double* ru, double* Q, double* R, double* M, const int32_t* fresh,
+                            cudaStream_t st) {
     const long long n = (long long)N * batch;
-    k_plant_hamiltonian<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pp, bp, N, batch, X, U, lam, ru, Q, R, M);
+    k_plant_hamiltonian<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pp, bp, N, batch, X, U, lam, ru, Q, R, M, fresh);
     PLANT_CHECK(st);
     return IPOC_OK;
 }
 template <class P>
 static int cost_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
-                     double* total, int32_t* feasible, cudaStream_t st) {
-    k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, 0, FinishIO{});
+                     double* total, int32_t* feasible, const int32_t* fresh, cudaStream_t st) {
+    k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, 0, FinishIO{}, fresh);
     PLANT_CHECK(st);
     return IPOC_OK;
 }
 template <class P>
 static int cost_finish_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
                             double* total, int32_t* feasible, const FinishIO& fin, cudaStream_t st) {
-    k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, 1, fin);
+    k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, 1, fin, nullptr);
     PLANT_CHECK(st);
     return IPOC_OK;
 }
@@ -421,33 +426,34 @@ int ipoc_plant_derivatives_f64(int plant, int N, int batch, double Ts, double bo
 
 int ipoc_plant_linearize_f64(int plant, int N, int batch, double Ts, double bound, const double* bp, const double* x,
                              const double* u, double* fx, double* fu, double* cx, double* cu, double* lamT,
-                             ipoc_stream_t stream) {
+                             const int32_t* fresh, ipoc_stream_t stream) {
     if (N < 1 || batch < 1 || !bp || !x || !u || !fx || !fu || !cx || !cu) return IPOC_EINVAL;
     const PlantParams pp{Ts, bound};
     cudaStream_t st = (cudaStream_t)stream;
-    if (plant == IPOC_PLANT_PENDULUM) return linearize_impl<Pendulum>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, st);
-    if (plant == IPOC_PLANT_CARTPOLE) return linearize_impl<Cartpole>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, st);
+    if (plant == IPOC_PLANT_PENDULUM) return linearize_impl<Pendulum>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, fresh, st);
+    if (plant == IPOC_PLANT_CARTPOLE) return linearize_impl<Cartpole>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, fresh, st);
     return IPOC_EINVAL;
 }
 
 int ipoc_plant_hamiltonian_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
                                const double* x, const double* u, const double* lam, double* ru, double* Q,
-                               double* R, double* M, ipoc_stream_t stream) {
+                               double* R, double* M, const int32_t* fresh, ipoc_stream_t stream) {
     if (N < 1 || batch < 1 || !bp || !x || !u || !lam || !ru || !Q || !R || !M) return IPOC_EINVAL;
     const PlantParams pp{Ts, bound};
     cudaStream_t st = (cudaStream_t)stream;
-    if (plant == IPOC_PLANT_PENDULUM) return hamiltonian_impl<Pendulum>(pp, bp, N, batch, x, u, lam, ru, Q, R, M, st);
-    if (plant == IPOC_PLANT_CARTPOLE) return hamiltonian_impl<Cartpole>(pp, bp, N, batch, x, u, lam, ru, Q, R, M, st);
+    if (plant == IPOC_PLANT_PENDULUM) return hamiltonian_impl<Pendulum>(pp, bp, N, batch, x, u, lam, ru, Q, R, M, fresh, st);
+    if (plant == IPOC_PLANT_CARTPOLE) return hamiltonian_impl<Cartpole>(pp, bp, N, batch, x, u, lam, ru, Q, R, M, fresh, st);
     return IPOC_EINVAL;
 }
 
 int ipoc_plant_cost_f64(int plant, int N, int batch, double Ts, double bound, const double* bp, const double* x,
-                        const double* u, double* total_cost, int32_t* feasible, ipoc_stream_t stream) {
+                        const double* u, double* total_cost, int32_t* feasible, const int32_t* fresh,
+                        ipoc_stream_t stream) {
     if (N < 1 || batch < 1 || !bp || !x || !u || !total_cost || !feasible) return IPOC_EINVAL;
     const PlantParams pp{Ts, bound};
     cudaStream_t st = (cudaStream_t)stream;
-    if (plant == IPOC_PLANT_PENDULUM) return cost_impl<Pendulum>(pp, bp, N, batch, x, u, total_cost, feasible, st);
-    if (plant == IPOC_PLANT_CARTPOLE) return cost_impl<Cartpole>(pp, bp, N, batch, x, u, total_cost, feasible, st);
+    if (plant == IPOC_PLANT_PENDULUM) return cost_impl<Pendulum>(pp, bp, N, batch, x, u, total_cost, feasible, fresh, st);
+    if (plant == IPOC_PLANT_CARTPOLE) return cost_impl<Cartpole>(pp, bp, N, batch, x, u, total_cost, feasible, fresh, st);
     return IPOC_EINVAL;
 }
 

@@ -21,7 +21,8 @@ _SIGS = {
     "ipoc_set_literal_lqt": (None, [_I]),
     "ipoc_set_hier": (None, [_I, _I, _I]),
     "ipoc_workspace_init": (_I, [_P, _SZ, _P]),
-    "ipoc_costates_f64": (_I, [_I] * 4 + [_P] * 6 + [_P, _SZ, _P]),
+    "ipoc_set_affine_occupancy": (None, [_I]),
+    "ipoc_costates_f64": (_I, [_I] * 4 + [_P] * 7 + [_P, _SZ, _P]),
     "ipoc_newton_attempt_f64": (_I, [_I] * 5 + [_P] * 29 + [_P, _SZ, _P]),
     "ipoc_launch_count": (ctypes.c_ulonglong, []),
     "ipoc_carry_doubles": (_I, [_I, _I]),
@@ -49,9 +50,9 @@ _SIGS = {
     "ipoc_newton_step_host_f64": (_I, [_I] * 4 + [_P] * 11 + [_P, _SZ, _P]),
     "ipoc_plant_dims": (_I, [_I] + [ctypes.POINTER(ctypes.c_int)] * 3),
     "ipoc_plant_derivatives_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 14 + [_P]),
-    "ipoc_plant_linearize_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 8 + [_P]),
-    "ipoc_plant_hamiltonian_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 8 + [_P]),
-    "ipoc_plant_cost_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 5 + [_P]),
+    "ipoc_plant_linearize_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 9 + [_P]),
+    "ipoc_plant_hamiltonian_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 9 + [_P]),
+    "ipoc_plant_cost_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 6 + [_P]),
     "ipoc_plant_rollout_f64": (_I, [_I, _I, _I, ctypes.c_double] + [_P] * 3 + [_P]),
     "ipoc_profile_begin": (_I, [_P]),
     "ipoc_profile_end": (_I, [ctypes.c_char_p, _SZ, ctypes.POINTER(ctypes.c_float), _I]),

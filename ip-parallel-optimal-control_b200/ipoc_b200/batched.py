@@ -221,11 +221,15 @@ class _DeviceLadder:
             dst[:k].copy_(src)
             if k < lp.B:
                 dst[k:].copy_(src[:1].expand((lp.B - k,) + tuple(src.shape[1:])))
+        # the trial buffers of an earlier attempt are dead once a new attempt starts (the next one overwrites them),
+        # so tx := x makes "take the step" a no-op and adv = 1 marks every iterate as new in this loop's buffers
+        lp.tx.copy_(lp.x)
+        lp.tu.copy_(lp.u)
         lp.act.fill_(0)
         lp.act[:k] = 1
         lp.outer_done.fill_(True)
         lp.outer_done[:k] = False
-        lp.adv.zero_()
+        lp.adv.fill_(1)
         lp.buf.hu.fill_(1.0)
 
     def run_stage(self, x, u, bp):

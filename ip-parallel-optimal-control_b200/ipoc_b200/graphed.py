@@ -149,6 +149,7 @@ class DeviceLoopNewton:
         self.iteration = torch.zeros(B, dtype=torch.int64, device=self.dev)
         self.outer_done = torch.zeros(B, dtype=torch.bool, device=self.dev)
         self.buf = noc.AttemptBuffers(B, N, nx, nu, self.dev)
+        self._eval = {}                            # iterate-evaluation buffers, kept across replays (see _step)
         self.depth = 3 if N * B <= 20000 else 1    # replays kept in flight (a replay is > 1 ms for long horizons)
         self.ring = 8
         self.flags = torch.zeros(self.ring, B, dtype=torch.bool).pin_memory()
@@ -164,10 +165,17 @@ class DeviceLoopNewton:
                                              L.stream_ptr()))                               # :184
         plant = plants.plant_of(self.ocp)
         if plant is not None:                                                              # :142-149
-            fx, fu, cx, cu, lamT = plants.linearize(plant, self.x, self.u, self.bp)
-            cost, _ = plants.cost(plant, self.x, self.u, self.bp)
-            lam, cu_norm = noc.costates_fused(fx, cx, lamT, cu)                            # :147, :116
-            ru, Q, R, M = plants.hamiltonian(plant, self.x, self.u, lam, self.bp)
+            # `adv` doubles as the "iterate changed" flag: after a REJECTED attempt the iterate is the same, every
+            # member-wise kernel below skips the member and its buffers keep the previous evaluation
+            fr, ev = self.adv, self._eval
+            ev["lin"] = plants.linearize(plant, self.x, self.u, self.bp, fresh=fr, out=ev.get("lin"))
+            ev["cost"] = plants.cost(plant, self.x, self.u, self.bp, fresh=fr, out=ev.get("cost"))
+            fx, fu, cx, cu, lamT = ev["lin"]
+            cost = ev["cost"][0]
+            ev["cos"] = noc.costates_fused(fx, cx, lamT, cu, fresh=fr, out=ev.get("cos"))   # :147, :116
+            lam, cu_norm = ev["cos"]
+            ev["ham"] = plants.hamiltonian(plant, self.x, self.u, lam, self.bp, fresh=fr, out=ev.get("ham"))
+            ru, Q, R, M = ev["ham"]
         else:
             cost, fx, fu, cu, ru, Q, R, M = noc.eval_iteration(self.ocp, self.x, self.u, self.bp)
             _, cu_norm, _ = noc.reductions(cu=cu)
@@ -195,7 +203,7 @@ class DeviceLoopNewton:
         self.r_inc.fill_(2.0)                                                              # :135
         self.buf.hu.fill_(1.0)
         self.act.fill_(1)
-        self.adv.zero_()
+        self.adv.fill_(1)      # "take the step tx -> x" is a no-op (tx == x) and marks every iterate as new
         self.inner.zero_()
         self.iteration.zero_()
         self.outer_done.zero_()

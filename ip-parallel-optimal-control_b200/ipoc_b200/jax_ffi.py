@@ -19,7 +19,11 @@ except Exception:  # pragma: no cover
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 XLA_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libipoc_xla.so")
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libipoc.so")
 _registered = False
+_TARGETS = {"ipoc_newton_step": "IpocNewtonStep", "ipoc_affine_scan": "IpocAffineScan", "ipoc_lqt_bwd": "IpocLqtBwd",
+            "ipoc_lqt_fwd": "IpocLqtFwd", "ipoc_reductions": "IpocReductions", "ipoc_accept_update": "IpocAcceptUpdate",
+            "ipoc_costates": "IpocCostates", "ipoc_newton_attempt": "IpocNewtonAttempt"}
 
 
 def register():
@@ -30,14 +34,22 @@ def register():
     if _registered:
         return
     lib = ctypes.CDLL(XLA_LIB_PATH)
-    jax.ffi.register_ffi_target("ipoc_newton_step", jax.ffi.pycapsule(lib.IpocNewtonStep), platform="CUDA")
-    jax.ffi.register_ffi_target("ipoc_affine_scan", jax.ffi.pycapsule(lib.IpocAffineScan), platform="CUDA")
+    for target, symbol in _TARGETS.items():
+        jax.ffi.register_ffi_target(target, jax.ffi.pycapsule(getattr(lib, symbol)), platform="CUDA")
     _registered = True
 
 
+_core = None
+
+
 def _ws_bytes(kind, N, nx, nu, batch):
-    from . import _lib
-    return int(_lib.lib().ipoc_workspace_bytes(kind, N, nx, nu, batch))
+    """Workspace size through plain ctypes on libipoc.so — no torch import on the JAX side."""
+    global _core
+    if _core is None:
+        _core = ctypes.CDLL(LIB_PATH)
+        _core.ipoc_workspace_bytes.restype = ctypes.c_size_t
+        _core.ipoc_workspace_bytes.argtypes = [ctypes.c_int] * 5
+    return int(_core.ipoc_workspace_bytes(kind, N, nx, nu, batch))
 
 
 def newton_step(fx, fu, ru, Q, R, M, reg):
@@ -72,3 +84,50 @@ def par_costates_scan(fx, cx, lamda_T):
     lam, _ = jax.ffi.ffi_call("ipoc_affine_scan", out_types)(fx[None], cx[None], lamda_T[None],
                                                              reverse=np.int32(1), transpose=np.int32(1))
     return lam[0]
+
+
+def par_bwd_pass_effective(A, B, c, X, U, M, q, p, ST, vT):
+    """`paroc.par_bwd_pass` on effective LQT terms (H, Z folded in by the caller) -> (Kx, d, S, v, pred, feasible);
+    ref call sites noc/par_interior_point_newton.py:120, examples/linear_mpc_parallel.py:68."""
+    register()
+    T, nx, nu = A.shape[0], A.shape[1], B.shape[-1]
+    f64 = jnp.float64
+    out_types = (jax.ShapeDtypeStruct((1, T, nu, nx), f64), jax.ShapeDtypeStruct((1, T, nu), f64),
+                 jax.ShapeDtypeStruct((1, T + 1, nx, nx), f64), jax.ShapeDtypeStruct((1, T + 1, nx), f64),
+                 jax.ShapeDtypeStruct((1,), f64), jax.ShapeDtypeStruct((1,), jnp.int32),
+                 jax.ShapeDtypeStruct((_ws_bytes(1, T, nx, nu, 1),), jnp.uint8))
+    Kx, d, S, v, pred, feas, _ = jax.ffi.ffi_call("ipoc_lqt_bwd", out_types)(
+        A[None], B[None], c[None], X[None], U[None], M[None], q[None], p[None], ST[None], vT[None])
+    return Kx[0], d[0], S[0], v[0], pred[0], feas[0] != 0
+
+
+def par_fwd_pass_effective(A, B, c, Kx, d, x0):
+    """`paroc.par_fwd_pass` -> (u, x); ref noc/par_interior_point_newton.py:121-123, linear_mpc_parallel.py:69."""
+    register()
+    T, nx, nu = A.shape[0], A.shape[1], B.shape[-1]
+    out_types = (jax.ShapeDtypeStruct((1, T, nu), jnp.float64), jax.ShapeDtypeStruct((1, T + 1, nx), jnp.float64),
+                 jax.ShapeDtypeStruct((_ws_bytes(2, T, nx, nu, 1),), jnp.uint8))
+    u, x, _ = jax.ffi.ffi_call("ipoc_lqt_fwd", out_types)(A[None], B[None], c[None], Kx[None], d[None], x0[None])
+    return u[0], x[0]
+
+
+def reductions(ru, cu, cons):
+    """(max|ru|, ||cu||_F, all(cons <= 0)) — ref :158, :116, :45-47."""
+    register()
+    N, nu, nc = ru.shape[0], ru.shape[1], cons.shape[-1]
+    out_types = (jax.ShapeDtypeStruct((1,), jnp.float64), jax.ShapeDtypeStruct((1,), jnp.float64),
+                 jax.ShapeDtypeStruct((1,), jnp.int32),
+                 jax.ShapeDtypeStruct((_ws_bytes(4, N, max(nu, nc), nu, 1),), jnp.uint8))
+    hu, cn, feas, _ = jax.ffi.ffi_call("ipoc_reductions", out_types)(ru[None], cu[None], cons[None])
+    return hu[0], cn[0], feas[0] != 0
+
+
+def accept_update(cost, new_cost, traj_feasible, pred, bwd_feasible, rp, r_inc):
+    """Functional A8 (ref :159-173) -> (rp', r_inc', success, gain_ratio); scalars as shape-(1,) arrays."""
+    register()
+    f1, i1 = jax.ShapeDtypeStruct((1,), jnp.float64), jax.ShapeDtypeStruct((1,), jnp.int32)
+    r = lambda a, t: jnp.reshape(a, (1,)).astype(t)
+    rp2, ri2, succ, gain = jax.ffi.ffi_call("ipoc_accept_update", (f1, f1, i1, f1))(
+        r(cost, jnp.float64), r(new_cost, jnp.float64), r(traj_feasible, jnp.int32), r(pred, jnp.float64),
+        r(bwd_feasible, jnp.int32), r(rp, jnp.float64), r(r_inc, jnp.float64))
+    return rp2[0], ri2[0], succ[0] != 0, gain[0]

@@ -204,18 +204,22 @@ def newton_advance(hu, inner_done, outer_done, inner, iteration, advanced, tx, t
                                                 L.stream_ptr()))
 
 
-def costates_fused(fx, cx, lamT, cu):
+def costates_fused(fx, cx, lamT, cu, fresh=None, out=None):
     """K1 with ||cu||_F folded into the up-sweep (ipoc_costates_f64; ref noc/costates.py:34-40 + :116 of the
-    Newton step) -> (lam (B,N+1,nx), cu_norm (B,)).  Batched (B,N,...) tensors."""
+    Newton step) -> (lam (B,N+1,nx), cu_norm (B,)).  Batched (B,N,...) tensors.  `fresh` (int32 per problem): members
+    whose flag is 0 are skipped and keep what `out` = (lam, cu_norm) of an earlier call holds."""
     fx, cx, cu = L.dev_f64(fx), L.dev_f64(cx), L.dev_f64(cu)
     lamT = L.dev_f64(lamT, fx.device).reshape(fx.shape[0], -1).contiguous()
     Bn, N, nx, nu = fx.shape[0], fx.shape[1], fx.shape[2], cu.shape[-1]
-    lam = torch.empty(Bn, N + 1, nx, dtype=torch.float64, device=fx.device)
-    cu_norm = torch.empty(Bn, dtype=torch.float64, device=fx.device)
+    if out is not None:
+        lam, cu_norm = out
+    else:
+        lam = torch.empty(Bn, N + 1, nx, dtype=torch.float64, device=fx.device)
+        cu_norm = torch.empty(Bn, dtype=torch.float64, device=fx.device)
     ws, nbytes = L.workspace(L.WS_COSTATES, N, nx, nu, Bn, fx.device)
     with torch.cuda.device(fx.device):
         L.check(L.lib().ipoc_costates_f64(N, nx, nu, Bn, L.ptr(fx), L.ptr(cx), L.ptr(lamT), L.ptr(cu), L.ptr(lam),
-                                          L.ptr(cu_norm), L.ptr(ws), nbytes, L.stream_ptr()))
+                                          L.ptr(cu_norm), L.ptr(fresh), L.ptr(ws), nbytes, L.stream_ptr()))
     return lam, cu_norm
 
 

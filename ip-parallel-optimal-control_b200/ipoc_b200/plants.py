@@ -82,24 +82,28 @@ def _prep(states, controls):
     return x, u, batched
 
 
-def linearize(plant, states, controls, bp):
-    """First-order pass (before the costate scan) -> fx, fu, cx, cu, lamT."""
+def linearize(plant, states, controls, bp, fresh=None, out=None):
+    """First-order pass (before the costate scan) -> fx, fu, cx, cu, lamT.  `fresh` (int32 per problem): members
+    whose flag is 0 are skipped and keep what `out` (the tuple returned by an earlier call) holds."""
     x, u, batched = _prep(states, controls)
     B, N = u.shape[0], u.shape[1]
     nx, nu, _ = _dims(plant)
     o = dict(dtype=torch.float64, device=x.device)
-    fx, fu = torch.empty(B, N, nx, nx, **o), torch.empty(B, N, nx, nu, **o)
-    cx, cu, lamT = torch.empty(B, N, nx, **o), torch.empty(B, N, nu, **o), torch.empty(B, nx, **o)
+    if out is not None:
+        fx, fu, cx, cu, lamT = out
+    else:
+        fx, fu = torch.empty(B, N, nx, nx, **o), torch.empty(B, N, nx, nu, **o)
+        cx, cu, lamT = torch.empty(B, N, nx, **o), torch.empty(B, N, nu, **o), torch.empty(B, nx, **o)
     bpt = _bp_tensor(bp, x.device)
     with torch.cuda.device(x.device):
         L.check(L.lib().ipoc_plant_linearize_f64(plant["id"], N, B, plant["Ts"], plant["bound"], L.ptr(bpt), L.ptr(x),
                                                  L.ptr(u), L.ptr(fx), L.ptr(fu), L.ptr(cx), L.ptr(cu), L.ptr(lamT),
-                                                 L.stream_ptr()))
+                                                 L.ptr(fresh), L.stream_ptr()))
     out = (fx, fu, cx, cu, lamT)
     return out if batched else tuple(t[0] for t in out)
 
 
-def hamiltonian(plant, states, controls, lam, bp):
+def hamiltonian(plant, states, controls, lam, bp, fresh=None, out=None):
     """Second-order pass (after the costate scan): ru, Q, R, M = H_u, H_xx, H_uu, H_xu of
     H = stage_cost + lam[k+1]' f  (== compute_lqr_params, ref noc/par_interior_point_newton.py:31-42)."""
     x, u, batched = _prep(states, controls)
@@ -109,18 +113,21 @@ def hamiltonian(plant, states, controls, lam, bp):
     B, N = u.shape[0], u.shape[1]
     nx, nu, _ = _dims(plant)
     o = dict(dtype=torch.float64, device=x.device)
-    ru, Q = torch.empty(B, N, nu, **o), torch.empty(B, N, nx, nx, **o)
-    R, M = torch.empty(B, N, nu, nu, **o), torch.empty(B, N, nx, nu, **o)
+    if out is not None:
+        ru, Q, R, M = out
+    else:
+        ru, Q = torch.empty(B, N, nu, **o), torch.empty(B, N, nx, nx, **o)
+        R, M = torch.empty(B, N, nu, nu, **o), torch.empty(B, N, nx, nu, **o)
     bpt = _bp_tensor(bp, x.device)
     with torch.cuda.device(x.device):
         L.check(L.lib().ipoc_plant_hamiltonian_f64(plant["id"], N, B, plant["Ts"], plant["bound"], L.ptr(bpt), L.ptr(x),
                                                    L.ptr(u), L.ptr(lam), L.ptr(ru), L.ptr(Q), L.ptr(R), L.ptr(M),
-                                                   L.stream_ptr()))
+                                                   L.ptr(fresh), L.stream_ptr()))
     out = (ru, Q, R, M)
     return out if batched else tuple(t[0] for t in out)
 
 
-def cost(plant, states, controls, bp):
+def cost(plant, states, controls, bp, fresh=None, out=None):
     """-> (total_cost (B,), feasible (B,) int32) of trajectories: final cost + sum of stage costs (log barrier
     included; NaN where infeasible, as in the reference) and all(constraints <= 0)."""
     x, u = L.dev_f64(states), L.dev_f64(controls)
@@ -128,12 +135,15 @@ def cost(plant, states, controls, bp):
         x, u = x.unsqueeze(0), u.unsqueeze(0)
     B, N = u.shape[0], u.shape[1]
     dev = x.device
-    total = torch.empty(B, dtype=torch.float64, device=dev)
-    feas = torch.empty(B, dtype=torch.int32, device=dev)
+    if out is not None:
+        total, feas = out
+    else:
+        total = torch.empty(B, dtype=torch.float64, device=dev)
+        feas = torch.empty(B, dtype=torch.int32, device=dev)
     bpt = _bp_tensor(bp, dev)
     with torch.cuda.device(dev):
         L.check(L.lib().ipoc_plant_cost_f64(plant["id"], N, B, plant["Ts"], plant["bound"], L.ptr(bpt), L.ptr(x),
-                                            L.ptr(u), L.ptr(total), L.ptr(feas), L.stream_ptr()))
+                                            L.ptr(u), L.ptr(total), L.ptr(feas), L.ptr(fresh), L.stream_ptr()))
     return total, feas
 
 

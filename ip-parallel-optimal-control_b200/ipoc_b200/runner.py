@@ -101,7 +101,7 @@ class NewtonPass:
         """K1 with ||cu||_F as a side job of the up-sweep (ipoc_costates_f64): two launches."""
         p, lib = L.ptr, L.lib()
         L.check(lib.ipoc_costates_f64(self.N, self.nx, self.nu, self.B, p(self.fx), p(self.cx), p(self.lamT), p(self.cu),
-                                      p(self.lam), p(self.cu_norm), p(self.ws_cos), self.ws_cos_bytes, L.stream_ptr()))
+                                      p(self.lam), p(self.cu_norm), None, p(self.ws_cos), self.ws_cos_bytes, L.stream_ptr()))
 
     def attempt_fused(self):
         """K2 + K3 with reg = rp*||cu|| formed in the kernel, max|ru| folded into the up-sweep, the constraint

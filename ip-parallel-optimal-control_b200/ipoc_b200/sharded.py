@@ -69,6 +69,47 @@ class SegmentNewton:
             self.fwd_apply(self.g_fwd[:, :na].contiguous())
         return self
 
+    def capture_one(self, reg, ST, all_gather_into):
+        """The whole time-sharded Newton step — three local phases AND the two all-gathers of the carries — as
+        ONE CUDA graph (NCCL collectives are graph-capturable): one launch per step on every rank instead of
+        three graph launches and two host-issued collectives.  `step_one()` replays it."""
+        o = dict(dtype=torch.float64, device=self.dev)
+        self.g_reg = L.dev_f64(reg, self.dev).reshape(1).clone()
+        self.g_ST = L.dev_f64(ST, self.dev).clone()
+        na = carry_doubles(L.CARRY_AFFINE, self.nx)
+        self.g_carries = torch.zeros(self.nranks, carry_doubles(L.CARRY_RICCATI, self.nx), **o)
+        self.g_fwd = torch.zeros(self.nranks, na + 2, **o)
+        self.g_mine = torch.zeros(na + 2, **o)
+
+        def body():
+            carry = self.bwd_reduce(self.g_reg)
+            all_gather_into(self.g_carries, carry)
+            fc = self.bwd_apply(self.g_carries, self.g_ST)
+            self.g_mine[:na].copy_(fc)
+            self.g_mine[na:na + 1].copy_(self.pred)
+            self.g_mine[na + 1:].copy_(self.feas.to(torch.float64))
+            all_gather_into(self.g_fwd, self.g_mine)
+            self.fwd_apply(self.g_fwd[:, :na].contiguous())
+
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):          # warm-up outside the capture (communicator, allocator, lazy inits)
+            for _ in range(2):
+                body()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        self.graph_one = g
+        return self
+
+    def step_one(self):
+        """Replay of `capture_one`: -> (dx, du, pred_total, feasible_all)."""
+        self.graph_one.replay()
+        na = self.g_fwd.shape[1] - 2
+        return self.dx, self.du, self.g_fwd[:, na].sum(), (self.g_fwd[:, na + 1] != 0).all()
+
     def step_graphed(self, all_gather_into):
         """One time-sharded Newton step from the captured graphs; `all_gather_into(out, t)` fills the
         (P, len) tensor `out` with every rank's `t`.  Returns (dx, du, pred_total, feasible_all)."""

@@ -66,6 +66,11 @@ def main():
     errg = max(rel(dxg, dx1[lo:hi + 1]), rel(dug, du1[lo:hi]), abs(float(predg) - float(pred1)) / abs(float(pred1)))
     ok = ok and errg < 1e-10
     ms_graphed = timed(lambda: seg.step_graphed(gather_into))
+    seg.capture_one(reg, ST, gather_into)
+    dxo, duo, predo, _ = seg.step_one()
+    torch.cuda.synchronize()
+    ok = ok and max(rel(dxo, dx1[lo:hi + 1]), rel(duo, du1[lo:hi]), abs(float(predo) - float(pred1)) / abs(float(pred1))) < 1e-10
+    ms_one = timed(seg.step_one)
     ms_single = timed(lambda: noc.newton_step(*full, reg))
     # ---- the WHOLE pass (K1 + K4 + K2 + K3) time-sharded, three all-gathers captured inside ONE CUDA graph
     from ipoc_b200.runner import NewtonPass
@@ -88,7 +93,7 @@ def main():
     ref.capture()
     ms_pass_single = timed(ref.replay)
     print(f"[rank {rank}/{world}] N={N} nx={nx} segment=[{lo},{hi}) max rel err {max(max(errs), errg, errp):.2e} "
-          f"{'OK' if ok else 'FAIL'}  time-sharded K2+K3 {ms_sharded:.3f} ms (graphed {ms_graphed:.3f} ms) "
+          f"{'OK' if ok else 'FAIL'}  time-sharded K2+K3 {ms_sharded:.3f} ms (3 graphs {ms_graphed:.3f} ms, one graph incl. NCCL {ms_one:.3f} ms) "
           f"vs single-GPU {ms_single:.3f} ms;  whole pass, one graph incl. 3 NCCL all-gathers {ms_pass:.3f} ms "
           f"vs single-GPU graph {ms_pass_single:.3f} ms", flush=True)
     dist.destroy_process_group()
