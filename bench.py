@@ -295,6 +295,16 @@ def run_ours(args):
     ms_step = float(np.mean(ms))
     ms_plain = float(np.mean(time_steps(npass.run, args.steps, args.warmup, do_flush=True)))
     ms_warm = float(np.mean(time_steps(npass.replay, args.steps, args.warmup, do_flush=False)))
+    # the same pass in the round-1 organisation (separate level kernels, K4 and A8 as their own launches: 11
+    # launches), graph-replayed on the same box in the same run — the like-for-like "before" of the fused pass
+    lib.ipoc_set_hier(0, 0, 0)
+    _, npass_r1 = make_pass(N_HEADLINE, seed=1 + rank)
+    npass_r1.fused = False
+    launches_r1 = npass_r1.launches_per_pass()
+    npass_r1.capture()
+    ms_r1 = float(np.mean(time_steps(npass_r1.replay, args.steps, args.warmup, do_flush=True)))
+    lib.ipoc_set_hier(1, 0, 0)
+    del npass_r1
 
     # ---- per-launch profile (CUDA events after every launch, on the launching stream), L2 flushed
     def profile_pass(p, reps):
@@ -677,6 +687,9 @@ def run_ours(args):
             "kernels_ms_per_step": {k: round(v, 5) for k, v in sorted(kern.items(), key=lambda kv: -kv[1])},
             "phases_ms_per_step": {k: round(v, 5) for k, v in phases.items()},
             "ms_per_step_plain_launch": ms_plain, "ms_per_step_l2_warm": ms_warm,
+            "ms_per_step_round1_organisation": {"ms_per_step": ms_r1, "launches_per_step": launches_r1,
+                                                "what": "same pass, same box, same run: separate level kernels, "
+                                                        "K4 / A8 as their own launches (graph replay, L2 flushed)"},
             "sweep": sweep,
             "time_sharded": time_sharded,
             "xla_proxy": proxy,
@@ -689,7 +702,14 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs holding captured NCCL kernels are still alive (time-sharded records): tearing the process
+        # group down under them hangs, so every rank synchronises and leaves without the collective teardown
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _noc2_step(w, reg, dev):

@@ -19,6 +19,10 @@ from helpers import random_lq
 from ipoc_b200 import noc, sharded
 
 
+def stage(msg):
+    print(f"[rank {os.environ.get('RANK')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100003
     nx = int(sys.argv[2]) if len(sys.argv) > 2 else 4
@@ -31,6 +35,7 @@ def main():
     T = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
     full = [T(a) for a in (fx, fu, ru, Q, R, M)]
     reg = torch.tensor([0.25], dtype=torch.float64, device=dev)
+    stage("init done")
     dx1, du1, Kx1, d1, pred1, feas1 = noc.newton_step(*full, reg)
     lo, hi = sharded.segment_bounds(N, world)[rank]
     seg = sharded.SegmentNewton(*(t[lo:hi] for t in full), rank, world)
@@ -38,6 +43,7 @@ def main():
     ST = full[3][0].contiguous()
     dx, du, pred, feas = sharded.newton_step_time_sharded(seg, reg, ST, gather)
     torch.cuda.synchronize()
+    stage("eager sharded step done")
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
     errs = (rel(dx, dx1[lo:hi + 1]), rel(du, du1[lo:hi]), rel(seg.Kx, Kx1[lo:hi]), rel(seg.d, d1[lo:hi]),
             abs(float(pred) - float(pred1)) / abs(float(pred1)))
@@ -59,18 +65,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
     ms_sharded = timed(lambda: sharded.newton_step_time_sharded(seg, reg, ST, gather))
+    stage("eager timing done")
     seg.capture(reg, ST)
+    stage("3-graph capture done")
     gather_into = sharded.dist_all_gather_into()
     dxg, dug, predg, _ = seg.step_graphed(gather_into)
     torch.cuda.synchronize()
     errg = max(rel(dxg, dx1[lo:hi + 1]), rel(dug, du1[lo:hi]), abs(float(predg) - float(pred1)) / abs(float(pred1)))
     ok = ok and errg < 1e-10
     ms_graphed = timed(lambda: seg.step_graphed(gather_into))
+    stage("3-graph timing done")
     seg.capture_one(reg, ST, gather_into)
+    stage("one-graph capture done")
     dxo, duo, predo, _ = seg.step_one()
     torch.cuda.synchronize()
     ok = ok and max(rel(dxo, dx1[lo:hi + 1]), rel(duo, du1[lo:hi]), abs(float(predo) - float(pred1)) / abs(float(pred1))) < 1e-10
     ms_one = timed(seg.step_one)
+    stage("one-graph timing done")
     ms_single = timed(lambda: noc.newton_step(*full, reg))
     # ---- the WHOLE pass (K1 + K4 + K2 + K3) time-sharded, three all-gathers captured inside ONE CUDA graph
     from ipoc_b200.runner import NewtonPass
@@ -81,9 +92,12 @@ def main():
     ref.run()
     sp = sharded.SegmentPass(full[0][lo:hi], full[1][lo:hi], cx[lo:hi], cu[lo:hi], lamT, full[2][lo:hi],
                              full[3][lo:hi], full[4][lo:hi], full[5][lo:hi], rank, world, cons[lo:hi], rp=0.8)
+    stage("pass objects built")
     sp.capture(gather_into, ST)
+    stage("pass captured")
     sp.replay()
     torch.cuda.synchronize()
+    stage("pass replayed")
     pred_p, bf_p, tf_p = sp.scalars()
     errp = max(rel(sp.lam, ref.lam[0, lo:hi + 1]), rel(sp.new.dx, ref.dx[0, lo:hi + 1]), rel(sp.new.du, ref.du[0, lo:hi]),
                abs(float(pred_p) - float(ref.pred)) / abs(float(ref.pred)),
@@ -96,8 +110,15 @@ def main():
           f"{'OK' if ok else 'FAIL'}  time-sharded K2+K3 {ms_sharded:.3f} ms (3 graphs {ms_graphed:.3f} ms, one graph incl. NCCL {ms_one:.3f} ms) "
           f"vs single-GPU {ms_single:.3f} ms;  whole pass, one graph incl. 3 NCCL all-gathers {ms_pass:.3f} ms "
           f"vs single-GPU graph {ms_pass_single:.3f} ms", flush=True)
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    # CUDA graphs that captured NCCL kernels must be gone before the communicator is torn down (destroying the
+    # process group first hangs); leave without the collective teardown altogether
+    del sp, seg, ref
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

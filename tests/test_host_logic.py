@@ -76,3 +76,42 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert abs(d["e2e"]["value"] - d["value"]) < 1e-9 * d["value"]
+
+
+def test_workspace_sizes_include_the_control_block():
+    """Every scan workspace starts with the IPOC_WS_CONTROL_BYTES control block (arrival counters of the in-kernel
+    levels); the fused kinds add room for the stand-alone reductions they may have to run."""
+    from ipoc_b200 import _lib
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "ipoc.h")).read()
+    ctrl = int(re.search(r"#define IPOC_WS_CONTROL_BYTES (\d+)", hdr).group(1))
+    for kind in (_lib.WS_NEWTON_STEP, _lib.WS_LQT_BWD, _lib.WS_LQT_FWD, _lib.WS_AFFINE_SCAN):
+        assert L.ipoc_workspace_bytes(kind, 17, 4, 1, 1) > ctrl
+    step = L.ipoc_workspace_bytes(_lib.WS_NEWTON_STEP, 100000, 4, 1, 1)
+    att = L.ipoc_workspace_bytes(_lib.WS_NEWTON_ATTEMPT, 100000, 4, 2, 1)
+    red = L.ipoc_workspace_bytes(_lib.WS_REDUCTIONS, 100000, 2, 2, 1)
+    assert att == step + red
+    assert L.ipoc_workspace_bytes(_lib.WS_COSTATES, 1000, 9, 1, 1) == 0        # unsupported nx stays 0
+
+
+def test_plant_descriptor_requires_all_five_callables():
+    """the fused plant kernels hard-code dynamics, costs, goal and box, so an OCP in which any callable of a
+    built-in problem was replaced must NOT take the plant fast path."""
+    import torch
+    from ipoc_b200 import plants, problems
+    from ipoc_b200.optimal_control_problem import OCP
+    ocp = problems.make_cartpole(0.01)
+    assert plants.plant_of(ocp) is not None and plants.plant_of(ocp)["name"] == "cartpole"
+    mine = lambda x, u, bp: (x * x).sum() + (u * u).sum()
+    assert plants.plant_of(ocp._replace(stage_cost=mine)) is None
+    assert plants.plant_of(OCP(ocp.dynamics, lambda x, u: u - 1.0, ocp.stage_cost, ocp.final_cost, ocp.total_cost)) is None
+    other = problems.make_cartpole(0.02)
+    assert plants.plant_of(OCP(ocp.dynamics, *other[1:])) is None               # mixed instances: Ts / bound may differ
+    assert plants.plant_of(other)["Ts"] == 0.02
+
+
+def test_time_segments_must_be_non_empty_but_batch_shards_may_be():
+    from ipoc_b200 import sharded
+    with pytest.raises(ValueError):
+        sharded.segment_bounds(3, 8)
+    assert sharded.shard_batch(3, 7, 8) == (3, 3)
