@@ -48,9 +48,9 @@ def alg_bytes(N, nx=NX, nu=NU, nc=NC):
 
 
 # DRAM bytes (read + write) per pass of each phase at the headline workload, from the committed ncu capture
-# profiles/r01_launches_N1e4_ncu.csv (dram__bytes_read.sum + dram__bytes_write.sum summed over the phase's
-# launches; writes mostly stay in L2 at this size).  Offline measurement, as the bench contract asks.
-NCU_TRAFFIC_N1E4 = {"K1": 3.6e6, "K2": 7.8e6, "K3": 2.4e6}
+# profiles/r02_launches_bench_ncu.csv (dram__bytes_read.sum + dram__bytes_write.sum, median per kernel, summed over
+# the phase's launches; writes mostly stay in L2 at this size).  Offline measurement, as the bench contract asks.
+NCU_TRAFFIC_N1E4 = {"K1": 3.80e6, "K2": 7.87e6, "K3": 2.62e6}
 
 PHASE_OF = {
     "k_aff_seed": "K1", "k_aff_leaf_up": "K1", "k_aff_leaf_down": "K1",
@@ -680,7 +680,9 @@ def run_ours(args):
             "launches_per_step": launches_per_pass,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_N1E4.get(dom),
-                         "traffic_source": "ncu dram__bytes_{read,write}.sum, profiles/r01_launches_N1e4_ncu.csv",
+                         "traffic_source": "ncu dram__bytes_{read,write}.sum, profiles/r02_launches_bench_ncu.csv "
+                                           "(K2 = k_ric_leaf_up 3.43 MB + k_top 0.10 MB + k_ric_leaf_down 4.33 MB: the "
+                                           "inputs are read by the up- and by the down-sweep)",
                          "kernel": f"{dom} phase (all its launches)", "peak_source": peak_src,
                          "algorithmic_bytes": ab[dom], "duration_ms": dom_ms,
                          "note": "N=1e4 moves 8 MB: latency regime, see sweep for N>=1e5"},
