@@ -155,6 +155,25 @@ def require_supported(nx, nu):
 
 
 _tuning = (0, 0, 0)
+_knob_lock = __import__("threading").RLock()
+
+
+class tuning:
+    """`with tuning(leaf_chunk=T): ...` — set the scan-plan knobs for the duration of a block and restore them, under a
+    process-wide lock (the knobs are globals of the C library: a concurrent caller must not see a half-changed plan)."""
+
+    def __init__(self, leaf_chunk=0, mid_fanin=0, top_max=0):
+        self.new = (leaf_chunk, mid_fanin, top_max)
+
+    def __enter__(self):
+        _knob_lock.acquire()
+        self.prev = set_tuning(*self.new)
+        return self
+
+    def __exit__(self, *exc):
+        set_tuning(*self.prev)
+        _knob_lock.release()
+        return False
 
 
 def set_tuning(leaf_chunk=0, mid_fanin=0, top_max=0):

@@ -85,8 +85,24 @@ class GraphedNewton:
         return bool(rec[0] != 0), float(rec[1]), float(rec[2]), float(rec[3]), float(rec[4])
 
 
+# Captured graphs are cached per (identity of the OCP's five callables, horizon, dimensions, device) — the semantics
+# of a jit cache: a captured graph bakes in every Python scalar and global the user functions read, so changing a
+# closed-over constant WITHOUT creating new callables replays stale arithmetic; call `clear_cache()` (or build a new
+# OCP) after such a change.  Failed captures are remembered too (with the OCP kept alive, so that its ids cannot be
+# recycled by another object).
 _cache = {}          # insertion-ordered; bounded so that throw-away OCP closures cannot pile up graphs
 _CACHE_MAX = 8
+_failed_keepalive = {}
+
+
+def clear_cache():
+    """Drop every captured loop body / device-resident loop / batched ladder (they are re-captured on next use)."""
+    _cache.clear()
+    _loop_cache.clear()
+    _failed_keepalive.clear()
+    from . import batched
+    batched._tail_cache.clear()
+    batched._ladder_cache.clear()
 
 
 def get(ocp: OCP, N, nx, nu, device, x, u, bp):
@@ -105,9 +121,11 @@ def get(ocp: OCP, N, nx, nu, device, x, u, bp):
                           f"{str(e)[:120]}); using eager launches for this problem")
             torch.cuda.synchronize(g.dev)
             g = False
+            _failed_keepalive[key] = ocp
         else:
             g._keepalive = ocp
         while len(_cache) >= _CACHE_MAX:
+            _failed_keepalive.pop(next(iter(_cache)), None)
             _cache.pop(next(iter(_cache)))
         _cache[key] = g
     return g
@@ -275,9 +293,11 @@ def get_device_loop(ocp: OCP, N, nx, nu, device, x, u, bp):
                           f"{str(e)[:120]}); using the host-steered loop for this problem")
             torch.cuda.synchronize(g.dev)
             g = False
+            _failed_keepalive[("loop",) + key] = ocp
         else:
             g._keepalive = ocp
         while len(_loop_cache) >= _CACHE_MAX:
+            _failed_keepalive.pop(("loop",) + next(iter(_loop_cache)), None)
             _loop_cache.pop(next(iter(_loop_cache)))
         _loop_cache[key] = g
     return g

@@ -63,12 +63,10 @@ class MpcLoop:
             self._step(x0, i)
 
     def _with_tuning(self, fn):
-        prev = L.set_tuning(leaf_chunk=self.T) if self.serial else None
-        try:
+        if not self.serial:
+            return fn()
+        with L.tuning(leaf_chunk=self.T):     # one chunk per horizon = the serial twins; knobs restored, lock held
             fn()
-        finally:
-            if prev is not None:
-                L.set_tuning(*prev)
 
     def capture(self):
         side = torch.cuda.Stream(device=self.dev)

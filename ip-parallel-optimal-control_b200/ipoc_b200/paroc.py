@@ -116,20 +116,14 @@ def seq_bwd_pass(lqt: LQT):
     recursion, one thread walking the whole horizon (the same kernels with a single chunk per problem).
     -> (Kx, d, S, v)"""
     T = lqt.A.shape[-3]
-    prev = L.set_tuning(leaf_chunk=T)
-    try:
+    with L.tuning(leaf_chunk=T):
         Kx, d, S, v, _, _ = par_bwd_pass(lqt)
-    finally:
-        L.set_tuning(*prev)
     return Kx, d, S, v
 
 
 def seq_fwd_pass(lqt: LQT, x0, Kx, d):
     """Serial twin of `par_fwd_pass` (ref examples/linear_mpc_parallel.py:8,75) -> (u, x)."""
     T = lqt.A.shape[-3]
-    prev = L.set_tuning(leaf_chunk=T)
-    try:
+    with L.tuning(leaf_chunk=T):
         out = par_fwd_pass(lqt, x0, Kx, d)
-    finally:
-        L.set_tuning(*prev)
     return out
