@@ -81,8 +81,11 @@ void ipoc_set_literal_lqt(int on);
 
 /* Scan organisation knob (tests / experiments): by default the levels above the warp scans are completed
  * inside the leaf kernels by their last-arriving warps ("hierarchical" plans: no top / mid kernels, no
- * spin-waiting).  enabled = 0 selects the separate level kernels; group_warps (<= 32, 0 = 32) and
- * serial_top (<= 32, 0 = 8) shape the hierarchy.  ipoc_set_tuning with a non-zero mid_fanin or top_max
+ * spin-waiting) for the affine scans and for Riccati scans of more than 32 groups of warps; Riccati scans
+ * of 6 ... 32 groups run their levels in ONE lane-cooperative level kernel (every combine of a round on up
+ * to 8 lanes, the groups on separate SMs), shorter ones in a single-CTA top kernel.  enabled = 0 selects the
+ * separate single-thread level kernels everywhere, 2 the in-kernel levels everywhere, 3 the mix without
+ * the cooperative kernel (single-CTA top kernel under 24 groups), 4 the cooperative kernel from 1 group; group_warps (<= 32, 0 = 32) and serial_top (<= 32, 0 = 8) shape the hierarchy.  ipoc_set_tuning with a non-zero mid_fanin or top_max
  * also selects the separate level kernels. */
 void ipoc_set_hier(int enabled, int group_warps, int serial_top);
 /* Leaf warps per SM the stand-alone affine scans are planned for (0 = default); experiment knob. */

@@ -436,7 +436,7 @@ int ipoc_workspace_init(void* ws, size_t ws_bytes, ipoc_stream_t stream) {
 void ipoc_set_affine_occupancy(int warps_per_sm) { g_hier.aff_warps_per_sm = warps_per_sm; }
 
 void ipoc_set_hier(int enabled, int group_warps, int serial_top) {
-    g_hier.enabled = enabled ? 1 : 0;
+    g_hier.enabled = enabled < 0 ? 0 : (enabled > 4 ? 4 : enabled);
     g_hier.group_warps = group_warps;
     g_hier.serial_top = serial_top;
 }

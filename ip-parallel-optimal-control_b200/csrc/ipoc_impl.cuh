@@ -512,6 +512,96 @@ IPOC_DEV void hier_finish(const Hier& h, int nW, int batch, const double* agg0, 
     }
 }
 
+// ------------------------------------------------------------------ lane-cooperative Riccati levels
+// The levels of the Riccati scan (warp totals -> value entering every warp) when the level scans do NOT run
+// inside the up-sweep: one CTA per group of <= 32 warp totals, every combine of a Kogge-Stone round done by
+// coop_gs<NX>() cooperating lanes (ric_compose_coop), the groups of a sequence on different SMs; the CTA
+// that arrives last on the sequence's counter scans the (<= 32) group totals the same way and pushes the
+// seed through them.  Writes the same arrays as hier_finish (incl1, agg2, val2), so the down-sweep enters
+// through hier_enter.  Replaces the single-CTA k_top<RicOp> whose rounds cost one full single-thread combine.
+template <int NX>
+__host__ __device__ constexpr int coop_gs() { return NX <= 1 ? 1 : (NX <= 2 ? 2 : (NX <= 4 ? 4 : 8)); }
+
+// Inclusive scan (scan order = slot order) of n <= 32 aggregates held component-major in buf[0] of a
+// 2 x ESZ x 32 ping-pong; all 32 * GS threads of the CTA call it.  Returns the buffer holding the result.
+template <int NX>
+static __device__ __noinline__ int coop_scan(double* buf, int slot, int g, int n) {   // one copy: cold code is fetched once
+    constexpr int ESZ = RicElem<NX>::ESZ, GS = coop_gs<NX>();
+    int cur = 0;
+#pragma unroll 1
+    for (int delta = 1; delta < n; delta <<= 1) {
+        const double* src = buf + cur * (ESZ * 32);
+        double* dst = buf + (cur ^ 1) * (ESZ * 32);
+        if (slot >= delta && slot < n) {
+            if (g < NX) ric_compose_coop<NX>(dst + slot, src + slot - delta, src + slot, g);
+        } else {
+            for (int c = g; c < ESZ; c += GS) dst[c * 32 + slot] = src[c * 32 + slot];
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    return cur;
+}
+
+template <int NX>
+__global__ void __launch_bounds__(32 * coop_gs<NX>())
+k_ric_top_coop(const double* __restrict__ agg0, size_t a0stride, int nW, int batch, Hier h, SideJobs sj) {
+    using Op = RicOp<NX>;
+    using Val = typename Op::Val;
+    constexpr int ESZ = RicElem<NX>::ESZ, GS = coop_gs<NX>();
+    extern __shared__ __align__(16) double s_buf[];   // [2][ESZ][32]
+    __shared__ int s_last;
+    const int b = blockIdx.x / h.ngroups, grp = blockIdx.x % h.ngroups;
+    const int t = threadIdx.x, slot = t / GS, g = t % GS;
+    const int g0 = grp * h.gw, gsize = min(h.gw, nW - g0);
+    // component c of the identity element (A = I, the rest zero) without a runtime-indexed local array
+    auto idc = [](int c) { return (c < NX * NX && c / NX == c % NX) ? 1.0 : 0.0; };
+    for (int c = g; c < ESZ; c += GS)
+        s_buf[c * 32 + slot] = (slot < gsize) ? agg0[(size_t)c * a0stride + (size_t)b * nW + g0 + slot] : idc(c);
+    __syncthreads();
+    {
+        const double* inc = s_buf + coop_scan<NX>(s_buf, slot, g, gsize) * (ESZ * 32);
+        if (slot < gsize)
+            for (int c = g; c < ESZ; c += GS) h.incl1[(size_t)c * h.s1 + (size_t)b * nW + g0 + slot] = inc[c * 32 + slot];
+        if (slot == gsize - 1)
+            for (int c = g; c < ESZ; c += GS) h.agg2[(size_t)c * h.s2 + (size_t)b * h.ngroups + grp] = inc[c * 32 + slot];
+    }
+    const size_t gb = (size_t)b * h.ngroups;
+    if (h.ngroups > 1) {
+        // the CTA's stores happen-before the barrier, the barrier before thread 0's release increment
+        __syncthreads();
+        if (t == 0) {
+            unsigned old = 0;
+            asm volatile("atom.acq_rel.gpu.global.inc.u32 %0, [%1], %2;"
+                         : "=r"(old) : "l"(h.cnt + (size_t)batch * h.ngroups + b), "r"((unsigned)h.ngroups - 1u) : "memory");
+            s_last = (old == (unsigned)h.ngroups - 1u) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_last) return;
+    }
+    if (t < 32) side_finish(sj, b, t);
+    if (h.ngroups == 1) {
+        if (t == 0) {
+            Val v;
+            soa_load_cg(v, h.seed, (size_t)batch, (size_t)b);
+            soa_store(v, h.val2, h.s2, gb);
+        }
+        return;
+    }
+    for (int c = g; c < ESZ; c += GS)
+        s_buf[c * 32 + slot] = (slot < h.ngroups) ? __ldcg(h.agg2 + (size_t)c * h.s2 + gb + slot) : idc(c);
+    __syncthreads();
+    const double* inc = s_buf + coop_scan<NX>(s_buf, slot, g, h.ngroups) * (ESZ * 32);
+    if (h.incl2 != nullptr && slot < h.ngroups)
+        for (int c = g; c < ESZ; c += GS) h.incl2[(size_t)c * h.s2 + gb + slot] = inc[c * 32 + slot];
+    if (g == 0 && slot < h.ngroups) {   // value entering group `slot`: the seed through the groups before it
+        Val v;
+        soa_load_cg(v, h.seed, (size_t)batch, (size_t)b);
+        if (slot > 0) Op::apply_mm(v, inc + slot - 1, 32);
+        soa_store(v, h.val2, h.s2, gb + slot);
+    }
+}
+
 // Way down: the value entering warp s of sequence b (every lane computes the same thing).
 //   chain (time-sharded phase 2): the seed of the whole horizon is first pushed through the gathered
 //   aggregates of the other ranks (rank-major AoS), then through this rank's inclusive group aggregates.
@@ -1485,6 +1575,7 @@ struct Plan {
     int T[MAXLEV];     // fan-in from level l to l+1
     long long warps, slots;
     int hier;          // 1: the levels CAN be completed inside the leaf kernels (last arriver), no level kernels
+    int ric_coop;      // 1: Riccati levels by the lane-cooperative level kernel (k_ric_top_coop)
     int hier_ric;      // 1: ... also those of the Riccati up-sweep (pays only for long horizons, see make_plan)
     int gw, ngroups, serial_top;
 };
@@ -1549,6 +1640,15 @@ static Plan make_plan(int N, int batch, bool force_scan = false, int target_thre
         // faster until the group scans can hide behind the streaming of later groups (N = 1e5: +13 us,
         // N = 1e6: -8 us), i.e. from about two dozen groups.  enabled = 2 forces them everywhere (tests).
         p.hier_ric = (p.hier && (g_hier.enabled == 2 || p.ngroups >= 24)) ? 1 : 0;
+        // Lane-cooperative level kernel (k_ric_top_coop): one launch like k_top, but its combine rounds run on
+        // coop_gs lanes each (measured 2.2 us per round against 3.4) and the groups on separate SMs, at the price
+        // of one more `apply` on the way into the down-sweep (hier_enter).  Measured (profiles/r02_variants_coop.log,
+        // r02_chunk_sweep.log): 3 groups (N = 1e4) +5 us, 13 groups (1e5) -9 us, 31 groups (1e6) -25 us, so it is
+        // the default from 6 groups up to the 32 its top scan takes; the in-kernel Riccati levels remain beyond.
+        // enabled = 4 uses it for any number of groups <= 32 (tests), 2 / 3 never.
+        p.ric_coop = (p.hier && g_hier.enabled != 3 && g_hier.enabled != 2 && p.ngroups <= 32 && p.gw == 32 &&
+                      (p.ngroups >= 6 || g_hier.enabled == 4)) ? 1 : 0;
+        if (p.ric_coop) p.hier_ric = 0;
     }
     return p;
 }
@@ -1879,8 +1979,17 @@ static int run_bwd(const Plan& p, const NewtonWs& w, const Loader& ld, double* K
         }
         if (p.hier && want_fwd_agg) hf = make_hier<AffOp<NX>>(p, w.aff, w.aff.seed, nullptr);
         if (int rc = run_bwd_up<NX, NU>(p, w, ld, st, sj, hup, side, mx_part)) return rc;
-        if (p.nlev > 0 && !p.hier_ric)
+        if (p.nlev > 0 && p.ric_coop && NX > 1) {
+            const Hier hc = make_hier<RicOp<NX>>(p, w.ric, w.ric.seed, nullptr);
+            constexpr size_t smem = 2 * sizeof(RicElem<NX>) * 32;
+            if (int rc = set_smem_plain(k_ric_top_coop<NX>, smem)) return rc;
+            k_ric_top_coop<NX><<<p.g.batch * p.ngroups, 32 * coop_gs<NX>(), smem, st>>>(
+                w.ric.agg[0], (size_t)p.g.batch * p.g.nW, p.g.nW, p.g.batch, hc, side);
+            IPOC_LAUNCH_CHECK_N("k_ric_top_coop", st);
+            hin = make_hier_in(p, w.ric);
+        } else if (p.nlev > 0 && !p.hier_ric) {
             if (int rc = run_levels<RicOp<NX>>(p, w.ric, false, false, st, side)) return rc;
+        }
     }
     return run_bwd_down<NX, NU>(p, w, ld, Kx, d, S, v, pred, feasible, want_fwd_agg, st, defer_pred, hin, hf);
 }

@@ -482,6 +482,99 @@ struct RicOp {
     }
 };
 
+
+// ---------------------------------------------------------------- lane-cooperative Riccati combine
+// The latency-critical level scans run ONE combine on NX cooperating lanes instead of one: lane g owns column g
+// of every matrix result.  Both operands sit in shared memory (component c of a slot at p[c * 32]) and every
+// lane reads what it needs from there (same-address reads of a group are broadcasts), so the lanes exchange
+// nothing: the NX x NX factorisation of W = I + C1 J2 and the solve for b1 are done redundantly by every lane
+// (cheap next to the 2 NX + 2 right-hand sides of the single-thread form), each lane then substitutes only ITS
+// columns of [A1 | C1 A2'] — lane 0 also the two vector columns — and forms column g of A, C, J and entry g of
+// eta.  About 1/3 of the instructions per lane of RicOp::compose_t, the same operations per output element.
+template <int NX>
+IPOC_DEV void ric_compose_coop(double* dst, const double* first, const double* second, int g) {
+    using E = RicElem<NX>;
+    const RicView<NX> e2{first, 32};    // the LATER segment (earlier in scan order)
+    const RicView<NX> e1{second, 32};   // the EARLIER segment
+    double W[NX][NX], inv[NX];
+    int perm[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            double w = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < NX; ++k) w += e1.C(i, k) * e2.J(k, j);
+            W[i][j] = w;
+        }
+    }
+    lu_factor<NX>(W, inv, perm);
+    // right-hand sides in pivot order: [A1(:,g) | (C1 A2')(:,g) | b1 | C1 eta2]
+    double X[NX][4];
+    double a2row[NX];   // row g of A2
+#pragma unroll
+    for (int k = 0; k < NX; ++k) a2row[k] = e2.A(g, k);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        const int r = perm[i];
+        double ca = 0.0, ce = 0.0;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) {
+            const double c = e1.C(r, k);
+            ca += c * a2row[k];
+            ce += c * e2.eta(k);
+        }
+        X[i][0] = e1.A(r, g);
+        X[i][1] = ca;
+        X[i][2] = e1.b(r);
+        X[i][3] = ce;
+    }
+    lu_subst<NX, 4>(W, inv, X);
+    // column g of A = A2 XA, of J2 XA, and J2 xb
+    double jxa[NX], jxb[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        double a = 0.0, ja = 0.0, jb = 0.0;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) {
+            a += e2.A(i, k) * X[k][0];
+            ja += e2.J(i, k) * X[k][0];
+            jb += e2.J(i, k) * X[k][2];
+        }
+        dst[(E::OA + i * NX + g) * 32] = a;
+        jxa[i] = ja;
+        jxb[i] = jb;
+    }
+    // upper part of column g of C = C2 + A2 XD and J = J1 + A1' (J2 XA)
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        if (i <= g) {
+            double c = e2.C(i, g), jj = e1.J(i, g);
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                c += e2.A(i, k) * X[k][1];
+                jj += e1.A(k, i) * jxa[k];
+            }
+            dst[(E::OC + Sym<NX>::at(i, g)) * 32] = c;
+            dst[(E::OJ + Sym<NX>::at(i, g)) * 32] = jj;
+        }
+    }
+    // eta_g = eta1_g + XA(:,g)' eta2 - A1(:,g)' (J2 xb)
+    double s = e1.eta(g);
+#pragma unroll
+    for (int k = 0; k < NX; ++k) s += X[k][0] * e2.eta(k) - e1.A(k, g) * jxb[k];
+    dst[(E::OE + g) * 32] = s;
+    if (g == 0) {   // b = b2 + A2 (xb + xc)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            double bb = e2.b(i);
+#pragma unroll
+            for (int k = 0; k < NX; ++k) bb += e2.A(i, k) * (X[k][2] + X[k][3]);
+            dst[(E::OB + i) * 32] = bb;
+        }
+    }
+}
+
 // ================================================================ one time step of the LQ problem
 // x+ = A x + B u + c,  stage cost 1/2 x'Xx + 1/2 u'Uu + x'Mu + q'x + p'u   (X, U symmetric)
 template <int NX, int NU>

@@ -20,7 +20,9 @@ for N in [int(float(a)) for a in sys.argv[1:]] or [10000]:
     shape = fx.shape[:-2]
     args = (T(fx), T(fu), T(rng.standard_normal(shape + (4,))), T(rng.standard_normal(shape + (1,))),
             T(rng.standard_normal((1, 4))), T(ru), T(Q), T(R), T(M), T(-np.ones(shape + (2,))))
-    for label, hier, fused in (("fused", 1, True), ("hier, separate calls", 1, False), ("level kernels", 0, False)):
+    for label, hier, fused in (("fused", 1, True), ("fused, Riccati levels in-kernel", 2, True),
+                               ("fused, no cooperative level kernel (r02 mid-round)", 3, True),
+                               ("hier, separate calls", 1, False), ("level kernels", 0, False)):
         _lib.lib().ipoc_set_hier(hier, 0, 0)
         p = NewtonPass(*args)
         p.fused = fused

@@ -754,7 +754,9 @@ def test_config5_batched_subsample_histogram(problem):
 
 
 # ====================================================================== in-kernel levels (round 2)
-HIER_SHAPES = [(0, 0, 0, 0), (1, 1, 2, 1), (1, 1, 5, 32), (1, 2, 32, 3), (1, 3, 7, 8), (1, 0, 3, 2)]
+# (1, 1, 0, 0): ten groups through the lane-cooperative level kernel; 2 = in-kernel levels everywhere; 3 = round-2 mix
+HIER_SHAPES = [(0, 0, 0, 0), (1, 1, 2, 1), (1, 1, 5, 32), (1, 2, 32, 3), (1, 3, 7, 8), (1, 0, 3, 2),
+               (1, 1, 0, 0), (4, 1, 0, 0), (4, 0, 0, 0), (2, 1, 0, 0), (3, 0, 0, 0)]
 
 
 @pytest.mark.parametrize("enabled,leaf_chunk,group_warps,serial_top", HIER_SHAPES)
@@ -797,6 +799,27 @@ def test_in_kernel_levels_all_shapes(enabled, leaf_chunk, group_warps, serial_to
     uo, xo = paroc_np.par_fwd_pass(lq, x0, Kxo, do)
     u, x = par_fwd_pass(LQT(*(T(a) for a in lq)), T(x0), T(Kxo), T(do))
     assert relerr(N_(u), uo) < 1e-10 and relerr(N_(x), xo) < 1e-10
+
+
+@pytest.mark.parametrize("nx", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("N,B,leaf_chunk", [(5000, 1, 1), (40000, 1, 0), (1500, 3, 1), (33, 2, 1)])
+def test_cooperative_level_kernel_every_nx(nx, N, B, leaf_chunk):
+    """Riccati levels by the lane-cooperative kernel (2, 4 or 8 lanes per combine, one CTA per group of 32 warp
+    totals, last CTA scans the groups): single and several groups, ragged last group, batches, every nx."""
+    from ipoc_b200 import noc, _lib
+    rng = np.random.default_rng(100 * nx + N)
+    nu = 1 + (nx % 2 if nx > 1 else 0)
+    fx, fu, ru, Q, R, M = random_lq(rng, N, nx, nu, batch=B)
+    reg = 0.05 + 0.1 * rng.random(B)
+    _lib.lib().ipoc_set_tuning(leaf_chunk, 0, 0)
+    _lib.lib().ipoc_set_hier(4, 0, 0)   # the cooperative kernel for any number of groups (default: from 6)
+    for rep in range(2):
+        dx, du, Kx, d, pred, feas = noc.newton_step(T(fx), T(fu), T(ru), T(Q), T(R), T(M), T(reg))
+    for b in range(B):
+        dxo, duo, Kxo, do, predo, feaso = oracle_newton(fx[b], fu[b], ru[b], Q[b], R[b], M[b], reg[b])
+        assert relerr(N_(dx[b]), dxo) < 1e-10 and relerr(N_(du[b]), duo) < 1e-10
+        assert relerr(N_(Kx[b]), Kxo) < 1e-10 and relerr(N_(d[b]), do) < 1e-10
+        assert abs(float(pred[b]) - predo) <= 1e-10 * abs(predo) and bool(feas[b]) == bool(feaso)
 
 
 @pytest.mark.parametrize("enabled,leaf_chunk,group_warps,serial_top", HIER_SHAPES)
