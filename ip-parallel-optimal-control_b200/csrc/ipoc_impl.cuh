@@ -1181,13 +1181,13 @@ k_ric_leaf_down(Loader ld, Geom g, const double* __restrict__ incl, size_t istri
     if (g.per_lane) {
         soa_load(val, wvals, wvstride, (size_t)L.b);
     } else {
+        // exclusive prefix (scan order) = inclusive aggregate of the next lane; requested BEFORE the value entering
+        // the warp is derived (hier_enter's `apply` is a call the load could not be moved across by the compiler)
+        RicElem<NX> ex;
+        if (lane < 31) soa_load(ex, incl, istride, (size_t)L.slot + 1);
         if (hin.on) hier_enter<RicOp<NX>>(val, hin, g.nW, L.b, g.nW - 1 - L.wi);
         else soa_load(val, wvals, wvstride, (size_t)L.b * g.nW + (g.nW - 1 - L.wi));
-        if (lane < 31) {   // exclusive prefix (scan order) = inclusive aggregate of the next lane
-            RicElem<NX> ex;
-            soa_load(ex, incl, istride, (size_t)L.slot + 1);
-            RicOp<NX>::apply(val, ex, val);
-        }
+        if (lane < 31) RicOp<NX>::apply(val, ex, val);
     }
     AffElem<NX> fa;
     AffOp<NX>::identity(fa);
@@ -1393,9 +1393,17 @@ k_fwd_leaf_down(FwdLoader<NX, NU> ld, Geom g, const double* __restrict__ fincl, 
     // ---- constraint feasibility of a given array + accept / regularisation update by the last arriver
     int ok = 1;
     if (tail.cons != nullptr) {
-        const double* cp = tail.cons + (size_t)L.t0 * tail.nc;
-        const int n = L.len * tail.nc;
-        for (int i = 0; i < n; ++i) ok &= (__ldg(cp + i) <= 0.0) ? 1 : 0;
+        // the warp's steps are contiguous: coalesced, sixteen loads in flight per lane (NaN compares false -> infeasible)
+        const double* cp = tail.cons + (size_t)w.map.tb * tail.nc;
+        const int n = w.map.remc * tail.nc;
+        constexpr int U = 16;
+        for (int i0 = lane; i0 < n; i0 += 32 * U) {
+            double v[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) v[k] = (i0 + 32 * k < n) ? __ldg(cp + i0 + 32 * k) : 0.0;
+#pragma unroll
+            for (int k = 0; k < U; ++k) ok &= (v[k] <= 0.0) ? 1 : 0;
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ok &= __shfl_xor_sync(0xffffffffu, ok, o);
         if (lane == 0) tail.cons_part[wg] = ok;
@@ -1473,6 +1481,18 @@ k_aff_leaf_up(AffLoader<NX> ld, int reverse, int transpose, Geom g, double* __re
     // sequence arrives anywhere, so its counters stay at zero)
     if (fresh != nullptr && !g.per_lane && fresh[L.b] == 0) return;
     const WarpSmem w = warp_smem(smem, g, wib, wg);
+    // side job ||cu||_F: the warp's rows of `sq_src` are contiguous; the first eight values per lane are requested
+    // before the walk (consumed after it: no exposed latency up to 256 values per warp), the rest in batches
+    constexpr int SQP = 8;
+    double sqv[SQP];
+    const double* sq_cp = nullptr;
+    int sq_n = 0;
+    if (sq_part != nullptr) {
+        sq_cp = sq_src + (size_t)w.map.tb * sq_width;
+        sq_n = w.map.remc * sq_width;
+#pragma unroll
+        for (int k = 0; k < SQP; ++k) sqv[k] = (lane + 32 * k < sq_n) ? __ldg(sq_cp + lane + 32 * k) : 0.0;
+    }
     AffElem<NX> a;
     AffOp<NX>::identity(a);
     AffElem<NX> se;
@@ -1484,12 +1504,16 @@ k_aff_leaf_up(AffLoader<NX> ld, int reverse, int transpose, Geom g, double* __re
     const int sidx = reverse ? g.nW - 1 - L.wi : L.wi;   // index of this warp in scan order
     if (lane == (reverse ? 0 : 31)) soa_store(a, agg1, a1stride, (size_t)L.b * g.nW + sidx);
     if (sq_part != nullptr) {   // side job: sum of squares of this warp's rows of `sq_src` (||cu||_F, ref :116)
-        const double* cp = sq_src + (size_t)L.t0 * sq_width;
-        const int n = L.len * sq_width;
         double acc = 0.0;
-        for (int i = 0; i < n; ++i) {
-            const double v = __ldg(cp + i);
-            acc += v * v;
+#pragma unroll
+        for (int k = 0; k < SQP; ++k) acc += sqv[k] * sqv[k];
+        constexpr int U = 16;
+        for (int i0 = lane + 32 * SQP; i0 < sq_n; i0 += 32 * U) {
+            double v[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) v[k] = (i0 + 32 * k < sq_n) ? __ldg(sq_cp + i0 + 32 * k) : 0.0;
+#pragma unroll
+            for (int k = 0; k < U; ++k) acc += v[k] * v[k];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
