@@ -332,6 +332,11 @@ int ipoc_newton_step_host_f64(int N, int nx, int nu, int batch,
  *   ipoc_plant_cost_f64: total_cost (ref examples/cartpole_runtime.py:48-51) and all(constraints<=0)
  *       (ref noc/par_interior_point_newton.py:45-47) per problem, fixed summation order.
  *   ipoc_plant_rollout_f64: serial rollout (ref noc/utils.py:57-63), one thread per problem.
+ *   ipoc_plant_rollout_lin_f64: one iteration's inputs of the parallel-in-time rollout: along a
+ *       guess x (batch,N+1,nx) of the trajectory, F_k = df/dx and c_k = f(x_k,u_k) - F_k x_k (feed them to
+ *       ipoc_affine_scan_f64 with seed x_0 for the next guess), fv_k = f(x_k,u_k) in the serial rollout's arithmetic,
+ *       stats (batch,2) = (max_k |x_{k+1} - fv_k|, max |fv|) per problem (a NaN defect stays NaN).  Iterated to a
+ *       defect at rounding level, (x_0, fv) IS the serial rollout up to rounding; host loop: ipoc_b200/plants.py.
  */
 enum { IPOC_PLANT_PENDULUM = 1, IPOC_PLANT_CARTPOLE = 2 };
 int ipoc_plant_dims(int plant, int* nx, int* nu, int* nc);
@@ -359,6 +364,8 @@ int ipoc_plant_cost_f64(int plant, int N, int batch, double Ts, double bound, co
                         const int32_t* fresh, ipoc_stream_t stream);
 int ipoc_plant_rollout_f64(int plant, int N, int batch, double Ts, const double* x0, const double* u,
                            double* x, ipoc_stream_t stream);
+int ipoc_plant_rollout_lin_f64(int plant, int N, int batch, double Ts, const double* x, const double* u,
+                               double* F, double* c, double* fv, double* stats, ipoc_stream_t stream);
 /* ipoc_plant_cost_f64 of the trial point (tx, tu) followed, in the same launch, by ipoc_attempt_finish_f64 with
  * the cost / feasibility just computed (members with active == 0 are skipped altogether). */
 int ipoc_plant_attempt_finish_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,

@@ -340,6 +340,61 @@ __global__ void k_plant_rollout(PlantParams pp, int N, int batch, const double* 
     }
 }
 
+// ---------------------------------------------------------------- parallel-in-time rollout: one Newton iteration's inputs
+// Linearisation of the rollout equations x_{k+1} = f(x_k, u_k) along a GUESS of the whole trajectory, one thread per
+// (problem, step):  F_k = df/dx,  c_k = f(x_k, u_k) - F_k x_k  (the caller solves the affine recursion for all k at
+// once with ipoc_affine_scan_f64),  fv_k = f(x_k, u_k) in the arithmetic of the serial rollout, and per problem
+// stats[2b] = max_k |x_{k+1} - fv_k| (the guess's defect; NaN wins), stats[2b+1] = max |fv|.
+template <class P>
+__global__ void __launch_bounds__(128)
+k_plant_rollout_lin(PlantParams pp, int N, int batch, const double* __restrict__ X, const double* __restrict__ U,
+                    double* __restrict__ F, double* __restrict__ c, double* __restrict__ fv,
+                    unsigned long long* __restrict__ stats) {
+    constexpr int NX = P::NX, NU = P::NU;
+    using J = Jet<NX>;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)batch * N) return;
+    const int b = (int)(g / N), k = (int)(g % N);
+    const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
+    double xv[NX], uv[NU], ov[NX];
+    J x[NX], u[NU], o[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        xv[i] = xp[i];
+        x[i] = J::var(xv[i], i);
+    }
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+        uv[a] = U[(size_t)g * NU + a];
+        u[a] = J(uv[a]);
+    }
+    P::ode(x, u, o);
+    P::ode(xv, uv, ov);
+    double Fv[NX * NX], cv[NX], fvv[NX];
+    double defect = 0.0, amax = 0.0;
+#pragma unroll
+    for (int r = 0; r < NX; ++r) {
+        fvv[r] = xv[r] + pp.Ts * ov[r];   // exactly the serial rollout's update
+        double acc = fvv[r];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const double fri = ((i == r) ? 1.0 : 0.0) + pp.Ts * o[r].g[i];
+            Fv[r * NX + i] = fri;
+            acc -= fri * xv[i];
+        }
+        cv[r] = acc;
+        const double dd = fabs(xp[NX + r] - fvv[r]);
+        defect = (dd != dd || defect != defect) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(defect, dd);
+        amax = fmax(amax, fabs(fvv[r]));
+    }
+    store_row<NX * NX>(F + (size_t)g * NX * NX, Fv);
+    store_row<NX>(c + (size_t)g * NX, cv);
+    store_row<NX>(fv + (size_t)g * NX, fvv);
+    // non-negative doubles (and NaN above +inf) order like their bit patterns
+    atomicMax(stats + 2 * (size_t)b, (unsigned long long)__double_as_longlong(defect) & 0x7fffffffffffffffULL);
+    atomicMax(stats + 2 * (size_t)b + 1, (unsigned long long)__double_as_longlong(amax) & 0x7fffffffffffffffULL);
+}
+
 #define PLANT_CHECK(st)                                              \
     do {                                                             \
         ++g_launches;                                                \
@@ -393,6 +448,17 @@ template <class P>
 static int rollout_impl(PlantParams pp, int N, int batch, const double* x0, const double* U, double* X,
                         cudaStream_t st) {
     k_plant_rollout<P><<<(batch + 31) / 32, 32, 0, st>>>(pp, N, batch, x0, U, X);
+    PLANT_CHECK(st);
+    return IPOC_OK;
+}
+
+template <class P>
+static int rollout_lin_impl(PlantParams pp, int N, int batch, const double* X, const double* U, double* F, double* c,
+                            double* fv, double* stats, cudaStream_t st) {
+    if (cudaMemsetAsync(stats, 0, 2 * sizeof(double) * (size_t)batch, st) != cudaSuccess) return IPOC_ECUDA;
+    const long long n = (long long)N * batch;
+    k_plant_rollout_lin<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pp, N, batch, X, U, F, c, fv,
+                                                                      reinterpret_cast<unsigned long long*>(stats));
     PLANT_CHECK(st);
     return IPOC_OK;
 }
@@ -482,6 +548,16 @@ int ipoc_plant_rollout_f64(int plant, int N, int batch, double Ts, const double*
     cudaStream_t st = (cudaStream_t)stream;
     if (plant == IPOC_PLANT_PENDULUM) return rollout_impl<Pendulum>(pp, N, batch, x0, u, x, st);
     if (plant == IPOC_PLANT_CARTPOLE) return rollout_impl<Cartpole>(pp, N, batch, x0, u, x, st);
+    return IPOC_EINVAL;
+}
+
+int ipoc_plant_rollout_lin_f64(int plant, int N, int batch, double Ts, const double* x, const double* u, double* F,
+                               double* c, double* fv, double* stats, ipoc_stream_t stream) {
+    if (N < 1 || batch < 1 || !x || !u || !F || !c || !fv || !stats) return IPOC_EINVAL;
+    const PlantParams pp{Ts, 0.0};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plant == IPOC_PLANT_PENDULUM) return rollout_lin_impl<Pendulum>(pp, N, batch, x, u, F, c, fv, stats, st);
+    if (plant == IPOC_PLANT_CARTPOLE) return rollout_lin_impl<Cartpole>(pp, N, batch, x, u, F, c, fv, stats, st);
     return IPOC_EINVAL;
 }
 

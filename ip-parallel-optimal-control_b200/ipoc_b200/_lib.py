@@ -54,6 +54,7 @@ _SIGS = {
     "ipoc_plant_hamiltonian_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 9 + [_P]),
     "ipoc_plant_cost_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 6 + [_P]),
     "ipoc_plant_rollout_f64": (_I, [_I, _I, _I, ctypes.c_double] + [_P] * 3 + [_P]),
+    "ipoc_plant_rollout_lin_f64": (_I, [_I, _I, _I, ctypes.c_double] + [_P] * 6 + [_P]),
     "ipoc_profile_begin": (_I, [_P]),
     "ipoc_profile_end": (_I, [ctypes.c_char_p, _SZ, ctypes.POINTER(ctypes.c_float), _I]),
 }

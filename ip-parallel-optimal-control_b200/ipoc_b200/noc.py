@@ -335,21 +335,28 @@ def eval_trial(ocp: OCP, tx, tu, bp):
     return ocp.total_cost(tx, tu, bp).reshape(1), traj_feas              # :161 (masked to inf by A8)
 
 
-def initial_rollout(ocp: OCP, u, initial_state, parallel_rollout_from=256):
-    """states of the nominal rollout (ref :133): device kernel for the built-in plants, the parallel
-    Newton-on-the-rollout scan for long horizons, else the serial host loop."""
+PLANT_PARALLEL_ROLLOUT_FROM = 2048   # serial kernel: ~0.4 us per step; parallel: a handful of ~60 us iterations
+
+
+def initial_rollout(ocp: OCP, u, initial_state, parallel_rollout_from=256, x_guess=None):
+    """states of the nominal rollout (ref :133).  Built-in plants: the serial device kernel for short horizons, the
+    parallel-in-time Newton-on-the-rollout iteration on the plant's own kernels for long ones (`x_guess`, e.g. the
+    trajectory the previous barrier stage ended with, saves iterations).  User OCPs: the same iteration through
+    the host framework's autodiff for long horizons, else the serial host loop."""
     plant = plants.plant_of(ocp)
     N = u.shape[0]
-    if plant is not None and N <= 20000:
+    if plant is not None:
+        if N >= PLANT_PARALLEL_ROLLOUT_FROM:
+            return plants.rollout_parallel(plant, u, initial_state.to(u.device), x_guess)[0]
         return plants.rollout(plant, u, initial_state.to(u.device))
     if N >= parallel_rollout_from:
-        return rollout_parallel(ocp.dynamics, u, initial_state.to(u.device))[0]
+        return rollout_parallel(ocp.dynamics, u, initial_state.to(u.device), x_guess)[0]
     return rollout(ocp.dynamics, u, initial_state.to(u.device))
 
 
 # ------------------------------------------------------------------ driver loops
 def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, barrier_param: float, trace=None,
-              stage: int = 0, use_graphs: bool = True, parallel_rollout_from: int = 256):
+              stage: int = 0, use_graphs: bool = True, parallel_rollout_from: int = 256, x_guess=None):
     """ref noc/par_interior_point_newton.py:127-225 -> (opt_x, opt_u, iterations).
     use_graphs=True (default): for the built-in plants the whole loop runs from one CUDA graph with its
     control flow on the device (graphed.DeviceLoopNewton; the host only watches the exit flag; "device"
@@ -358,7 +365,7 @@ def newton_oc(ocp: OCP, controls: torch.Tensor, initial_state: torch.Tensor, bar
     (graphed.GraphedNewton).  use_graphs=False: the eager path below, the same sequence of statements."""
     dev = controls.device
     u = L.dev_f64(controls)
-    x = initial_rollout(ocp, u, initial_state, parallel_rollout_from)   # :133
+    x = initial_rollout(ocp, u, initial_state, parallel_rollout_from, x_guess)   # :133
     if use_graphs:
         from . import graphed
         # Whole loop on the device (no per-attempt host read) where re-evaluating the iterate after a rejected
@@ -433,8 +440,9 @@ def par_interior_point_optimal_control(ocp: OCP, controls: torch.Tensor, initial
         raise L.IpocError("par_interior_point_optimal_control needs CUDA tensors; there is no CPU fallback")
     u = controls
     bp, total, stage = 0.1, 0, 0                                         # :233
+    x = None   # the reference keeps only u between stages (:237); the last trajectory merely seeds the parallel rollout
     while bp > 1e-4:                                                     # :243-245
-        _, u, its = newton_oc(ocp, u, initial_state, bp, trace, stage, use_graphs)   # :237
+        x, u, its = newton_oc(ocp, u, initial_state, bp, trace, stage, use_graphs, x_guess=x)   # :237
         bp = bp / 5                                                      # :238
         total += its                                                     # :239
         stage += 1

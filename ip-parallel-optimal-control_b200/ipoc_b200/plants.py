@@ -161,3 +161,46 @@ def rollout(plant, controls, initial_state):
         L.check(L.lib().ipoc_plant_rollout_f64(plant["id"], N, B, plant["Ts"], L.ptr(x0.contiguous()), L.ptr(u), L.ptr(x),
                                                L.stream_ptr()))
     return x if batched else x[0]
+
+
+def rollout_parallel(plant, controls, initial_state, x_guess=None, tol=1e-13, max_iter=100):
+    """Parallel-in-time rollout of a built-in plant (the reference's `rollout` is a serial
+    `lax.scan`, ref noc/utils.py:57-63): Newton's method on the rollout equations x_{k+1} = f(x_k, u_k).  Per iteration
+    one linearisation kernel along the current guess (ipoc_plant_rollout_lin_f64: F_k, c_k, f(x_k,u_k), the guess's
+    defect) and one forward affine scan (ipoc_affine_scan_f64) for the next guess; the host reads 16 bytes per
+    problem and iteration.  The iteration stops when the defect max_k |x_{k+1} - f(x_k,u_k)| is at rounding level
+    (tol * (1 + max|x|)) or has stopped shrinking below 1e-10; the result is (x_0, f(x_k, u_k)) — every state is the
+    serial rollout's update of its predecessor.  `x_guess` (e.g. the previous barrier stage's trajectory) saves
+    iterations.  Falls back to the serial kernel on divergence.  -> (states, iterations or -1)."""
+    from .noc import affine_scan
+    u = L.dev_f64(controls)
+    x0 = L.dev_f64(initial_state, u.device)
+    batched = u.dim() == 3
+    if not batched:
+        u, x0 = u.unsqueeze(0), x0.unsqueeze(0)
+        x_guess = None if x_guess is None else x_guess.unsqueeze(0)
+    u = u.contiguous()
+    B, N, nx = u.shape[0], u.shape[1], x0.shape[-1]
+    o = dict(dtype=torch.float64, device=u.device)
+    if x_guess is not None and tuple(x_guess.shape) == (B, N + 1, nx) and bool(torch.isfinite(x_guess).all()):
+        X = L.dev_f64(x_guess, u.device).clone()
+    else:
+        X = x0.unsqueeze(1).expand(B, N + 1, nx).contiguous()
+    X[:, 0] = x0
+    F, c, fv = torch.empty(B, N, nx, nx, **o), torch.empty(B, N, nx, **o), torch.empty(B, N, nx, **o)
+    stats = torch.empty(B, 2, **o)
+    prev = float("inf")
+    with torch.cuda.device(u.device):
+        for it in range(1, max_iter + 1):
+            L.check(L.lib().ipoc_plant_rollout_lin_f64(plant["id"], N, B, plant["Ts"], L.ptr(X), L.ptr(u), L.ptr(F),
+                                                       L.ptr(c), L.ptr(fv), L.ptr(stats), L.stream_ptr()))
+            st = stats.cpu()
+            defect, scale = float(st[:, 0].max()), 1.0 + float(st[:, 1].max())
+            if not (defect == defect) or defect == float("inf") or scale == float("inf"):
+                break                                                     # diverged: serial kernel below
+            if defect <= tol * scale or (defect <= 1e-10 * scale and defect >= 0.5 * prev):
+                X[:, 1:] = fv
+                return (X if batched else X[0]), it
+            prev = defect
+            X = affine_scan(F, c, x0, reverse=False, transpose=False)
+    return rollout(plant, controls, initial_state), -1

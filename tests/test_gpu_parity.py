@@ -977,3 +977,39 @@ def test_time_sharded_pass_nccl_two_gpus():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count(" OK ") == 2
+
+
+# ====================================================================== parallel-in-time rollout of the built-in plants
+@pytest.mark.parametrize("name,N,amp", [("cartpole", 10000, 0.1), ("cartpole", 4096, 20.0), ("pendulum", 5000, 0.1),
+                                        ("pendulum", 3000, 4.0), ("cartpole", 100000, 0.1)])
+def test_plant_parallel_rollout_equals_serial_kernel(name, N, amp):
+    """Newton on the rollout equations (ipoc_plant_rollout_lin_f64 + forward affine scan per iteration) against the
+    serial one-thread kernel (ref noc/utils.py:57-63): same trajectory to rounding, from a cold start and from a
+    perturbed guess (what a barrier stage hands to the next)."""
+    from ipoc_b200 import plants, problems
+    ocp = (problems.make_cartpole if name == "cartpole" else problems.make_pendulum)(1.0 / N)
+    x0 = (problems.cartpole_x0 if name == "cartpole" else problems.pendulum_x0)(device="cuda")
+    plant = plants.plant_of(ocp)
+    u = T(amp * np.random.default_rng(3).standard_normal((N, 1)))
+    xs = plants.rollout(plant, u, x0)
+    scale = 1.0 + float(xs.abs().max())
+    xp, it = plants.rollout_parallel(plant, u, x0)
+    assert 0 < it <= 40, it
+    assert float((xp - xs).abs().max()) <= 1e-10 * scale
+    guess = xs + 1e-3 * torch.randn_like(xs)
+    xw, itw = plants.rollout_parallel(plant, u, x0, x_guess=guess)
+    assert 0 < itw <= it and float((xw - xs).abs().max()) <= 1e-10 * scale
+    # batched, members with different controls
+    ub = torch.stack((u, 0.5 * u, -u))
+    xb, itb = plants.rollout_parallel(plant, ub, x0.expand(3, -1).contiguous())
+    xsb = plants.rollout(plant, ub, x0.expand(3, -1).contiguous())
+    assert itb > 0 and float((xb - xsb).abs().max()) <= 1e-10 * (1.0 + float(xsb.abs().max()))
+
+
+def test_plant_parallel_rollout_falls_back_on_divergence():
+    from ipoc_b200 import plants, problems
+    N = 4096
+    plant = plants.plant_of(problems.make_cartpole(1.0 / N))
+    u = T(np.full((N, 1), 1e300))
+    x, it = plants.rollout_parallel(plant, u, problems.cartpole_x0(device="cuda"))
+    assert it == -1 and tuple(x.shape) == (N + 1, 4)       # the serial kernel's (non-finite) result, no exception
