@@ -6,6 +6,7 @@
 // User-defined OCPs keep going through the host framework's autodiff; this path only serves OCPs built by
 // ipoc_b200.problems.make_pendulum / make_cartpole and is cross-checked against torch.func in the tests.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include "../../include/ipoc.h"
 #include "ipoc_jet.cuh"
@@ -261,20 +262,28 @@ template <class P>
 __global__ void __launch_bounds__(1024)
 k_plant_cost(PlantParams pp, const double* __restrict__ bp_ptr, int N, const double* __restrict__ X,
              const double* __restrict__ U, double* __restrict__ total, int32_t* __restrict__ feasible, int finish,
-             FinishIO fin, const int32_t* __restrict__ fresh) {
+             FinishIO fin, const int32_t* __restrict__ fresh, int csize) {
+    // One thread-block CLUSTER of `csize` CTAs per problem (csize = 1: a plain launch): the CTAs take interleaved
+    // blocks of 1024 steps, reduce them in a fixed order and leave their partial in shared memory; CTA 0 of the
+    // cluster adds the partials in rank order through distributed shared memory — deterministic, no global
+    // scratch, no second launch.  A long single horizon spreads over up to 8 SMs instead of one.
+    namespace cg = cooperative_groups;
     constexpr int NX = P::NX, NU = P::NU;
     __shared__ double s_sum[32];
     __shared__ int s_ok[32];
-    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (fresh != nullptr && fresh[b] == 0) return;
+    __shared__ double s_part;
+    __shared__ int s_pok;
+    const int b = blockIdx.x / csize, rank = blockIdx.x % csize;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (fresh != nullptr && fresh[b] == 0) return;    // uniform over the cluster
     if (finish && !fin.active[b]) {   // frozen member of a device-resident loop: nothing to evaluate
-        if (t == 0) fin.advanced[b] = 0;
+        if (t == 0 && rank == 0) fin.advanced[b] = 0;
         return;
     }
     const double bp = *bp_ptr;
     double acc = 0.0;
     int ok = 1;
-    for (int k = t; k < N; k += 1024) {
+    for (int k = rank * 1024 + t; k < N; k += 1024 * csize) {
         double x[NX], u[NU];
         const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
 #pragma unroll
@@ -303,15 +312,59 @@ k_plant_cost(PlantParams pp, const double* __restrict__ bp_ptr, int N, const dou
             ok &= __shfl_xor_sync(0xffffffffu, ok, o);
         }
         if (lane == 0) {
-            double xn[NX];
-#pragma unroll
-            for (int i = 0; i < NX; ++i) xn[i] = X[((size_t)b * (N + 1) + N) * NX + i];
-            const double tot = P::state_cost(xn) + acc;
-            total[b] = tot;
-            feasible[b] = ok;
-            if (finish) attempt_finish_rule(fin, b, tot, ok);   // accept + loop bookkeeping (ref :159-202)
+            s_part = acc;
+            s_pok = ok;
         }
     }
+    if (csize > 1) cg::this_cluster().sync();
+    if (rank == 0 && t == 0) {
+        acc = s_part;
+        ok = s_pok;
+        for (int r = 1; r < csize; ++r) {
+            acc += *cg::this_cluster().map_shared_rank(&s_part, r);
+            ok &= *cg::this_cluster().map_shared_rank(&s_pok, r);
+        }
+        double xn[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xn[i] = X[((size_t)b * (N + 1) + N) * NX + i];
+        const double tot = P::state_cost(xn) + acc;
+        total[b] = tot;
+        feasible[b] = ok;
+        if (finish) attempt_finish_rule(fin, b, tot, ok);   // accept + loop bookkeeping (ref :159-202)
+    }
+    if (csize > 1) cg::this_cluster().sync();   // the peers' shared memory stays alive until CTA 0 has read it
+}
+
+// CTAs per problem for the cost kernel: one per 1024 steps up to a portable cluster of 8, only when the batch
+// leaves SMs idle (batched solves keep the single-CTA arithmetic).
+static int cost_cluster(int N, int batch) {
+    if (batch >= 32) return 1;
+    int c = 1;
+    while (c < 8 && c * 1024 < N) c *= 2;
+    return c;
+}
+template <class P>
+static int launch_cost(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
+                       double* total, int32_t* feasible, int finish, const FinishIO& fin, const int32_t* fresh,
+                       cudaStream_t st) {
+    const int c = cost_cluster(N, batch);
+    if (c == 1) {
+        k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, finish, fin, fresh, 1);
+        return IPOC_OK;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(batch * c));
+    cfg.blockDim = dim3(1024);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)c;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_plant_cost<P>, pp, bp, N, X, U, total, feasible, finish, fin, fresh, c) == cudaSuccess
+               ? IPOC_OK : IPOC_ECUDA;
 }
 
 // ---------------------------------------------------------------- serial rollout, one thread per problem
@@ -433,14 +486,14 @@ static int hamiltonian_impl(PlantParams pp, const double* bp, int N, int batch, 
 template <class P>
 static int cost_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
                      double* total, int32_t* feasible, const int32_t* fresh, cudaStream_t st) {
-    k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, 0, FinishIO{}, fresh);
+    if (int rc = launch_cost<P>(pp, bp, N, batch, X, U, total, feasible, 0, FinishIO{}, fresh, st)) return rc;
     PLANT_CHECK(st);
     return IPOC_OK;
 }
 template <class P>
 static int cost_finish_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
                             double* total, int32_t* feasible, const FinishIO& fin, cudaStream_t st) {
-    k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, 1, fin, nullptr);
+    if (int rc = launch_cost<P>(pp, bp, N, batch, X, U, total, feasible, 1, fin, nullptr, st)) return rc;
     PLANT_CHECK(st);
     return IPOC_OK;
 }
