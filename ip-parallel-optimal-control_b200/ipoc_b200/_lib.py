@@ -133,7 +133,10 @@ def workspace(kind, N, nx, nu, batch, device):
     One buffer per (device, kind, CURRENT STREAM): calls enqueued on different streams — including a CUDA graph
     captured on one stream and eager calls on another — never share scratch, which makes this binding as
     re-entrant as the C ABI itself (a workspace must not be used by two calls at the same time).  Buffers are
-    zero-filled at allocation: the control block of a scan workspace must start zeroed (include/ipoc.h)."""
+    zero-filled at allocation: the control block of a scan workspace must start zeroed (include/ipoc.h).
+    Graph captures in this package warm up and capture on the SAME side stream (`torch.cuda.graph(g, stream=side)`), so
+    the buffer exists before the capture starts — allocated inside a capture, its zero-fill would become a node of
+    the graph and run on every replay."""
     need = lib().ipoc_workspace_bytes(kind, N, nx, nu, batch)
     if need == 0:
         raise IpocError(f"unsupported problem size (nx={nx}, nu={nu}): no kernel instantiated, no CPU fallback")

@@ -66,10 +66,10 @@ class GraphedNewton:
         self.rp.copy_(rp0)
         self.r_inc.copy_(ri0)
         ga = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ga):
+        with torch.cuda.graph(ga, stream=side):
             self._iteration()
         gb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gb, pool=ga.pool()):
+        with torch.cuda.graph(gb, pool=ga.pool(), stream=side):
             self._attempt()
         self.rp.copy_(rp0)
         self.r_inc.copy_(ri0)
@@ -236,7 +236,7 @@ class DeviceLoopNewton:
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=side):
             self._step()
         self.graph = g
 

@@ -78,7 +78,7 @@ class MpcLoop:
         g = torch.cuda.CUDAGraph()
 
         def cap():
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=side):
                 self._chunk()
         self._with_tuning(cap)
         self.graph = g

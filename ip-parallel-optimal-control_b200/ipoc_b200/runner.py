@@ -142,7 +142,7 @@ class NewtonPass:
             self.run()
         torch.cuda.current_stream(self.dev).wait_stream(side)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=side):
             self.run()
         self.graph = g
         return g
@@ -261,7 +261,7 @@ class HostNewtonPass:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=side):
             self.run()
         self.graph = g
         return g

@@ -58,14 +58,14 @@ class SegmentNewton:
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         self.graph1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph1):
+        with torch.cuda.graph(self.graph1, stream=side):
             self.g_carry = self.bwd_reduce(self.g_reg)
         self.graph2 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph2, pool=self.graph1.pool()):
+        with torch.cuda.graph(self.graph2, pool=self.graph1.pool(), stream=side):
             fc = self.bwd_apply(self.g_carries, self.g_ST)
             self.g_scal = torch.cat((fc, self.pred, self.feas.to(torch.float64)))
         self.graph3 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph3, pool=self.graph1.pool()):
+        with torch.cuda.graph(self.graph3, pool=self.graph1.pool(), stream=side):
             self.fwd_apply(self.g_fwd[:, :na].contiguous())
         return self
 
@@ -99,7 +99,7 @@ class SegmentNewton:
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=side):
             body()
         self.graph_one = g
         return self
@@ -272,7 +272,7 @@ class SegmentPass:
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=side):
             self.step(all_gather_into, self.g_ST)
         self.graph = g
         return self
