@@ -502,7 +502,7 @@ def run_ours(args):
     plant_fast_path = None
     if rank == 0 and world == 1 and not args.no_solve:
         from ipoc_b200 import noc as _noc2, problems as _pb, batched as _bt
-        for Ns in (1000, 10_000, 100_000):
+        for Ns in (1000, 10_000, 100_000, 1_000_000):
             try:
                 ocp_ = _pb.make_cartpole(1.0 / Ns)
                 x0_ = _pb.cartpole_x0(device=dev)

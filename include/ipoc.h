@@ -359,9 +359,15 @@ int ipoc_plant_hamiltonian_f64(int plant, int N, int batch, double Ts, double bo
                                const double* x, const double* u, const double* lam,
                                double* ru, double* Q, double* R, double* M, const int32_t* fresh,
                                ipoc_stream_t stream);
+/* `ws` (may be NULL): scratch of ipoc_plant_cost_workspace_bytes(N, batch) bytes, ZERO-FILLED once by the caller (its
+ * arrival counters return to zero after every launch).  With it, small batches of long horizons (batch < 32,
+ * N > 8192) spread the FP64-bound stage-cost sum over up to 256 CTAs per problem whose last arriver folds the
+ * partials in a fixed order; without it the kernel runs as one thread-block cluster of <= 8 CTAs per problem
+ * (partials through distributed shared memory).  Both are deterministic; they differ in summation order. */
+size_t ipoc_plant_cost_workspace_bytes(int N, int batch);   /* 0: this shape does not use scratch */
 int ipoc_plant_cost_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
                         const double* x, const double* u, double* total_cost, int32_t* feasible,
-                        const int32_t* fresh, ipoc_stream_t stream);
+                        const int32_t* fresh, void* ws, size_t ws_bytes, ipoc_stream_t stream);
 int ipoc_plant_rollout_f64(int plant, int N, int batch, double Ts, const double* x0, const double* u,
                            double* x, ipoc_stream_t stream);
 int ipoc_plant_rollout_lin_f64(int plant, int N, int batch, double Ts, const double* x, const double* u,
@@ -373,7 +379,7 @@ int ipoc_plant_attempt_finish_f64(int plant, int N, int batch, double Ts, double
                                   const double* cost, const double* pred, const int32_t* bwd_feasible, const double* hu,
                                   int32_t* active, double* rp, double* r_inc, int32_t* success, double* gain_ratio,
                                   int64_t* inner, int64_t* iteration, uint8_t* outer_done, int32_t* advanced,
-                                  double hu_tol, int max_attempts, int max_iterations, ipoc_stream_t stream);
+                                  double hu_tol, int max_attempts, int max_iterations, void* ws, size_t ws_bytes, ipoc_stream_t stream);
 
 /* Number of kernels the library has launched since load (for launch accounting in bench.py). */
 unsigned long long ipoc_launch_count(void);

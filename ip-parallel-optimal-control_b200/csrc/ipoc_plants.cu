@@ -258,22 +258,58 @@ k_plant_hamiltonian(PlantParams pp, const double* __restrict__ bp_ptr, int N, in
 // ---------------------------------------------------------------- total cost + feasibility
 // total_cost = final_cost(x_N) + sum_k stage_cost(x_k, u_k, bp); feasible = all(constraints <= 0).
 // One CTA of 1024 threads per problem; fixed summation order (thread-strided partials, shuffle trees).
+// caller-provided scratch of the grid form of the cost kernel (see ipoc_plant_cost_workspace_bytes)
+struct CostScratch {
+    int G;            // CTAs per problem (<= 1: not used)
+    unsigned* cnt;    // [batch] arrival counters
+    double* part;     // [batch][G]
+    int* ok;          // [batch][G]
+};
+static int cost_grid_ctas(int N, int batch) {   // 0 = the cluster / single-CTA forms serve this shape
+    if (batch >= 32 || N <= 8 * 1024) return 0;
+    const int g = (N + 2047) / 2048;
+    return g > 256 ? 256 : g;
+}
+static size_t cost_scratch_bytes(int N, int batch) {
+    const int G = cost_grid_ctas(N, batch);
+    if (G == 0) return 0;
+    return 256 + ((size_t)batch * 4 + 255) / 256 * 256 + (size_t)batch * G * (sizeof(double) + sizeof(int));
+}
+static CostScratch carve_cost_scratch(int N, int batch, void* ws, size_t ws_bytes) {
+    CostScratch c{0, nullptr, nullptr, nullptr};
+    const int G = cost_grid_ctas(N, batch);
+    if (G == 0 || ws == nullptr || ws_bytes < cost_scratch_bytes(N, batch)) return c;
+    char* p = (char*)(((uintptr_t)ws + 255) / 256 * 256);
+    c.G = G;
+    c.cnt = (unsigned*)p;
+    p += ((size_t)batch * 4 + 255) / 256 * 256;
+    c.part = (double*)p;
+    p += (size_t)batch * G * sizeof(double);
+    c.ok = (int*)p;
+    return c;
+}
+
 template <class P>
 __global__ void __launch_bounds__(1024)
 k_plant_cost(PlantParams pp, const double* __restrict__ bp_ptr, int N, const double* __restrict__ X,
              const double* __restrict__ U, double* __restrict__ total, int32_t* __restrict__ feasible, int finish,
-             FinishIO fin, const int32_t* __restrict__ fresh, int csize) {
-    // One thread-block CLUSTER of `csize` CTAs per problem (csize = 1: a plain launch): the CTAs take interleaved
-    // blocks of 1024 steps, reduce them in a fixed order and leave their partial in shared memory; CTA 0 of the
-    // cluster adds the partials in rank order through distributed shared memory — deterministic, no global
-    // scratch, no second launch.  A long single horizon spreads over up to 8 SMs instead of one.
+             FinishIO fin, const int32_t* __restrict__ fresh, int csize, CostScratch gs) {
+    // Several CTAs per problem take interleaved blocks of 1024 steps and reduce them in a fixed order.
+    //  * cluster form (no scratch given): one thread-block CLUSTER of `csize` <= 8 CTAs per problem (csize = 1: a
+    //    plain launch); every CTA leaves its partial in shared memory and CTA 0 adds them in rank order through
+    //    distributed shared memory — deterministic, no global scratch, no second launch;
+    //  * grid form (gs.G > 1, caller's scratch): up to 256 CTAs per problem, partials in global memory, the CTA that
+    //    arrives last on the problem's counter (zero-initialised, wraps back to zero) folds them in a fixed order —
+    //    the stage cost is FP64-throughput-bound (two logs, wrap, plant: ~300 FP64 operations per step), so a
+    //    horizon of 1e5 ... 1e6 steps needs the whole chip, not 8 SMs.
     namespace cg = cooperative_groups;
     constexpr int NX = P::NX, NU = P::NU;
     __shared__ double s_sum[32];
     __shared__ int s_ok[32];
     __shared__ double s_part;
     __shared__ int s_pok;
-    const int b = blockIdx.x / csize, rank = blockIdx.x % csize;
+    const int per = gs.G > 1 ? gs.G : csize;   // CTAs per problem
+    const int b = blockIdx.x / per, rank = blockIdx.x % per;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (fresh != nullptr && fresh[b] == 0) return;    // uniform over the cluster
     if (finish && !fin.active[b]) {   // frozen member of a device-resident loop: nothing to evaluate
@@ -283,7 +319,7 @@ k_plant_cost(PlantParams pp, const double* __restrict__ bp_ptr, int N, const dou
     const double bp = *bp_ptr;
     double acc = 0.0;
     int ok = 1;
-    for (int k = rank * 1024 + t; k < N; k += 1024 * csize) {
+    for (int k = rank * 1024 + t; k < N; k += 1024 * per) {
         double x[NX], u[NU];
         const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
 #pragma unroll
@@ -316,6 +352,40 @@ k_plant_cost(PlantParams pp, const double* __restrict__ bp_ptr, int N, const dou
             s_pok = ok;
         }
     }
+    auto conclude = [&](double sum, int all_ok) {
+        double xn[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xn[i] = X[((size_t)b * (N + 1) + N) * NX + i];
+        const double tot = P::state_cost(xn) + sum;
+        total[b] = tot;
+        feasible[b] = all_ok;
+        if (finish) attempt_finish_rule(fin, b, tot, all_ok);   // accept + loop bookkeeping (ref :159-202)
+    };
+    if (gs.G > 1) {
+        __shared__ int s_last;
+        if (t == 0) {
+            gs.part[(size_t)b * gs.G + rank] = s_part;
+            gs.ok[(size_t)b * gs.G + rank] = s_pok;
+            unsigned old;
+            asm volatile("atom.acq_rel.gpu.global.inc.u32 %0, [%1], %2;" : "=r"(old) : "l"(gs.cnt + b), "r"((unsigned)gs.G - 1u) : "memory");
+            s_last = (old == (unsigned)gs.G - 1u) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_last || w != 0) return;
+        double a = 0.0;
+        int o = 1;
+        for (int r = lane; r < gs.G; r += 32) {   // lane l: ranks l, l + 32, ... in order; then a fixed butterfly
+            a += __ldcg(gs.part + (size_t)b * gs.G + r);
+            o &= __ldcg(gs.ok + (size_t)b * gs.G + r);
+        }
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, sh);
+            o &= __shfl_xor_sync(0xffffffffu, o, sh);
+        }
+        if (lane == 0) conclude(a, o);
+        return;
+    }
     if (csize > 1) cg::this_cluster().sync();
     if (rank == 0 && t == 0) {
         acc = s_part;
@@ -324,13 +394,7 @@ k_plant_cost(PlantParams pp, const double* __restrict__ bp_ptr, int N, const dou
             acc += *cg::this_cluster().map_shared_rank(&s_part, r);
             ok &= *cg::this_cluster().map_shared_rank(&s_pok, r);
         }
-        double xn[NX];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) xn[i] = X[((size_t)b * (N + 1) + N) * NX + i];
-        const double tot = P::state_cost(xn) + acc;
-        total[b] = tot;
-        feasible[b] = ok;
-        if (finish) attempt_finish_rule(fin, b, tot, ok);   // accept + loop bookkeeping (ref :159-202)
+        conclude(acc, ok);
     }
     if (csize > 1) cg::this_cluster().sync();   // the peers' shared memory stays alive until CTA 0 has read it
 }
@@ -346,10 +410,15 @@ static int cost_cluster(int N, int batch) {
 template <class P>
 static int launch_cost(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
                        double* total, int32_t* feasible, int finish, const FinishIO& fin, const int32_t* fresh,
-                       cudaStream_t st) {
+                       void* ws, size_t ws_bytes, cudaStream_t st) {
+    const CostScratch gs = carve_cost_scratch(N, batch, ws, ws_bytes);
+    if (gs.G > 1) {
+        k_plant_cost<P><<<batch * gs.G, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, finish, fin, fresh, 1, gs);
+        return IPOC_OK;
+    }
     const int c = cost_cluster(N, batch);
     if (c == 1) {
-        k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, finish, fin, fresh, 1);
+        k_plant_cost<P><<<batch, 1024, 0, st>>>(pp, bp, N, X, U, total, feasible, finish, fin, fresh, 1, gs);
         return IPOC_OK;
     }
     cudaLaunchConfig_t cfg = {};
@@ -363,7 +432,7 @@ static int launch_cost(PlantParams pp, const double* bp, int N, int batch, const
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_plant_cost<P>, pp, bp, N, X, U, total, feasible, finish, fin, fresh, c) == cudaSuccess
+    return cudaLaunchKernelEx(&cfg, k_plant_cost<P>, pp, bp, N, X, U, total, feasible, finish, fin, fresh, c, gs) == cudaSuccess
                ? IPOC_OK : IPOC_ECUDA;
 }
 
@@ -485,15 +554,16 @@ static int hamiltonian_impl(PlantParams pp, const double* bp, int N, int batch, 
 }
 template <class P>
 static int cost_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
-                     double* total, int32_t* feasible, const int32_t* fresh, cudaStream_t st) {
-    if (int rc = launch_cost<P>(pp, bp, N, batch, X, U, total, feasible, 0, FinishIO{}, fresh, st)) return rc;
+                     double* total, int32_t* feasible, const int32_t* fresh, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (int rc = launch_cost<P>(pp, bp, N, batch, X, U, total, feasible, 0, FinishIO{}, fresh, ws, ws_bytes, st)) return rc;
     PLANT_CHECK(st);
     return IPOC_OK;
 }
 template <class P>
 static int cost_finish_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
-                            double* total, int32_t* feasible, const FinishIO& fin, cudaStream_t st) {
-    if (int rc = launch_cost<P>(pp, bp, N, batch, X, U, total, feasible, 1, fin, nullptr, st)) return rc;
+                            double* total, int32_t* feasible, const FinishIO& fin, void* ws, size_t ws_bytes,
+                            cudaStream_t st) {
+    if (int rc = launch_cost<P>(pp, bp, N, batch, X, U, total, feasible, 1, fin, nullptr, ws, ws_bytes, st)) return rc;
     PLANT_CHECK(st);
     return IPOC_OK;
 }
@@ -566,14 +636,20 @@ int ipoc_plant_hamiltonian_f64(int plant, int N, int batch, double Ts, double bo
 }
 
 int ipoc_plant_cost_f64(int plant, int N, int batch, double Ts, double bound, const double* bp, const double* x,
-                        const double* u, double* total_cost, int32_t* feasible, const int32_t* fresh,
-                        ipoc_stream_t stream) {
+                        const double* u, double* total_cost, int32_t* feasible, const int32_t* fresh, void* ws,
+                        size_t ws_bytes, ipoc_stream_t stream) {
     if (N < 1 || batch < 1 || !bp || !x || !u || !total_cost || !feasible) return IPOC_EINVAL;
     const PlantParams pp{Ts, bound};
     cudaStream_t st = (cudaStream_t)stream;
-    if (plant == IPOC_PLANT_PENDULUM) return cost_impl<Pendulum>(pp, bp, N, batch, x, u, total_cost, feasible, fresh, st);
-    if (plant == IPOC_PLANT_CARTPOLE) return cost_impl<Cartpole>(pp, bp, N, batch, x, u, total_cost, feasible, fresh, st);
+    if (plant == IPOC_PLANT_PENDULUM)
+        return cost_impl<Pendulum>(pp, bp, N, batch, x, u, total_cost, feasible, fresh, ws, ws_bytes, st);
+    if (plant == IPOC_PLANT_CARTPOLE)
+        return cost_impl<Cartpole>(pp, bp, N, batch, x, u, total_cost, feasible, fresh, ws, ws_bytes, st);
     return IPOC_EINVAL;
+}
+
+size_t ipoc_plant_cost_workspace_bytes(int N, int batch) {
+    return (N < 1 || batch < 1) ? 0 : cost_scratch_bytes(N, batch);
 }
 
 int ipoc_plant_attempt_finish_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
@@ -581,7 +657,8 @@ int ipoc_plant_attempt_finish_f64(int plant, int N, int batch, double Ts, double
                                   const double* cost, const double* pred, const int32_t* bwd_feasible, const double* hu,
                                   int32_t* active, double* rp, double* r_inc, int32_t* success, double* gain_ratio,
                                   int64_t* inner, int64_t* iteration, uint8_t* outer_done, int32_t* advanced,
-                                  double hu_tol, int max_attempts, int max_iterations, ipoc_stream_t stream) {
+                                  double hu_tol, int max_attempts, int max_iterations, void* ws, size_t ws_bytes,
+                                  ipoc_stream_t stream) {
     if (N < 1 || batch < 1 || !bp || !tx || !tu || !new_cost || !traj_feasible || !cost || !pred || !bwd_feasible || !hu ||
         !active || !rp || !r_inc || !success || !inner || !iteration || !outer_done || !advanced)
         return IPOC_EINVAL;
@@ -589,8 +666,10 @@ int ipoc_plant_attempt_finish_f64(int plant, int N, int batch, double Ts, double
     cudaStream_t st = (cudaStream_t)stream;
     const FinishIO fin{AcceptIO{cost, pred, bwd_feasible, rp, r_inc, success, gain_ratio}, hu, active, (long long*)inner,
                        (long long*)iteration, outer_done, advanced, hu_tol, max_attempts, max_iterations};
-    if (plant == IPOC_PLANT_PENDULUM) return cost_finish_impl<Pendulum>(pp, bp, N, batch, tx, tu, new_cost, traj_feasible, fin, st);
-    if (plant == IPOC_PLANT_CARTPOLE) return cost_finish_impl<Cartpole>(pp, bp, N, batch, tx, tu, new_cost, traj_feasible, fin, st);
+    if (plant == IPOC_PLANT_PENDULUM)
+        return cost_finish_impl<Pendulum>(pp, bp, N, batch, tx, tu, new_cost, traj_feasible, fin, ws, ws_bytes, st);
+    if (plant == IPOC_PLANT_CARTPOLE)
+        return cost_finish_impl<Cartpole>(pp, bp, N, batch, tx, tu, new_cost, traj_feasible, fin, ws, ws_bytes, st);
     return IPOC_EINVAL;
 }
 

@@ -168,6 +168,7 @@ class DeviceLoopNewton:
         self.outer_done = torch.zeros(B, dtype=torch.bool, device=self.dev)
         self.buf = noc.AttemptBuffers(B, N, nx, nu, self.dev)
         self._eval = {}                            # iterate-evaluation buffers, kept across replays (see _step)
+        self._cost_ws = None
         self.depth = 3 if N * B <= 20000 else 1    # replays kept in flight (a replay is > 1 ms for long horizons)
         self.ring = 8
         self.flags = torch.zeros(self.ring, B, dtype=torch.bool).pin_memory()
@@ -187,7 +188,11 @@ class DeviceLoopNewton:
             # member-wise kernel below skips the member and its buffers keep the previous evaluation
             fr, ev = self.adv, self._eval
             ev["lin"] = plants.linearize(plant, self.x, self.u, self.bp, fresh=fr, out=ev.get("lin"))
-            ev["cost"] = plants.cost(plant, self.x, self.u, self.bp, fresh=fr, out=ev.get("cost"))
+            if self._cost_ws is None:        # private zero-filled scratch of the two cost evaluations of an attempt
+                self._cost_ws = (plants.cost_scratch(N, B, self.dev, private=True),
+                                 plants.cost_scratch(N, B, self.dev, private=True))
+            ev["cost"] = plants.cost(plant, self.x, self.u, self.bp, fresh=fr, out=ev.get("cost"),
+                                     scratch=self._cost_ws[0])
             fx, fu, cx, cu, lamT = ev["lin"]
             cost = ev["cost"][0]
             ev["cos"] = noc.costates_fused(fx, cx, lamT, cu, fresh=fr, out=ev.get("cos"))   # :147, :116
@@ -201,15 +206,17 @@ class DeviceLoopNewton:
                                  self.act)                                                 # :153-158
         fin = (p(cost.contiguous()), p(buf.pred), p(buf.bwd_feas), p(buf.hu), p(self.act), p(self.rp), p(self.r_inc),
                p(self.succ), p(self.gain), p(self.inner), p(self.iteration), p(self.outer_done), p(self.adv), 1e-4,
-               500, 1000, L.stream_ptr())                                                  # :159-202
+               500, 1000)                                                                  # :159-202
         with torch.cuda.device(self.dev):
             if plant is not None:
                 L.check(lib.ipoc_plant_attempt_finish_f64(plant["id"], N, B, plant["Ts"], plant["bound"],
                                                           p(plants._bp_tensor(self.bp, self.dev)), p(self.tx), p(self.tu),
-                                                          p(self.new_cost), p(self.traj_feas), *fin))
+                                                          p(self.new_cost), p(self.traj_feas), *fin,
+                                                          p(self._cost_ws[1][0]), self._cost_ws[1][1], L.stream_ptr()))
             else:
                 new_cost, traj_feas = noc.eval_trial(self.ocp, self.tx, self.tu, self.bp)  # :159-163
-                L.check(lib.ipoc_attempt_finish_f64(B, fin[0], p(new_cost.contiguous()), p(traj_feas), *fin[1:]))
+                L.check(lib.ipoc_attempt_finish_f64(B, fin[0], p(new_cost.contiguous()), p(traj_feas), *fin[1:],
+                                                    L.stream_ptr()))
 
     def _reset(self, x, u, bp):
         self.x.copy_(x.reshape(self.x.shape))

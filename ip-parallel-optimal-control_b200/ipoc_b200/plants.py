@@ -127,7 +127,26 @@ def hamiltonian(plant, states, controls, lam, bp, fresh=None, out=None):
     return out if batched else tuple(t[0] for t in out)
 
 
-def cost(plant, states, controls, bp, fresh=None, out=None):
+_cost_ws = {}
+
+
+def cost_scratch(N, B, dev, private=False):
+    """(tensor or None, bytes) — zero-filled scratch for the grid form of the cost kernel (long horizons, small
+    batches; ipoc_plant_cost_workspace_bytes).  Shared per (device, stream) unless `private` (graph captures)."""
+    nbytes = int(L.lib().ipoc_plant_cost_workspace_bytes(N, B))
+    if nbytes == 0:
+        return None, 0
+    if private:
+        return torch.zeros(nbytes, dtype=torch.uint8, device=dev), nbytes
+    dev = torch.device(dev)
+    key = (dev.index or 0, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _cost_ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _cost_ws[key] = torch.zeros(2 * nbytes, dtype=torch.uint8, device=dev)
+    return buf, buf.numel()
+
+
+def cost(plant, states, controls, bp, fresh=None, out=None, scratch=None):
     """-> (total_cost (B,), feasible (B,) int32) of trajectories: final cost + sum of stage costs (log barrier
     included; NaN where infeasible, as in the reference) and all(constraints <= 0)."""
     x, u = L.dev_f64(states), L.dev_f64(controls)
@@ -141,9 +160,11 @@ def cost(plant, states, controls, bp, fresh=None, out=None):
         total = torch.empty(B, dtype=torch.float64, device=dev)
         feas = torch.empty(B, dtype=torch.int32, device=dev)
     bpt = _bp_tensor(bp, dev)
+    ws, nbytes = scratch if scratch is not None else cost_scratch(N, B, dev)
     with torch.cuda.device(dev):
         L.check(L.lib().ipoc_plant_cost_f64(plant["id"], N, B, plant["Ts"], plant["bound"], L.ptr(bpt), L.ptr(x),
-                                            L.ptr(u), L.ptr(total), L.ptr(feas), L.ptr(fresh), L.stream_ptr()))
+                                            L.ptr(u), L.ptr(total), L.ptr(feas), L.ptr(fresh), L.ptr(ws), nbytes,
+                                            L.stream_ptr()))
     return total, feas
 
 

@@ -1013,3 +1013,38 @@ def test_plant_parallel_rollout_falls_back_on_divergence():
     u = T(np.full((N, 1), 1e300))
     x, it = plants.rollout_parallel(plant, u, problems.cartpole_x0(device="cuda"))
     assert it == -1 and tuple(x.shape) == (N + 1, 4)       # the serial kernel's (non-finite) result, no exception
+
+
+@pytest.mark.parametrize("name,N,B", [("cartpole", 100000, 1), ("cartpole", 20000, 3), ("pendulum", 1000000, 1),
+                                      ("cartpole", 9000, 2), ("cartpole", 3000, 1), ("pendulum", 700, 40)])
+def test_plant_cost_forms_agree(name, N, B):
+    """total_cost / feasibility of the built-in plants: single CTA, thread-block cluster (distributed shared memory)
+    and grid form (caller scratch, last arriver folds) against the host framework evaluating the same total_cost, incl. an
+    infeasible member, and twice in a row (the arrival counters must be back at zero)."""
+    from ipoc_b200 import plants, problems, _lib
+    Ts = 1.0 / N
+    ocp = (problems.make_cartpole if name == "cartpole" else problems.make_pendulum)(Ts)
+    plant = plants.plant_of(ocp)
+    rng = np.random.default_rng(N + B)
+    nx = 4 if name == "cartpole" else 2
+    x = rng.standard_normal((B, N + 1, nx))
+    u = 0.3 * plant["bound"] * rng.uniform(-1, 1, (B, N, 1))
+    if B > 1:
+        u[1, N // 2, 0] = 1.5 * plant["bound"]            # infeasible member: NaN cost, feasible = 0
+    bp = 0.02
+    xt, ut = T(x), T(u)
+    want = np.array([float(ocp.total_cost(xt[b], ut[b], bp)) for b in range(B)])
+    nbytes = int(_lib.lib().ipoc_plant_cost_workspace_bytes(N, B))
+    assert (nbytes > 0) == (B < 32 and N > 8192)
+    forms = [None] if nbytes == 0 else [None, (None, 0)]      # default (scratch if the shape uses it) / cluster form
+    for scratch in forms:
+        for rep in range(2):
+            tot, feas = plants.cost(plant, xt, ut, bp, scratch=scratch)
+            tot, feas = N_(tot), N_(feas)
+            for b in range(B):
+                bad = B > 1 and b == 1
+                assert bool(feas[b]) == (not bad)
+                if bad:
+                    assert np.isnan(tot[b]) and np.isnan(want[b])
+                else:
+                    assert abs(tot[b] - want[b]) <= 1e-11 * abs(want[b]), (scratch, rep, b, tot[b], want[b])
