@@ -319,16 +319,26 @@ static __global__ void k_attempt_begin(int batch, const uint8_t* __restrict__ do
     reg[b] = rp[b] * cu_norm[b];
 }
 
-static __global__ void k_trial_point(long long nxs, long long nus, const double* __restrict__ x,
+// mask (may be NULL): int32 per problem, members with 0 keep their tx / tu (per_x, per_u = doubles per problem)
+static __global__ void k_trial_point(long long nxs, long long nus, long long per_x, long long per_u,
+                                     const int32_t* __restrict__ mask, const double* __restrict__ x,
                                      const double* __restrict__ dx, const double* __restrict__ u,
                                      const double* __restrict__ du, double* __restrict__ tx, double* __restrict__ tu) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nxs) {
-        tx[i] = x[i] + dx[i];
+        if (mask == nullptr || mask[i / per_x] != 0) tx[i] = x[i] + dx[i];
     } else if (i < nxs + nus) {
         const long long j = i - nxs;
-        tu[j] = u[j] + du[j];
+        if (mask == nullptr || mask[j / per_u] != 0) tu[j] = u[j] + du[j];
     }
+}
+static int trial_point_masked(int N, int nx, int nu, int batch, const int32_t* mask, const double* x, const double* dx,
+                              const double* u, const double* du, double* tx, double* tu, cudaStream_t st_) {
+    const long long per_x = (long long)(N + 1) * nx, per_u = (long long)N * nu;
+    const long long nxs = batch * per_x, nus = batch * per_u;
+    k_trial_point<<<(unsigned)((nxs + nus + 255) / 256), 256, 0, st_>>>(nxs, nus, per_x, per_u, mask, x, dx, u, du, tx, tu);
+    IPOC_API_LAUNCH_CHECK(st_);
+    return IPOC_OK;
 }
 
 constexpr int kCommitThreads = 256;
@@ -576,11 +586,7 @@ int ipoc_attempt_begin_f64(int batch, const uint8_t* done, const double* rp, con
 int ipoc_trial_point_f64(int N, int nx, int nu, int batch, const double* x, const double* dx, const double* u,
                          const double* du, double* tx, double* tu, ipoc_stream_t stream) {
     CHECK_ARGS(N >= 1 && nx >= 1 && nu >= 1 && batch >= 1 && x && dx && u && du && tx && tu);
-    cudaStream_t st_ = (cudaStream_t)stream;
-    const long long nxs = (long long)batch * (N + 1) * nx, nus = (long long)batch * N * nu;
-    k_trial_point<<<(unsigned)((nxs + nus + 255) / 256), 256, 0, st_>>>(nxs, nus, x, dx, u, du, tx, tu);
-    IPOC_API_LAUNCH_CHECK(st_);
-    return IPOC_OK;
+    return trial_point_masked(N, nx, nu, batch, nullptr, x, dx, u, du, tx, tu, (cudaStream_t)stream);
 }
 
 int ipoc_attempt_commit_f64(int N, int nx, int nu, int batch, const int32_t* active, const int32_t* success,
@@ -750,8 +756,8 @@ int ipoc_newton_attempt_f64(int N, int nx, int nu, int nc, int batch, const doub
     if (hu != nullptr && !(xt.handled & IPOC_X_HU))
         if (int r2 = ipoc_reductions_f64(N, nu, 1, batch, ru, nullptr, nullptr, hu, nullptr, nullptr, nullptr, nullptr, rws,
                                          rbytes, stream)) return r2;
-    if (tx != nullptr && !(xt.handled & IPOC_X_TRIAL))
-        if (int r2 = ipoc_trial_point_f64(N, nx, nu, batch, x, dx, u, du, tx, tu, stream)) return r2;
+    if (tx != nullptr && !(xt.handled & IPOC_X_TRIAL))   // big problems: one coalesced pass beats the leaf kernel's per-lane rows
+        if (int r2 = trial_point_masked(N, nx, nu, batch, active, x, dx, u, du, tx, tu, (cudaStream_t)stream)) return r2;
     if (cons != nullptr && !(xt.handled & IPOC_X_CONS))
         if (int r2 = ipoc_reductions_f64(N, nu, nc, batch, nullptr, nullptr, cons, nullptr, nullptr, traj_feasible, nullptr,
                                          nullptr, rws, rbytes, stream)) return r2;
