@@ -373,13 +373,17 @@ int ipoc_plant_rollout_f64(int plant, int N, int batch, double Ts, const double*
 int ipoc_plant_rollout_lin_f64(int plant, int N, int batch, double Ts, const double* x, const double* u,
                                double* F, double* c, double* fv, double* stats, ipoc_stream_t stream);
 /* ipoc_plant_cost_f64 of the trial point (tx, tu) followed, in the same launch, by ipoc_attempt_finish_f64 with
- * the cost / feasibility just computed (members with active == 0 are skipped altogether). */
+ * the cost / feasibility just computed (members with active == 0 are skipped altogether).  cost_carry / need_cost
+ * (both may be NULL): when a member's step is taken its trial cost is also stored to cost_carry[b] — it IS the cost of
+ * the next iterate, bit for bit — and need_cost[b] is cleared for every member, so a loop that evaluates
+ * ipoc_plant_cost_f64(x, u, fresh = need_cost) pays that evaluation only after need_cost was set by whoever loaded
+ * a new iterate (start of a barrier stage). */
 int ipoc_plant_attempt_finish_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
                                   const double* tx, const double* tu, double* new_cost, int32_t* traj_feasible,
                                   const double* cost, const double* pred, const int32_t* bwd_feasible, const double* hu,
                                   int32_t* active, double* rp, double* r_inc, int32_t* success, double* gain_ratio,
                                   int64_t* inner, int64_t* iteration, uint8_t* outer_done, int32_t* advanced,
-                                  double hu_tol, int max_attempts, int max_iterations, void* ws, size_t ws_bytes, ipoc_stream_t stream);
+                                  double hu_tol, int max_attempts, int max_iterations, double* cost_carry, int32_t* need_cost, void* ws, size_t ws_bytes, ipoc_stream_t stream);
 
 /* Number of kernels the library has launched since load (for launch accounting in bench.py). */
 unsigned long long ipoc_launch_count(void);

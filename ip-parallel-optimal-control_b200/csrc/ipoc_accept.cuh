@@ -51,8 +51,15 @@ struct FinishIO {
     int32_t* advanced;
     double hu_tol;
     int max_attempts, max_iterations;
+    // Optional: when the step is taken, the trial point BECOMES the iterate, so its total cost IS the next
+    // iteration's `cost` (:142) — same kernel, same data, same summation order, hence the same bits.  cost_carry
+    // (may alias acc.cost) receives it; need_cost (per member) is cleared by every attempt and set by whoever loads
+    // a new iterate, so the loop's cost evaluation runs once per stage instead of once per iteration.
+    double* cost_carry;
+    int32_t* need_cost;
 };
 __device__ __forceinline__ void attempt_finish_rule(const FinishIO& f, int b, double new_cost, int traj_ok) {
+    if (f.need_cost != nullptr) f.need_cost[b] = 0;
     if (!f.active[b]) {
         f.advanced[b] = 0;
         return;
@@ -64,6 +71,7 @@ __device__ __forceinline__ void attempt_finish_rule(const FinishIO& f, int b, do
         f.iteration[b] = it;
         f.inner[b] = 0;
         f.advanced[b] = 1;
+        if (f.cost_carry != nullptr) f.cost_carry[b] = new_cost;
         if (f.hu[b] < f.hu_tol || it > f.max_iterations) {
             f.outer_done[b] = 1;
             f.active[b] = 0;

@@ -313,7 +313,10 @@ k_plant_cost(PlantParams pp, const double* __restrict__ bp_ptr, int N, const dou
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (fresh != nullptr && fresh[b] == 0) return;    // uniform over the cluster
     if (finish && !fin.active[b]) {   // frozen member of a device-resident loop: nothing to evaluate
-        if (t == 0 && rank == 0) fin.advanced[b] = 0;
+        if (t == 0 && rank == 0) {
+            fin.advanced[b] = 0;
+            if (fin.need_cost != nullptr) fin.need_cost[b] = 0;
+        }
         return;
     }
     const double bp = *bp_ptr;
@@ -657,15 +660,16 @@ int ipoc_plant_attempt_finish_f64(int plant, int N, int batch, double Ts, double
                                   const double* cost, const double* pred, const int32_t* bwd_feasible, const double* hu,
                                   int32_t* active, double* rp, double* r_inc, int32_t* success, double* gain_ratio,
                                   int64_t* inner, int64_t* iteration, uint8_t* outer_done, int32_t* advanced,
-                                  double hu_tol, int max_attempts, int max_iterations, void* ws, size_t ws_bytes,
-                                  ipoc_stream_t stream) {
+                                  double hu_tol, int max_attempts, int max_iterations, double* cost_carry,
+                                  int32_t* need_cost, void* ws, size_t ws_bytes, ipoc_stream_t stream) {
     if (N < 1 || batch < 1 || !bp || !tx || !tu || !new_cost || !traj_feasible || !cost || !pred || !bwd_feasible || !hu ||
         !active || !rp || !r_inc || !success || !inner || !iteration || !outer_done || !advanced)
         return IPOC_EINVAL;
     const PlantParams pp{Ts, bound};
     cudaStream_t st = (cudaStream_t)stream;
     const FinishIO fin{AcceptIO{cost, pred, bwd_feasible, rp, r_inc, success, gain_ratio}, hu, active, (long long*)inner,
-                       (long long*)iteration, outer_done, advanced, hu_tol, max_attempts, max_iterations};
+                       (long long*)iteration, outer_done, advanced, hu_tol, max_attempts, max_iterations, cost_carry,
+                       need_cost};
     if (plant == IPOC_PLANT_PENDULUM)
         return cost_finish_impl<Pendulum>(pp, bp, N, batch, tx, tu, new_cost, traj_feasible, fin, ws, ws_bytes, st);
     if (plant == IPOC_PLANT_CARTPOLE)

@@ -39,7 +39,7 @@ _SIGS = {
     "ipoc_attempt_finish_f64": (_I, [_I] + [_P] * 15 + [ctypes.c_double, _I, _I, _P]),
     "ipoc_masked_copy_f64": (_I, [_I] * 4 + [_P] * 5 + [_P]),
     "ipoc_plant_attempt_finish_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 18
-                                      + [ctypes.c_double, _I, _I, _P, ctypes.c_size_t, _P]),
+                                      + [ctypes.c_double, _I, _I, _P, _P, _P, ctypes.c_size_t, _P]),
     "ipoc_lqr_params_f64": (_I, [_I] * 4 + [_P] * 13 + [_P]),
     "ipoc_newton_bwd_reduce_f64": (_I, [_I] * 3 + [_P] * 8 + [_P, _SZ, _P]),
     "ipoc_newton_bwd_apply_f64": (_I, [_I] * 5 + [_P] * 14 + [_P, _SZ, _P]),

@@ -230,6 +230,7 @@ class _DeviceLadder:
         lp.outer_done.fill_(True)
         lp.outer_done[:k] = False
         lp.adv.fill_(1)
+        lp.need_cost.fill_(1)
         lp.buf.hu.fill_(1.0)
 
     def run_stage(self, x, u, bp):

@@ -169,6 +169,7 @@ class DeviceLoopNewton:
         self.buf = noc.AttemptBuffers(B, N, nx, nu, self.dev)
         self._eval = {}                            # iterate-evaluation buffers, kept across replays (see _step)
         self._cost_ws = None
+        self.need_cost = torch.ones(B, dtype=torch.int32, device=self.dev)   # see _step: cost is carried between iterations
         self.depth = 3 if N * B <= 20000 else 1    # replays kept in flight (a replay is > 1 ms for long horizons)
         self.ring = 8
         self.flags = torch.zeros(self.ring, B, dtype=torch.bool).pin_memory()
@@ -191,7 +192,10 @@ class DeviceLoopNewton:
             if self._cost_ws is None:        # private zero-filled scratch of the two cost evaluations of an attempt
                 self._cost_ws = (plants.cost_scratch(N, B, self.dev, private=True),
                                  plants.cost_scratch(N, B, self.dev, private=True))
-            ev["cost"] = plants.cost(plant, self.x, self.u, self.bp, fresh=fr, out=ev.get("cost"),
+            # the cost of an iterate that came from an accepted trial point was already computed as that attempt's
+            # new_cost (same kernel, same data): the finish kernel carries it over and clears `need_cost`, which is
+            # set again only where a new iterate is loaded (_reset, batched._load)
+            ev["cost"] = plants.cost(plant, self.x, self.u, self.bp, fresh=self.need_cost, out=ev.get("cost"),
                                      scratch=self._cost_ws[0])
             fx, fu, cx, cu, lamT = ev["lin"]
             cost = ev["cost"][0]
@@ -211,7 +215,7 @@ class DeviceLoopNewton:
             if plant is not None:
                 L.check(lib.ipoc_plant_attempt_finish_f64(plant["id"], N, B, plant["Ts"], plant["bound"],
                                                           p(plants._bp_tensor(self.bp, self.dev)), p(self.tx), p(self.tu),
-                                                          p(self.new_cost), p(self.traj_feas), *fin,
+                                                          p(self.new_cost), p(self.traj_feas), *fin, p(cost), p(self.need_cost),
                                                           p(self._cost_ws[1][0]), self._cost_ws[1][1], L.stream_ptr()))
             else:
                 new_cost, traj_feas = noc.eval_trial(self.ocp, self.tx, self.tu, self.bp)  # :159-163
@@ -229,6 +233,7 @@ class DeviceLoopNewton:
         self.buf.hu.fill_(1.0)
         self.act.fill_(1)
         self.adv.fill_(1)      # "take the step tx -> x" is a no-op (tx == x) and marks every iterate as new
+        self.need_cost.fill_(1)
         self.inner.zero_()
         self.iteration.zero_()
         self.outer_done.zero_()
