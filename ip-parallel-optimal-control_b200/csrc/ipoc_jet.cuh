@@ -125,18 +125,53 @@ __device__ __forceinline__ Jet<NV> jwrap(const Jet<NV>& a) {
     r.v = a.v - two_pi * floor(a.v / two_pi);
     return r;
 }
+// Operations with a plain scalar.  A scalar is a jet whose derivatives are structurally zero; writing the products
+// out (instead of promoting the scalar to a jet) drops the 0 * x terms the compiler must keep under IEEE rules —
+// about 3/4 of the arithmetic of a jet product — and gives the same bits for finite operands (x + 0 * y == x).
 template <int NV>
-__device__ __forceinline__ Jet<NV> operator*(double c, const Jet<NV>& a) { return Jet<NV>(c) * a; }
+__device__ __forceinline__ Jet<NV> operator*(double c, const Jet<NV>& a) {
+    Jet<NV> r;
+    r.v = c * a.v;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r.g[i] = c * a.g[i];
+#pragma unroll
+    for (int i = 0; i < Jet<NV>::NH; ++i) r.h[i] = c * a.h[i];
+    return r;
+}
 template <int NV>
-__device__ __forceinline__ Jet<NV> operator*(const Jet<NV>& a, double c) { return a * Jet<NV>(c); }
+__device__ __forceinline__ Jet<NV> operator*(const Jet<NV>& a, double c) {
+    Jet<NV> r;
+    r.v = a.v * c;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r.g[i] = a.g[i] * c;
+#pragma unroll
+    for (int i = 0; i < Jet<NV>::NH; ++i) r.h[i] = a.h[i] * c;
+    return r;
+}
 template <int NV>
-__device__ __forceinline__ Jet<NV> operator+(const Jet<NV>& a, double c) { return a + Jet<NV>(c); }
+__device__ __forceinline__ Jet<NV> operator+(const Jet<NV>& a, double c) {
+    Jet<NV> r = a;
+    r.v = a.v + c;
+    return r;
+}
 template <int NV>
-__device__ __forceinline__ Jet<NV> operator+(double c, const Jet<NV>& a) { return Jet<NV>(c) + a; }
+__device__ __forceinline__ Jet<NV> operator+(double c, const Jet<NV>& a) {
+    Jet<NV> r = a;
+    r.v = c + a.v;
+    return r;
+}
 template <int NV>
-__device__ __forceinline__ Jet<NV> operator-(const Jet<NV>& a, double c) { return a - Jet<NV>(c); }
+__device__ __forceinline__ Jet<NV> operator-(const Jet<NV>& a, double c) {
+    Jet<NV> r = a;
+    r.v = a.v - c;
+    return r;
+}
 template <int NV>
-__device__ __forceinline__ Jet<NV> operator-(double c, const Jet<NV>& a) { return Jet<NV>(c) - a; }
+__device__ __forceinline__ Jet<NV> operator-(double c, const Jet<NV>& a) {
+    Jet<NV> r = -a;
+    r.v = c - a.v;
+    return r;
+}
 template <int NV>
 __device__ __forceinline__ Jet<NV> operator/(const Jet<NV>& a, double c) {   // true division, like the host framework
     Jet<NV> r;
