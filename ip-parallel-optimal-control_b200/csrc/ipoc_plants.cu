@@ -478,46 +478,66 @@ k_plant_rollout_lin(PlantParams pp, int N, int batch, const double* __restrict__
     constexpr int NX = P::NX, NU = P::NU;
     using J = Jet<NX>;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)batch * N) return;
-    const int b = (int)(g / N), k = (int)(g % N);
-    const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
-    double xv[NX], uv[NU], ov[NX];
-    J x[NX], u[NU], o[NX];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-        xv[i] = xp[i];
-        x[i] = J::var(xv[i], i);
-    }
-#pragma unroll
-    for (int a = 0; a < NU; ++a) {
-        uv[a] = U[(size_t)g * NU + a];
-        u[a] = J(uv[a]);
-    }
-    P::ode(x, u, o);
-    P::ode(xv, uv, ov);
-    double Fv[NX * NX], cv[NX], fvv[NX];
+    const bool valid = g < (long long)batch * N;
+    const int b = valid ? (int)(g / N) : -1, k = valid ? (int)(g % N) : 0;
     double defect = 0.0, amax = 0.0;
-#pragma unroll
-    for (int r = 0; r < NX; ++r) {
-        fvv[r] = xv[r] + pp.Ts * ov[r];   // exactly the serial rollout's update
-        double acc = fvv[r];
+    if (valid) {
+        const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
+        double xv[NX], uv[NU], ov[NX];
+        J x[NX], u[NU], o[NX];
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-            const double fri = ((i == r) ? 1.0 : 0.0) + pp.Ts * o[r].g[i];
-            Fv[r * NX + i] = fri;
-            acc -= fri * xv[i];
+            xv[i] = xp[i];
+            x[i] = J::var(xv[i], i);
         }
-        cv[r] = acc;
-        const double dd = fabs(xp[NX + r] - fvv[r]);
-        defect = (dd != dd || defect != defect) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(defect, dd);
-        amax = fmax(amax, fabs(fvv[r]));
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+            uv[a] = U[(size_t)g * NU + a];
+            u[a] = J(uv[a]);
+        }
+        P::ode(x, u, o);
+        P::ode(xv, uv, ov);
+        double Fv[NX * NX], cv[NX], fvv[NX];
+#pragma unroll
+        for (int r = 0; r < NX; ++r) {
+            fvv[r] = xv[r] + pp.Ts * ov[r];   // exactly the serial rollout's update
+            double acc = fvv[r];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                const double fri = ((i == r) ? 1.0 : 0.0) + pp.Ts * o[r].g[i];
+                Fv[r * NX + i] = fri;
+                acc -= fri * xv[i];
+            }
+            cv[r] = acc;
+            const double dd = fabs(xp[NX + r] - fvv[r]);
+            defect = (dd != dd || defect != defect) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(defect, dd);
+            amax = fmax(amax, fabs(fvv[r]));
+        }
+        store_row<NX * NX>(F + (size_t)g * NX * NX, Fv);
+        store_row<NX>(c + (size_t)g * NX, cv);
+        store_row<NX>(fv + (size_t)g * NX, fvv);
     }
-    store_row<NX * NX>(F + (size_t)g * NX * NX, Fv);
-    store_row<NX>(c + (size_t)g * NX, cv);
-    store_row<NX>(fv + (size_t)g * NX, fvv);
-    // non-negative doubles (and NaN above +inf) order like their bit patterns
-    atomicMax(stats + 2 * (size_t)b, (unsigned long long)__double_as_longlong(defect) & 0x7fffffffffffffffULL);
-    atomicMax(stats + 2 * (size_t)b + 1, (unsigned long long)__double_as_longlong(amax) & 0x7fffffffffffffffULL);
+    // Non-negative doubles (and NaN above +inf) order like their bit patterns.  One atomic pair per WARP when all its
+    // lanes belong to one problem (every thread hitting the same two words serialised 2e6 atomics into 1.3 ms at
+    // N = 1e6, profiles/r02_ncu_full_new_kernels_summary.txt).
+    unsigned long long db = (unsigned long long)__double_as_longlong(defect) & 0x7fffffffffffffffULL;
+    unsigned long long ab = (unsigned long long)__double_as_longlong(amax) & 0x7fffffffffffffffULL;
+    const int b0 = __shfl_sync(0xffffffffu, b, 0);
+    if (__all_sync(0xffffffffu, !valid || b == b0)) {
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) {
+            const unsigned long long d2 = __shfl_xor_sync(0xffffffffu, db, sh), a2 = __shfl_xor_sync(0xffffffffu, ab, sh);
+            db = d2 > db ? d2 : db;
+            ab = a2 > ab ? a2 : ab;
+        }
+        if ((threadIdx.x & 31) == 0 && b0 >= 0) {
+            atomicMax(stats + 2 * (size_t)b0, db);
+            atomicMax(stats + 2 * (size_t)b0 + 1, ab);
+        }
+    } else if (valid) {
+        atomicMax(stats + 2 * (size_t)b, db);
+        atomicMax(stats + 2 * (size_t)b + 1, ab);
+    }
 }
 
 #define PLANT_CHECK(st)                                              \
