@@ -1048,3 +1048,19 @@ def test_plant_cost_forms_agree(name, N, B):
                     assert np.isnan(tot[b]) and np.isnan(want[b])
                 else:
                     assert abs(tot[b] - want[b]) <= 1e-11 * abs(want[b]), (scratch, rep, b, tot[b], want[b])
+
+
+@pytest.mark.parametrize("name,N", [("cartpole", 3000), ("pendulum", 6000)])
+def test_mid_horizon_solve_device_loop_equals_host_steered(name, N):
+    """Horizons between the fixture sizes: the device-resident loop here launches the plant cost kernel as a
+    thread-block cluster INSIDE a captured graph (1024 < N <= 8192) and starts every stage with the parallel plant
+    rollout (N >= 2048); the host-steered graphs of the same solver (one host read per attempt, plant kernels,
+    shared cost scratch) must give the same iterate and Newton iteration count."""
+    from ipoc_b200 import noc, problems
+    ocp = (problems.make_cartpole if name == "cartpole" else problems.make_pendulum)(1.0 / N)
+    x0 = (problems.cartpole_x0 if name == "cartpole" else problems.pendulum_x0)(device="cuda")
+    u0 = T(0.1 * np.random.default_rng(1).standard_normal((N, 1)))
+    ud, itd = noc.par_interior_point_optimal_control(ocp, u0, x0)
+    uh, ith = noc.par_interior_point_optimal_control(ocp, u0, x0, use_graphs="host")
+    assert itd == ith and itd > 20
+    assert relerr(N_(ud), N_(uh)) < 1e-9
