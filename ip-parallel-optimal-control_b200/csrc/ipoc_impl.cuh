@@ -563,8 +563,11 @@ k_ric_top_coop(const double* __restrict__ agg0, size_t a0stride, int nW, int bat
         const double* inc = s_buf + coop_scan<NX>(s_buf, slot, g, gsize) * (ESZ * 32);
         if (slot < gsize)
             for (int c = g; c < ESZ; c += GS) h.incl1[(size_t)c * h.s1 + (size_t)b * nW + g0 + slot] = inc[c * 32 + slot];
-        if (slot == gsize - 1)
+        if (slot == gsize - 1) {
             for (int c = g; c < ESZ; c += GS) h.agg2[(size_t)c * h.s2 + (size_t)b * h.ngroups + grp] = inc[c * 32 + slot];
+            if (h.total != nullptr && h.ngroups == 1)   // a single group: its total is the sequence's
+                for (int c = g; c < ESZ; c += GS) h.total[(size_t)c * batch + b] = inc[c * 32 + slot];
+        }
     }
     const size_t gb = (size_t)b * h.ngroups;
     if (h.ngroups > 1) {
@@ -581,7 +584,7 @@ k_ric_top_coop(const double* __restrict__ agg0, size_t a0stride, int nW, int bat
     }
     if (t < 32) side_finish(sj, b, t);
     if (h.ngroups == 1) {
-        if (t == 0) {
+        if (t == 0 && h.seed != nullptr) {
             Val v;
             soa_load_cg(v, h.seed, (size_t)batch, (size_t)b);
             soa_store(v, h.val2, h.s2, gb);
@@ -594,6 +597,9 @@ k_ric_top_coop(const double* __restrict__ agg0, size_t a0stride, int nW, int bat
     const double* inc = s_buf + coop_scan<NX>(s_buf, slot, g, h.ngroups) * (ESZ * 32);
     if (h.incl2 != nullptr && slot < h.ngroups)
         for (int c = g; c < ESZ; c += GS) h.incl2[(size_t)c * h.s2 + gb + slot] = inc[c * 32 + slot];
+    if (h.total != nullptr && slot == h.ngroups - 1)   // composition of the whole sequence (time-sharded reduce phase)
+        for (int c = g; c < ESZ; c += GS) h.total[(size_t)c * batch + b] = inc[c * 32 + slot];
+    if (h.seed == nullptr) return;                     // reduce only: the values come with the apply phase
     if (g == 0 && slot < h.ngroups) {   // value entering group `slot`: the seed through the groups before it
         Val v;
         soa_load_cg(v, h.seed, (size_t)batch, (size_t)b);
@@ -2261,15 +2267,29 @@ static int newton_bwd_reduce_impl(int N, const double* fx, const double* fu, con
     carve_newton<NX>(bp, p, w);
     if (bp.off > ws_bytes) return IPOC_EWORKSPACE;
     const bool split_hier = p.hier && p.ngroups <= 32;
+    // from two groups on the levels of the segment run in the lane-cooperative level kernel (reduce-only form: the
+    // group scans on separate SMs, the last CTA composes the segment total) instead of inside the up-sweep
+    const bool coop = split_hier && NX > 1 && p.gw == 32 && p.ngroups >= 2 && g_hier.enabled != 2 && g_hier.enabled != 3;
     Hier h{};
     if (split_hier) h = make_hier<RicOp<NX>>(p, w.ric, nullptr, carry_out);   // batch = 1: SoA == AoS
+    const Hier hup = coop ? Hier{} : h;
     const SeedJob nosj{nullptr, 0, nullptr, 0, nullptr, nullptr};
     if (g_literal_lqt) {
         NewtonLoader<NX, NU, true> ld{fx, fu, ru, Q, R, M, reg, nullptr};
-        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st, nosj, h, SideJobs{}, nullptr)) return rc;
+        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st, nosj, hup, SideJobs{}, nullptr)) return rc;
     } else {
         NewtonLoader<NX, NU, false> ld{fx, fu, ru, Q, R, M, reg, nullptr};
-        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st, nosj, h, SideJobs{}, nullptr)) return rc;
+        if (int rc = run_bwd_up<NX, NU>(p, w, ld, st, nosj, hup, SideJobs{}, nullptr)) return rc;
+    }
+    if (coop) {
+        if constexpr (NX > 1) {
+            constexpr size_t smem = 2 * sizeof(RicElem<NX>) * 32;
+            if (int rc = set_smem_plain(k_ric_top_coop<NX>, smem)) return rc;
+            k_ric_top_coop<NX><<<p.ngroups, 32 * coop_gs<NX>(), smem, st>>>(w.ric.agg[0], (size_t)p.g.nW, p.g.nW, 1, h,
+                                                                            SideJobs{});
+            IPOC_LAUNCH_CHECK_N("k_ric_top_coop", st);
+        }
+        return IPOC_OK;
     }
     if (split_hier) return IPOC_OK;
     if (int rc = run_levels<RicOp<NX>>(p, w.ric, true, true, st)) return rc;
