@@ -355,6 +355,12 @@ int ipoc_plant_derivatives_f64(int plant, int N, int batch, double Ts, double bo
 int ipoc_plant_linearize_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
                              const double* x, const double* u, double* fx, double* fu, double* cx, double* cu,
                              double* lamT, const int32_t* fresh, ipoc_stream_t stream);
+/* ipoc_masked_copy_f64(mask = fresh: x <- tx, u <- tu) and ipoc_plant_linearize_f64 in ONE launch: members with
+ * fresh != 0 take their iterate from (tx, tu) — written to x (batch,N+1,nx) and u (batch,N,nu) — and are linearised
+ * there; the others are left alone, as in ipoc_plant_linearize_f64.  (Device-resident loops: fresh = `advanced`.) */
+int ipoc_plant_take_linearize_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
+                                  const double* tx, const double* tu, double* x, double* u, double* fx, double* fu,
+                                  double* cx, double* cu, double* lamT, const int32_t* fresh, ipoc_stream_t stream);
 int ipoc_plant_hamiltonian_f64(int plant, int N, int batch, double Ts, double bound, const double* bp,
                                const double* x, const double* u, const double* lam,
                                double* ru, double* Q, double* R, double* M, const int32_t* fresh,

@@ -165,7 +165,11 @@ __global__ void __launch_bounds__(128)
 k_plant_linearize(PlantParams pp, const double* __restrict__ bp_ptr, int N, int batch,
                   const double* __restrict__ X, const double* __restrict__ U, double* __restrict__ fx,
                   double* __restrict__ fu, double* __restrict__ cx, double* __restrict__ cu,
-                  double* __restrict__ lamT, const int32_t* __restrict__ fresh) {
+                  double* __restrict__ lamT, const int32_t* __restrict__ fresh, const double* __restrict__ TX,
+                  const double* __restrict__ TU, double* Xw, double* Uw) {
+    // TX / TU (may be NULL): the iterate is first TAKEN from there — x <- tx, u <- tu for the members this call
+    // evaluates (fresh != 0), written through Xw / Uw (the same arrays as X / U) — i.e. the masked copy that takes an
+    // accepted step (ref :184) rides along with the first kernel that reads the new iterate.
     constexpr int NX = P::NX, NU = P::NU, NV = NX + NU;
     using J = Jet<NV>;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,12 +177,23 @@ k_plant_linearize(PlantParams pp, const double* __restrict__ bp_ptr, int N, int 
     const int b = (int)(g / N), k = (int)(g % N);
     if (fresh != nullptr && fresh[b] == 0) return;   // iterate unchanged since the last evaluation: outputs still valid
     const double bp = *bp_ptr;
-    const double* xp = X + ((size_t)b * (N + 1) + k) * NX;
+    const size_t xrow = ((size_t)b * (N + 1) + k) * NX;
+    const double* xp = (TX != nullptr ? TX : X) + xrow;
+    const double* up = (TU != nullptr ? TU : U) + (size_t)g * NU;
     J x[NX], u[NU];
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = J::var(xp[i], i);
 #pragma unroll
-    for (int a = 0; a < NU; ++a) u[a] = J::var(U[(size_t)g * NU + a], NX + a);
+    for (int a = 0; a < NU; ++a) u[a] = J::var(up[a], NX + a);
+    if (TX != nullptr) {
+        double xv[NX], uv[NU];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xv[i] = x[i].v;
+#pragma unroll
+        for (int a = 0; a < NU; ++a) uv[a] = u[a].v;
+        store_row<NX>(Xw + xrow, xv);
+        store_row<NU>(Uw + (size_t)g * NU, uv);
+    }
     J o[NX];
     P::ode(x, u, o);
     double fxv[NX * NX], fuv[NX * NU], cxv[NX], cuv[NU];
@@ -199,8 +214,14 @@ k_plant_linearize(PlantParams pp, const double* __restrict__ bp_ptr, int N, int 
     store_row<NX * NU>(fu + (size_t)g * NX * NU, fuv);
     store_row<NX>(cx + (size_t)g * NX, cxv);
     store_row<NU>(cu + (size_t)g * NU, cuv);
+    if (k == N - 1 && TX != nullptr) {   // the terminal state travels with the last step's thread
+        double xv[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xv[i] = TX[xrow + NX + i];
+        store_row<NX>(Xw + xrow + NX, xv);
+    }
     if (k == N - 1 && lamT != nullptr) {
-        const double* xn = X + ((size_t)b * (N + 1) + N) * NX;
+        const double* xn = (TX != nullptr ? TX : X) + ((size_t)b * (N + 1) + N) * NX;
         J xe[NX];
 #pragma unroll
         for (int i = 0; i < NX; ++i) xe[i] = J::var(xn[i], i);
@@ -560,9 +581,10 @@ static int derivs_impl(PlantParams pp, const double* bp, int N, int batch, const
 template <class P>
 static int linearize_impl(PlantParams pp, const double* bp, int N, int batch, const double* X, const double* U,
                           double* fx, double* fu, double* cx, double* cu, double* lamT, const int32_t* fresh,
-                          cudaStream_t st) {
+                          const double* TX, const double* TU, double* Xw, double* Uw, cudaStream_t st) {
     const long long n = (long long)N * batch;
-    k_plant_linearize<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pp, bp, N, batch, X, U, fx, fu, cx, cu, lamT, fresh);
+    k_plant_linearize<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pp, bp, N, batch, X, U, fx, fu, cx, cu, lamT, fresh,
+                                                                    TX, TU, Xw, Uw);
     PLANT_CHECK(st);
     return IPOC_OK;
 }
@@ -642,8 +664,23 @@ int ipoc_plant_linearize_f64(int plant, int N, int batch, double Ts, double boun
     if (N < 1 || batch < 1 || !bp || !x || !u || !fx || !fu || !cx || !cu) return IPOC_EINVAL;
     const PlantParams pp{Ts, bound};
     cudaStream_t st = (cudaStream_t)stream;
-    if (plant == IPOC_PLANT_PENDULUM) return linearize_impl<Pendulum>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, fresh, st);
-    if (plant == IPOC_PLANT_CARTPOLE) return linearize_impl<Cartpole>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, fresh, st);
+    if (plant == IPOC_PLANT_PENDULUM)
+        return linearize_impl<Pendulum>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, fresh, nullptr, nullptr, nullptr, nullptr, st);
+    if (plant == IPOC_PLANT_CARTPOLE)
+        return linearize_impl<Cartpole>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, fresh, nullptr, nullptr, nullptr, nullptr, st);
+    return IPOC_EINVAL;
+}
+
+int ipoc_plant_take_linearize_f64(int plant, int N, int batch, double Ts, double bound, const double* bp, const double* tx,
+                                  const double* tu, double* x, double* u, double* fx, double* fu, double* cx, double* cu,
+                                  double* lamT, const int32_t* fresh, ipoc_stream_t stream) {
+    if (N < 1 || batch < 1 || !bp || !tx || !tu || !x || !u || !fx || !fu || !cx || !cu) return IPOC_EINVAL;
+    const PlantParams pp{Ts, bound};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plant == IPOC_PLANT_PENDULUM)
+        return linearize_impl<Pendulum>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, fresh, tx, tu, x, u, st);
+    if (plant == IPOC_PLANT_CARTPOLE)
+        return linearize_impl<Cartpole>(pp, bp, N, batch, x, u, fx, fu, cx, cu, lamT, fresh, tx, tu, x, u, st);
     return IPOC_EINVAL;
 }
 

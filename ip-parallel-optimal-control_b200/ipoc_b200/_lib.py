@@ -51,6 +51,7 @@ _SIGS = {
     "ipoc_plant_dims": (_I, [_I] + [ctypes.POINTER(ctypes.c_int)] * 3),
     "ipoc_plant_derivatives_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 14 + [_P]),
     "ipoc_plant_linearize_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 9 + [_P]),
+    "ipoc_plant_take_linearize_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 11 + [_P]),
     "ipoc_plant_hamiltonian_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 9 + [_P]),
     "ipoc_plant_cost_f64": (_I, [_I, _I, _I, ctypes.c_double, ctypes.c_double] + [_P] * 6 + [_P, ctypes.c_size_t, _P]),
     "ipoc_plant_cost_workspace_bytes": (ctypes.c_size_t, [_I, _I]),

@@ -180,15 +180,18 @@ class DeviceLoopNewton:
         from . import plants
         lib, p = L.lib(), L.ptr
         B, N, nx, nu = self.B, self.N, self.nx, self.nu
-        with torch.cuda.device(self.dev):
-            L.check(lib.ipoc_masked_copy_f64(N, nx, nu, B, p(self.adv), p(self.tx), p(self.tu), p(self.x), p(self.u),
-                                             L.stream_ptr()))                               # :184
         plant = plants.plant_of(self.ocp)
+        if plant is None:
+            with torch.cuda.device(self.dev):
+                L.check(lib.ipoc_masked_copy_f64(N, nx, nu, B, p(self.adv), p(self.tx), p(self.tu), p(self.x), p(self.u),
+                                                 L.stream_ptr()))                           # :184
         if plant is not None:                                                              # :142-149
             # `adv` doubles as the "iterate changed" flag: after a REJECTED attempt the iterate is the same, every
             # member-wise kernel below skips the member and its buffers keep the previous evaluation
             fr, ev = self.adv, self._eval
-            ev["lin"] = plants.linearize(plant, self.x, self.u, self.bp, fresh=fr, out=ev.get("lin"))
+            # the step of an accepted attempt (x <- tx, u <- tu where adv != 0, :184) is taken by the linearisation kernel
+            ev["lin"] = plants.linearize(plant, self.x, self.u, self.bp, fresh=fr, out=ev.get("lin"),
+                                         take=(self.tx, self.tu))
             if self._cost_ws is None:        # private zero-filled scratch of the two cost evaluations of an attempt
                 self._cost_ws = (plants.cost_scratch(N, B, self.dev, private=True),
                                  plants.cost_scratch(N, B, self.dev, private=True))

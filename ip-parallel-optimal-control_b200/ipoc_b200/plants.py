@@ -82,9 +82,11 @@ def _prep(states, controls):
     return x, u, batched
 
 
-def linearize(plant, states, controls, bp, fresh=None, out=None):
+def linearize(plant, states, controls, bp, fresh=None, out=None, take=None):
     """First-order pass (before the costate scan) -> fx, fu, cx, cu, lamT.  `fresh` (int32 per problem): members
-    whose flag is 0 are skipped and keep what `out` (the tuple returned by an earlier call) holds."""
+    whose flag is 0 are skipped and keep what `out` (the tuple returned by an earlier call) holds.  `take` =
+    (tx, tu): the evaluated members first take their iterate from there (states, controls are then written: the
+    masked copy of an accepted step in the same launch, ipoc_plant_take_linearize_f64)."""
     x, u, batched = _prep(states, controls)
     B, N = u.shape[0], u.shape[1]
     nx, nu, _ = _dims(plant)
@@ -96,9 +98,17 @@ def linearize(plant, states, controls, bp, fresh=None, out=None):
         cx, cu, lamT = torch.empty(B, N, nx, **o), torch.empty(B, N, nu, **o), torch.empty(B, nx, **o)
     bpt = _bp_tensor(bp, x.device)
     with torch.cuda.device(x.device):
-        L.check(L.lib().ipoc_plant_linearize_f64(plant["id"], N, B, plant["Ts"], plant["bound"], L.ptr(bpt), L.ptr(x),
-                                                 L.ptr(u), L.ptr(fx), L.ptr(fu), L.ptr(cx), L.ptr(cu), L.ptr(lamT),
-                                                 L.ptr(fresh), L.stream_ptr()))
+        if take is not None:
+            if x.data_ptr() != states.data_ptr() or u.data_ptr() != controls.data_ptr():
+                raise L.IpocError("linearize(take=...) writes states / controls in place: pass contiguous float64 CUDA tensors")
+            L.check(L.lib().ipoc_plant_take_linearize_f64(plant["id"], N, B, plant["Ts"], plant["bound"], L.ptr(bpt),
+                                                          L.ptr(take[0]), L.ptr(take[1]), L.ptr(x), L.ptr(u), L.ptr(fx),
+                                                          L.ptr(fu), L.ptr(cx), L.ptr(cu), L.ptr(lamT), L.ptr(fresh),
+                                                          L.stream_ptr()))
+        else:
+            L.check(L.lib().ipoc_plant_linearize_f64(plant["id"], N, B, plant["Ts"], plant["bound"], L.ptr(bpt), L.ptr(x),
+                                                     L.ptr(u), L.ptr(fx), L.ptr(fu), L.ptr(cx), L.ptr(cu), L.ptr(lamT),
+                                                     L.ptr(fresh), L.stream_ptr()))
     out = (fx, fu, cx, cu, lamT)
     return out if batched else tuple(t[0] for t in out)
 
