@@ -1638,7 +1638,10 @@ static Plan make_plan(int N, int batch, bool force_scan = false, int target_thre
             const long long t_lat = (long long)(sqrt((double)N) / 256.0 + 0.5) * 8;
             if (t > 4) t = ((t + 7) / 8) * 8;
             if (lat_heuristic && t < t_lat) t = t_lat;
-            T0 = (int)(t < 4 ? 4 : t);
+            // shortest chunk: 4 steps, 2 while the whole horizon then still fits ONE group of 32 warps (N <= 2048: no
+            // third level; measured N = 1e3: 75.8 us per pass with T0 = 2 against 81.9 with 4, r02_chunk_sweep.log)
+            const long long tmin = (N <= 2048) ? 2 : 4;
+            T0 = (int)(t < tmin ? tmin : t);
         }
     }
     if (T0 > N) T0 = N;
